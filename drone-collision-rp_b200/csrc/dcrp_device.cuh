@@ -1,0 +1,92 @@
+// dcrp_device.cuh -- device-side data layout of a scenario and a run.
+//
+// HBM layout (all engine-owned, built by dcrp_scenario_upload):
+//   tracks[n_tracks]            TrackDev: n_steps, takeoff_t, sample offset, target box
+//   ax, ay, az [sum n_steps]    fp64 SoA, tracks back to back  (exact / confirm kernels)
+//   trk32 [2 * sum n_steps]     fp32 screen copy, 32 B per sample, relative to the scenario
+//                               origin and negated, each value duplicated so that one
+//                               LDS.128 yields ready-made f32x2 operands:
+//                                 [2i]   = (-ax, -ax, -ay, -ay)
+//                                 [2i+1] = (-az, -az,  i ,  i )       (i as float)
+//   drones[n_drones]            x0, y0, sin(h0)*v, cos(h0)*v   (fp64; trig by the host's libm,
+//                               the same one the reference links, Drone.cpp:121-122)
+//   p1x, p1y [n_drones*t_max]   stage-1 path of every drone, sequentially accumulated fp64
+//   s1_first_hit [n_pairs]      first stage-1 index in collision (INT32_MAX if none)
+//   s1_prefmin  [n_pairs*t_max] prefix minimum of the stage-1 squared separation
+// Stage 1 does not depend on the draws except through t1st, so it is evaluated
+// once per (track, drone) and shared by all of that pair's trials.
+#pragma once
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "dcrp_math.cuh"
+
+namespace dcrp {
+
+struct TrackDev {
+    int32_t  n_steps;
+    int32_t  takeoff_t;
+    uint32_t off;        // first sample of this track in ax/ay/az (and trk32 / 2)
+    uint32_t pad;
+    double   box[6];
+};
+
+struct ScenarioDev {
+    const TrackDev* tracks;
+    const double*   ax;
+    const double*   ay;
+    const double*   az;
+    const float4*   trk32;
+    const double4*  drones;
+    double*         p1x;
+    double*         p1y;
+    int32_t*        s1_first_hit;
+    double*         s1_prefmin;
+    int32_t n_tracks, n_drones, t_max, n_steps_max;
+    double ox, oy, oz;               // fp32 origin
+    double start_alt, v_straight, v_ascend;
+    double radius;                   // R_drone + R_aircraft, summed in fp64 (Drone.cpp:260)
+    double thr_d2;                   // sqrt_rn(d2) < radius  <=>  d2 < thr_d2   (exact, host-searched)
+    float  thr2_screen;              // (radius + margin)^2 : fp32 screen, conservative
+    float  thr2_fp32;                // radius^2 in fp32    : DCRP_PRECISION_FP32 decisions
+    float  v_straight_f, coef_f;     // 19, 2*(19-8)/pi
+    int32_t bucket_shift;            // t1st bucket = (t1st-1) >> bucket_shift   (<= 64 buckets)
+};
+
+struct Record {          // == dcrp_record (56 bytes)
+    uint32_t track, drone;
+    uint64_t trial;
+    int32_t  t1st, first_hit;
+    double   tx, ty, tz;
+    double   min_dist;
+};
+
+struct Candidate {       // a trial the fp32 screen could not rule out
+    uint32_t pair;
+    uint32_t pad;
+    uint64_t trial;
+};
+
+enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_COUNT };
+
+struct RunDev {
+    uint64_t seed, trial_begin, trial_count;   // the whole run: trials [begin, begin+count) per pair
+    uint64_t slice_first, slice_count;         // this launch covers local trials [first, first+count)
+    uint32_t track_base, drone_base;           // Philox ids = base + scenario index
+    const Draw* replay;                  // device copy of the replay table or nullptr
+    unsigned long long* counts;          // [n_pairs]
+    int32_t*  first_conflict;            // [n_pairs]
+    Record*   records;
+    uint32_t* rec_count;
+    uint32_t  rec_cap;
+    Candidate* cands;
+    uint32_t* cand_count;
+    uint32_t  cand_cap;
+    unsigned long long* stats;           // [ST_COUNT]
+    uint8_t*  trial_hit;                 // per-trial outputs or nullptr
+    int32_t*  trial_first;
+    double*   trial_min;
+    int32_t   decide_fp32;               // screen kernel: 1 = DCRP_PRECISION_FP32
+};
+
+}  // namespace dcrp

@@ -1,0 +1,693 @@
+// kernels.cu -- hand-written sm_100a kernels of the Monte-Carlo trial path.
+//
+//   k_stage1      once per scenario: stage-1 paths + per-(track,drone) stage-1 tables
+//   k_screen      every trial, fp32 packed (FFMA2/FADD2/FMUL2/FMNMX3): Philox draws,
+//                 CTA-level binning by t1st, fp64->fp32 ray set-up, scan of the track
+//                 staged in shared memory by TMA bulk copies, warp-aggregated append
+//                 of the (rare) candidates
+//   k_confirm     candidates only, fp64 in the reference's order of operations
+//   k_exact       every trial in fp64 (DCRP_PRECISION_FP64; the parity kernel)
+//   k_draws       Philox replay-table dump
+//   k_trajectory  full fp64 trajectories of recorded collisions (Drone::Output rows)
+//   k_peak_*      FFMA / FFMA2 / DFMA / scan-mix micro-kernels (roofline denominators)
+//
+// Reference semantics: /root/reference/Drone.cpp:66-80,107-127,164-231,253-281
+// (restated in dcrp_math.cuh).  Nothing here is translated from the reference:
+// it has no device code at all.
+#include "dcrp_device.cuh"
+
+#include <limits.h>
+
+namespace dcrp {
+
+// =========================================================================
+// small device helpers
+// =========================================================================
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Warp-aggregated atomic slot claim; call from inside the (divergent) branch of
+// the lanes that need a slot.  One atomicAdd per group of converged lanes.
+__device__ __forceinline__ uint32_t warp_claim_slot(uint32_t* counter)
+{
+    const unsigned active = __activemask();
+    const int leader = __ffs(active) - 1;
+    const unsigned lt = (1u << lane_id()) - 1u;
+    uint32_t base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    return base + (uint32_t)__popc(active & lt);
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) and 3-input min (FMNMX3)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared), SASS: UBLKCP / SYNCS
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+// =========================================================================
+// stage 1: once per scenario
+// =========================================================================
+// One thread per (track, drone).  Walks the stage-1 indices 0..t_max-1 of the
+// drone (Drone.cpp:120-126: constant step (sin h0 * v, cos h0 * v), z = start
+// altitude), tests each against the track sample of the same index
+// (Drone.cpp:253-262) and keeps the first hit and the running minimum.
+__global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
+{
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= s.n_tracks * s.n_drones) return;
+    const int a = pair / s.n_drones, j = pair - a * s.n_drones;
+    const TrackDev t = s.tracks[a];
+    const double4 d = s.drones[j];
+    double x = d.x, y = d.y;
+    double mn = INFINITY;
+    int first = INT_MAX;
+    for (int i = 0; i < s.t_max; ++i) {
+        if (i > 0) { x = DADD(x, d.z); y = DADD(y, d.w); }
+        if (a == 0) { s.p1x[(size_t)j * s.t_max + i] = x; s.p1y[(size_t)j * s.t_max + i] = y; }
+        if (i < t.takeoff_t && i < t.n_steps) {
+            const double d2 = sep2(x, y, s.start_alt, s.ax[t.off + i], s.ay[t.off + i], s.az[t.off + i]);
+            if (d2 < mn) mn = d2;
+            if (d2 < s.thr_d2 && first == INT_MAX) first = i;
+        }
+        s.s1_prefmin[(size_t)pair * s.t_max + i] = mn;
+    }
+    s.s1_first_hit[pair] = first;
+}
+
+// =========================================================================
+// the exact trial (fp64, reference order of operations)
+// =========================================================================
+struct TrialOut {
+    int32_t first;     // first index in collision, -1 if none
+    double  min_d2;    // min squared separation over all indices
+};
+
+// ax/ay/az point at sample 0 of the track (global or shared).
+__device__ __forceinline__ TrialOut exact_trial(const ScenarioDev& s, int pair, int j, int n_steps,
+                                                const double* __restrict__ ax,
+                                                const double* __restrict__ ay,
+                                                const double* __restrict__ az, const Draw& d)
+{
+    const int last = d.t1st - 1;
+    const double xl = s.p1x[(size_t)j * s.t_max + last];
+    const double yl = s.p1y[(size_t)j * s.t_max + last];
+    const Ray64 r = stage2_ray(xl, yl, s.start_alt, d.tx, d.ty, d.tz, s.v_straight, s.v_ascend);
+    TrialOut o;
+    const int s1 = s.s1_first_hit[pair];
+    o.first = (s1 <= last) ? s1 : -1;
+    o.min_d2 = s.s1_prefmin[(size_t)pair * s.t_max + last];
+    double x = r.x, y = r.y, z = r.z;
+    for (int i = d.t1st; i < n_steps; ++i) {                // Drone.cpp:224-230
+        x = DADD(x, r.sx); y = DADD(y, r.sy); z = DADD(z, r.sz);
+        const double d2 = sep2(x, y, z, ax[i], ay[i], az[i]);
+        if (d2 < o.min_d2) o.min_d2 = d2;
+        if (d2 < s.thr_d2 && o.first < 0) o.first = i;      // Drone.cpp:260 (sqrt folded into thr_d2)
+    }
+    return o;
+}
+
+__device__ __forceinline__ Draw fetch_draw(const ScenarioDev& s, const RunDev& r, const TrackDev& t,
+                                           int pair, int a, int j, uint64_t local)
+{
+    if (r.replay) return r.replay[(size_t)pair * r.trial_count + local];
+    return make_draw(r.seed, r.trial_begin + local, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a,
+                     t.takeoff_t, t.box);
+}
+
+__device__ __forceinline__ void publish_hit(const ScenarioDev& s, const RunDev& r, int pair, int a, int j,
+                                            uint64_t trial, const Draw& d, const TrialOut& o)
+{
+    atomicAdd(&r.counts[pair], 1ull);
+    atomicMin(&r.first_conflict[pair], o.first);
+    const uint32_t slot = warp_claim_slot(r.rec_count);
+    if (slot < r.rec_cap) {
+        Record rec;
+        rec.track = (uint32_t)a; rec.drone = (uint32_t)j; rec.trial = trial;
+        rec.t1st = d.t1st; rec.first_hit = o.first;
+        rec.tx = d.tx; rec.ty = d.ty; rec.tz = d.tz;
+        rec.min_dist = DSQRT(o.min_d2);
+        r.records[slot] = rec;
+    }
+}
+
+__device__ __forceinline__ void flush_stats(const RunDev& r, unsigned long long ev, unsigned long long sh,
+                                            unsigned long long is, unsigned long long st,
+                                            unsigned long long hits)
+{
+    ev = warp_sum_u64(ev); sh = warp_sum_u64(sh); is = warp_sum_u64(is);
+    st = warp_sum_u64(st); hits = warp_sum_u64(hits);
+    if (lane_id() == 0) {
+        if (ev) atomicAdd(&r.stats[ST_EVALUATED], ev);
+        if (sh) atomicAdd(&r.stats[ST_SHARED], sh);
+        if (is) atomicAdd(&r.stats[ST_ISSUED], is);
+        if (st) atomicAdd(&r.stats[ST_STEPS], st);
+        if (hits) atomicAdd(&r.stats[ST_HITS], hits);
+    }
+}
+
+// Every trial in fp64.  Persistent CTAs walk (pair, chunk-of-EXB-trials) items.
+constexpr int EXB = 256;
+
+__global__ void __launch_bounds__(EXB) k_exact(const ScenarioDev s, const RunDev r,
+                                               uint32_t chunks_per_pair, uint32_t n_items, int use_smem)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    unsigned long long ev = 0, sh = 0, st = 0, hits = 0;
+    int loaded = -1;
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int pair = item / chunks_per_pair;
+        const uint32_t c = item - pair * chunks_per_pair;
+        const int a = pair / s.n_drones, j = pair - a * s.n_drones;
+        const TrackDev t = s.tracks[a];
+        const double *ax = s.ax + t.off, *ay = s.ay + t.off, *az = s.az + t.off;
+        if (use_smem) {
+            if (loaded != a) {
+                __syncthreads();
+                for (int i = threadIdx.x; i < t.n_steps; i += EXB) {
+                    sm[i] = ax[i];
+                    sm[s.n_steps_max + i] = ay[i];
+                    sm[2 * s.n_steps_max + i] = az[i];
+                }
+                __syncthreads();
+                loaded = a;
+            }
+            ax = sm; ay = sm + s.n_steps_max; az = sm + 2 * s.n_steps_max;
+        }
+        const uint64_t in_slice = (uint64_t)c * EXB + threadIdx.x;
+        const uint64_t local = r.slice_first + in_slice;       // index within the run
+        if (in_slice < r.slice_count) {
+            const Draw d = fetch_draw(s, r, t, pair, a, j, local);
+            const TrialOut o = exact_trial(s, pair, j, t.n_steps, ax, ay, az, d);
+            ev += (unsigned long long)(t.n_steps - d.t1st);
+            sh += (unsigned long long)d.t1st;
+            st += (unsigned long long)(t.n_steps - 1);
+            if (r.trial_hit) {
+                const size_t idx = (size_t)pair * r.trial_count + local;
+                r.trial_hit[idx] = o.first >= 0 ? 1 : 0;
+                r.trial_first[idx] = o.first;
+                r.trial_min[idx] = DSQRT(o.min_d2);
+            }
+            if (o.first >= 0) {
+                ++hits;
+                publish_hit(s, r, pair, a, j, r.trial_begin + local, d, o);
+            }
+        }
+    }
+    flush_stats(r, ev, sh, ev, st, hits);
+}
+
+// fp64 confirmation of the screen's candidates.  The list length lives on the
+// device (no host round trip between screen and confirm): grid-stride over it.
+__global__ void __launch_bounds__(128) k_confirm_all(const ScenarioDev s, const RunDev r)
+{
+    const uint32_t n_cand = min(*r.cand_count, r.cand_cap);
+    unsigned long long hits = 0;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_cand; idx += gridDim.x * blockDim.x) {
+        const Candidate cd = r.cands[idx];
+        const int pair = (int)cd.pair;
+        const int a = pair / s.n_drones, j = pair - a * s.n_drones;
+        const TrackDev t = s.tracks[a];
+        const uint64_t local = cd.trial - r.trial_begin;
+        const Draw d = fetch_draw(s, r, t, pair, a, j, local);
+        const TrialOut o = exact_trial(s, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
+        if (o.first >= 0) {
+            ++hits;
+            publish_hit(s, r, pair, a, j, cd.trial, d, o);
+        }
+    }
+    flush_stats(r, 0, 0, 0, 0, hits);
+}
+
+// =========================================================================
+// the fp32 packed screen: every trial
+// =========================================================================
+struct Setup32 {
+    Ray32   ray;
+    int32_t t1st;
+    bool    force;       // must be confirmed regardless of the scan (degenerate / stage-1 hit)
+    double  tx, ty, tz;
+};
+
+// q = staged trial: (w1, w2, w3, local | t1st << 12)
+__device__ __forceinline__ Setup32 setup_trial32(const ScenarioDev& s, const RunDev& r, const TrackDev& t,
+                                                 int pair, int j, int s1_first, uint64_t chunk_first,
+                                                 const uint4 q)
+{
+    Setup32 o;
+    o.t1st = (int32_t)(q.w >> 12);
+    const uint32_t local = q.w & 4095u;
+    if (r.replay) {
+        const Draw d = r.replay[(size_t)pair * r.trial_count + chunk_first + local];
+        o.tx = d.tx; o.ty = d.ty; o.tz = d.tz;
+    } else {
+        o.tx = draw_real(q.x, t.box[0], t.box[1]);
+        o.ty = draw_real(q.y, t.box[2], t.box[3]);
+        o.tz = draw_real(q.z, t.box[4], t.box[5]);
+    }
+    const int last = o.t1st - 1;
+    const double xl = __ldg(&s.p1x[(size_t)j * s.t_max + last]);
+    const double yl = __ldg(&s.p1y[(size_t)j * s.t_max + last]);
+    // differences and the recentring are formed in fp64 and rounded ONCE to fp32
+    const float dls = (float)DSUB(o.tx, xl);
+    const float dbs = (float)DSUB(o.ty, yl);
+    const float da  = (float)DSUB(o.tz, s.start_alt);
+    const float xlf = (float)DSUB(xl, s.ox);
+    const float ylf = (float)DSUB(yl, s.oy);
+    const float zlf = (float)DSUB(s.start_alt, s.oz);
+    o.ray = stage2_ray32(dls, dbs, da, xlf, ylf, zlf, (float)last, s.v_straight_f, s.coef_f);
+    o.force = o.ray.degenerate || (s1_first <= last);
+    return o;
+}
+
+// Scalar fp32 re-scan of ONE trial with exact index bookkeeping (rare path of
+// DCRP_PRECISION_FP32): starts at the trial's own t1st, keeps first index + min.
+__device__ __forceinline__ void rescan_fp32(const ScenarioDev& s, const RunDev& r, const TrackDev& t,
+                                            int pair, int a, int j, int s1_first, uint64_t trial,
+                                            const Setup32& u)
+{
+    const float4* __restrict__ g = s.trk32 + 2 * (size_t)t.off;
+    const int last = u.t1st - 1;
+    int first = (s1_first <= last) ? s1_first : -1;
+    float mn = (float)__ldg(&s.s1_prefmin[(size_t)pair * s.t_max + last]);
+    for (int i = u.t1st; i < t.n_steps; ++i) {
+        const float4 p = __ldg(&g[2 * i]), q = __ldg(&g[2 * i + 1]);
+        const float dx = fmaf(q.z, u.ray.sx, u.ray.bx) + p.x;
+        const float dy = fmaf(q.z, u.ray.sy, u.ray.by) + p.z;
+        const float dz = fmaf(q.z, u.ray.sz, u.ray.bz) + q.x;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        mn = fminf(mn, d2);
+        if (d2 < s.thr2_fp32 && first < 0) first = i;
+    }
+    if (first >= 0) {
+        Draw d; d.t1st = u.t1st; d.reserved = 0; d.tx = u.tx; d.ty = u.ty; d.tz = u.tz;
+        TrialOut o; o.first = first; o.min_d2 = (double)mn;
+        atomicAdd(&r.stats[ST_HITS], 1ull);
+        publish_hit(s, r, pair, a, j, trial, d, o);
+    }
+}
+
+// Shared-memory plan of k_screen (dynamic):
+//   [0, 2*tile_bytes)            two track tiles (TMA destinations), tile_steps*32 B each
+//   stage[CH]  uint4             the chunk's trials, binned by t1st
+//   hist[80]   uint32            bucket histogram / bases (65 used)
+//   bars[2]    uint64            one mbarrier per tile buffer
+template <int K, int BLOCK, bool REPLAY>
+__global__ void __launch_bounds__(BLOCK, (K <= 4 ? 2 : 1))
+k_screen(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int tile_steps)
+{
+    static_assert(K % 2 == 0, "trials are processed as packed f32x2 pairs");
+    constexpr int CH = K * BLOCK;
+    constexpr int NP = K / 2;
+    static_assert(CH <= 4096, "local trial index is packed in 12 bits");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4*   tiles = reinterpret_cast<float4*>(smem_raw);
+    uint4*    stage = reinterpret_cast<uint4*>(smem_raw + (size_t)2 * tile_steps * 32);
+    uint32_t* hist  = reinterpret_cast<uint32_t*>(stage + CH);
+    uint64_t* bars  = reinterpret_cast<uint64_t*>(hist + 80);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+
+    uint32_t phase0 = 0, phase1 = 0;      // mbarrier parities (uniform across the CTA)
+    int loaded_track = -1;                // track whose single tile sits in buffer 0
+    unsigned long long ev = 0, sh = 0, is = 0, st = 0, ncand = 0;
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int pair = item / chunks_per_pair;
+        const uint32_t c = item - pair * chunks_per_pair;
+        const int a = pair / s.n_drones, j = pair - a * s.n_drones;
+        const TrackDev t = s.tracks[a];
+        const int VL = t.n_steps;
+        const int n_tiles = (VL + tile_steps - 1) / tile_steps;
+        const uint64_t chunk_first64 = r.slice_first + (uint64_t)c * CH;  // first local trial of the chunk
+        const uint32_t n_valid = (uint32_t)min((uint64_t)CH, r.slice_count - (uint64_t)c * CH);
+        const int s1_first = __ldg(&s.s1_first_hit[pair]);
+        const float4* __restrict__ gtrk = s.trk32 + 2 * (size_t)t.off;
+
+        // ---------------- phase A: draws + histogram over t1st buckets
+        for (int h = tid; h < 80; h += BLOCK) hist[h] = 0;
+        __syncthreads();      // also: every thread is done with the previous item's stage[] and tiles
+
+        const bool need_load = !(n_tiles == 1 && loaded_track == a);
+        if (need_load && tid == 0) {
+            fence_proxy_async();
+            const uint32_t b0 = (uint32_t)min(VL, tile_steps) * 32u;
+            mbar_arrive_expect_tx(&bars[0], b0);
+            tma_bulk_g2s(tiles, gtrk, b0, &bars[0]);
+            if (n_tiles > 1) {
+                const uint32_t b1 = (uint32_t)min(VL - tile_steps, tile_steps) * 32u;
+                mbar_arrive_expect_tx(&bars[1], b1);
+                tma_bulk_g2s(tiles + 2 * (size_t)tile_steps, gtrk + 2 * (size_t)tile_steps, b1, &bars[1]);
+            }
+        }
+
+        uint32_t w1[K], w2[K], w3[K], meta[K], rank[K];
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+            const uint32_t local = (uint32_t)(m * BLOCK + tid);
+            uint32_t bucket = 64u;         // dead trials (past the end of the range) sort last
+            meta[m] = local;               // t1st == 0 marks a dead trial
+            w1[m] = w2[m] = w3[m] = 0u;
+            if (local < n_valid) {
+                int32_t t1st;
+                if (REPLAY) {
+                    t1st = r.replay[(size_t)pair * r.trial_count + chunk_first64 + local].t1st;
+                } else {
+                    const U4 w = trial_words(r.seed, r.trial_begin + chunk_first64 + local,
+                                             r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a);
+                    t1st = draw_t1st(w.x, t.takeoff_t);
+                    w1[m] = w.y; w2[m] = w.z; w3[m] = w.w;
+                }
+                bucket = (uint32_t)(t1st - 1) >> s.bucket_shift;
+                meta[m] = local | ((uint32_t)t1st << 12);
+            }
+            rank[m] = atomicAdd(&hist[bucket], 1u) | (bucket << 16);
+        }
+        __syncthreads();
+        if (warp == 0) {                   // exclusive scan of the 65 bucket counts
+            const uint32_t v0 = hist[lane], v1 = hist[lane + 32];
+            uint32_t i0 = v0, i1 = v1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u0 = __shfl_up_sync(0xffffffffu, i0, o);
+                const uint32_t u1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += u0; i1 += u1; }
+            }
+            const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+            const uint32_t tot1 = __shfl_sync(0xffffffffu, i1, 31);
+            hist[lane] = i0 - v0;
+            hist[lane + 32] = tot0 + i1 - v1;
+            if (lane == 0) hist[64] = tot0 + tot1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+            const uint32_t slot = hist[rank[m] >> 16] + (rank[m] & 0xffffu);
+            stage[slot] = make_uint4(w1[m], w2[m], w3[m], meta[m]);
+        }
+        __syncthreads();
+
+        // ---------------- phase B: set-up of this thread's K binned trials
+        float2 BX[NP], BY[NP], BZ[NP], SX[NP], SY[NP], SZ[NP];
+        int tmin = INT_MAX;
+        bool force = false;
+        const uint32_t slot0 = (uint32_t)(warp * 32 * K + lane);
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+            const uint4 q = stage[slot0 + m * 32];
+            float bx = 1e15f, by = 1e15f, bz = 1e15f, sx = 0.f, sy = 0.f, sz = 0.f;
+            if ((q.w >> 12) != 0u) {
+                const Setup32 u = setup_trial32(s, r, t, pair, j, s1_first, chunk_first64, q);
+                bx = u.ray.bx; by = u.ray.by; bz = u.ray.bz;
+                sx = u.ray.sx; sy = u.ray.sy; sz = u.ray.sz;
+                force |= u.force;
+                tmin = min(tmin, u.t1st);
+                ev += (unsigned long long)(VL - u.t1st);
+                sh += (unsigned long long)u.t1st;
+                st += (unsigned long long)(VL - 1);
+            }
+            if (m & 1) { BX[m >> 1].y = bx; BY[m >> 1].y = by; BZ[m >> 1].y = bz;
+                         SX[m >> 1].y = sx; SY[m >> 1].y = sy; SZ[m >> 1].y = sz; }
+            else       { BX[m >> 1].x = bx; BY[m >> 1].x = by; BZ[m >> 1].x = bz;
+                         SX[m >> 1].x = sx; SY[m >> 1].x = sy; SZ[m >> 1].x = sz; }
+        }
+        const int imin = __reduce_min_sync(0xffffffffu, tmin);   // warp-uniform scan start
+        if (imin < VL) is += (unsigned long long)(VL - imin) * K;
+
+        // ---------------- scan: d2(i) = |b + i*s - a_i|^2, running min over i and the K trials
+        float mn = 3.0e38f;
+        for (int tl = 0; tl < n_tiles; ++tl) {
+            const int buf = tl & 1;
+            if (need_load) {
+                if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
+                else          { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
+            }
+            const int t0 = tl * tile_steps;
+            const int lo = max(imin, t0), hi = min(VL, t0 + tile_steps);
+            const float4* __restrict__ tp = tiles + 2 * (size_t)buf * tile_steps - 2 * (size_t)t0;
+#pragma unroll 4
+            for (int i = lo; i < hi; ++i) {
+                const float4 p = tp[2 * i];          // (-ax,-ax,-ay,-ay)
+                const float4 q = tp[2 * i + 1];      // (-az,-az,  i,  i)
+                const float2 nax = make_float2(p.x, p.y), nay = make_float2(p.z, p.w);
+                const float2 naz = make_float2(q.x, q.y), fi = make_float2(q.z, q.w);
+#pragma unroll
+                for (int pp = 0; pp < NP; ++pp) {
+                    const float2 dx = fadd2(ffma2(fi, SX[pp], BX[pp]), nax);
+                    const float2 dy = fadd2(ffma2(fi, SY[pp], BY[pp]), nay);
+                    const float2 dz = fadd2(ffma2(fi, SZ[pp], BZ[pp]), naz);
+                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                    mn = fmin3(mn, d2.x, d2.y);
+                }
+            }
+            if (tl + 2 < n_tiles) {                  // recycle this buffer for tile tl+2
+                __syncthreads();
+                if (tid == 0) {
+                    fence_proxy_async();
+                    const int tn = (tl + 2) * tile_steps;
+                    const uint32_t bn = (uint32_t)min(VL - tn, tile_steps) * 32u;
+                    mbar_arrive_expect_tx(&bars[buf], bn);
+                    tma_bulk_g2s(tiles + 2 * (size_t)buf * tile_steps, gtrk + 2 * (size_t)tn, bn, &bars[buf]);
+                }
+            }
+        }
+        loaded_track = (n_tiles == 1) ? a : -1;
+
+        // ---------------- rare path: hand the thread's trials on
+        const float thr = r.decide_fp32 ? s.thr2_fp32 : s.thr2_screen;
+        if (force || mn < thr) {
+#pragma unroll 1
+            for (int m = 0; m < K; ++m) {
+                const uint4 q = stage[slot0 + m * 32];
+                if ((q.w >> 12) == 0u) continue;
+                const uint64_t trial = r.trial_begin + chunk_first64 + (q.w & 4095u);
+                if (!r.decide_fp32) {
+                    ++ncand;
+                    const uint32_t slot = warp_claim_slot(r.cand_count);
+                    if (slot < r.cand_cap) {
+                        Candidate cd; cd.pair = (uint32_t)pair; cd.pad = 0; cd.trial = trial;
+                        r.cands[slot] = cd;
+                    }
+                } else {
+                    const Setup32 u = setup_trial32(s, r, t, pair, j, s1_first, chunk_first64, q);
+                    rescan_fp32(s, r, t, pair, a, j, s1_first, trial, u);
+                }
+            }
+        }
+    }
+    flush_stats(r, ev, sh, is, st, 0);
+    ncand = warp_sum_u64(ncand);
+    if (lane == 0 && ncand) atomicAdd(&r.stats[ST_CANDIDATES], ncand);
+}
+
+// =========================================================================
+// replay table dump, trajectories
+// =========================================================================
+__global__ void __launch_bounds__(256) k_draws(const ScenarioDev s, int a, uint32_t track_id,
+                                               uint32_t drone_id, uint64_t seed, uint64_t trial_begin,
+                                               uint64_t n, Draw* out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TrackDev t = s.tracks[a];
+    out[i] = make_draw(seed, trial_begin + i, drone_id, track_id, t.takeoff_t, t.box);
+}
+
+// One thread per record; xyz layout: record r -> x[0..n) y[0..n) z[0..n) at r*3*stride.
+__global__ void __launch_bounds__(64) k_trajectory(const ScenarioDev s, const Record* recs, uint32_t n,
+                                                   double* xyz, int stride)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const Record rc = recs[idx];
+    const TrackDev t = s.tracks[rc.track];
+    double* X = xyz + (size_t)idx * 3 * stride;
+    double* Y = X + stride;
+    double* Z = Y + stride;
+    const int j = (int)rc.drone;
+    for (int i = 0; i < rc.t1st && i < t.n_steps; ++i) {       // stage 1, Drone.cpp:120-126
+        X[i] = s.p1x[(size_t)j * s.t_max + i];
+        Y[i] = s.p1y[(size_t)j * s.t_max + i];
+        Z[i] = s.start_alt;
+    }
+    const int last = rc.t1st - 1;
+    const Ray64 r = stage2_ray(X[last], Y[last], s.start_alt, rc.tx, rc.ty, rc.tz, s.v_straight, s.v_ascend);
+    double x = r.x, y = r.y, z = r.z;
+    for (int i = rc.t1st; i < t.n_steps; ++i) {                // stage 2, Drone.cpp:224-230
+        x = DADD(x, r.sx); y = DADD(y, r.sy); z = DADD(z, r.sz);
+        X[i] = x; Y[i] = y; Z[i] = z;
+    }
+}
+
+// =========================================================================
+// roofline denominators: pure-pipe micro-kernels
+// =========================================================================
+// Each thread runs `iters` rounds over 8 independent accumulators; the result is
+// stored so nothing is optimised away.  flops are counted by the host.
+__global__ void __launch_bounds__(256) k_peak_ffma(float* out, int iters, float b, float c)
+{
+    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+          a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void __launch_bounds__(256) k_peak_ffma2(float* out, int iters, float b, float c)
+{
+    float2 a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = make_float2(threadIdx.x + k, threadIdx.x - k);
+    const float2 bb = make_float2(b, b), cc = make_float2(c, c);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = ffma2(a[k], bb, cc);
+        }
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += a[k].x + a[k].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double b, double c)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// The scan loop's own instruction mix without its shared-memory loads: per pair
+// of tests 3 FFMA2 + 3 FADD2 + 1 FMUL2 + 2 FFMA2 + 1 FMNMX3, 4 independent pairs.
+__global__ void __launch_bounds__(256) k_peak_scanmix(float* out, int iters, float s0, float a0)
+{
+    float2 B[4], S[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        B[k] = make_float2(threadIdx.x * 0.5f + k, threadIdx.x * 0.25f - k);
+        S[k] = make_float2(s0 + k, s0 - k);
+    }
+    float2 fi = make_float2(0.f, 0.f);
+    const float2 one = make_float2(1.f, 1.f), na = make_float2(a0, a0);
+    float mn = 3.0e38f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 dx = fadd2(ffma2(fi, S[k], B[k]), na);
+                const float2 dy = fadd2(ffma2(fi, S[k], B[(k + 1) & 3]), na);
+                const float2 dz = fadd2(ffma2(fi, S[(k + 1) & 3], B[k]), na);
+                const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                mn = fmin3(mn, d2.x, d2.y);
+            }
+            fi = fadd2(fi, one);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = mn;
+}
+
+__global__ void __launch_bounds__(256) k_fill(float4* p, size_t n, float v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = make_float4(v, v, v, v);
+}
+
+}  // namespace dcrp

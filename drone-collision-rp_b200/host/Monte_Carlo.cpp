@@ -1,0 +1,110 @@
+// Monte_Carlo.cpp -- the reference driver (Monte_Carlo.cpp:8-39) on the GPU engine.
+// With no arguments it does what the reference's main() does, with the same
+// constants: first departure of the LHR day x 99 drones of the 1 km ring x
+// 10 000 trials, "Number of collisions: N" on stdout, collision blocks in
+// Drone_Collisions/Drone_coords_0.csv.  The constants the reference makes you
+// recompile for (Monte_Carlo.cpp:11-18,28,33) are flags here.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <sys/stat.h>
+
+#include "Aircraft.h"
+#include "Drone.h"
+#include "synth_day.h"
+
+using namespace std;
+
+static void usage(const char* argv0)
+{
+    cout << "usage: " << argv0 << " [--aircraft-csv F] [--drone-csv F] [--aircraft N] [--drones N]\n"
+            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS]\n"
+            "defaults are the reference's constants (Monte_Carlo.cpp:11-18,28,33)\n";
+}
+
+int main(int argc, char** argv)
+{
+    // Monte_Carlo.cpp:11-18
+    string FilePath_aircraft = dcrp_host::kReferenceAircraftCsv;
+    int no_col_aircraft = 22;
+    double aircraft_radius = 3.5;
+    string FilePath_drone = "drone_inital_positions_1km.csv";
+    int no_col_drone = 4;
+    int drone_total = 99;
+    double drone_radius = 0.19;
+    int aircraft_total = 1;          // Monte_Carlo.cpp:28
+    int number_runs = 10000;         // Monte_Carlo.cpp:33
+    uint64_t seed = 20170630ull;
+    int precision = DCRP_PRECISION_MIXED;
+    int synthetic = 0;
+
+    for (int i = 1; i < argc; ++i) {
+        const string a = argv[i];
+        auto next = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) { cout << "ERROR - " << name << " needs a value" << endl; exit(2); }
+            return argv[++i];
+        };
+        if (a == "--aircraft-csv") FilePath_aircraft = next("--aircraft-csv");
+        else if (a == "--drone-csv") FilePath_drone = next("--drone-csv");
+        else if (a == "--aircraft") aircraft_total = atoi(next("--aircraft"));
+        else if (a == "--drones") drone_total = atoi(next("--drones"));
+        else if (a == "--runs") number_runs = atoi(next("--runs"));
+        else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
+        else if (a == "--synthetic") synthetic = atoi(next("--synthetic"));
+        else if (a == "--precision") {
+            const string p = next("--precision");
+            if (p == "fp64") precision = DCRP_PRECISION_FP64;
+            else if (p == "mixed") precision = DCRP_PRECISION_MIXED;
+            else if (p == "fp32") precision = DCRP_PRECISION_FP32;
+            else { cout << "ERROR - unknown precision " << p << endl; return 2; }
+        } else { usage(argv[0]); return a == "--help" ? 0 : 2; }
+    }
+
+    if (synthetic > 0) {
+        ifstream probe(FilePath_aircraft);
+        if (!probe) {
+            if (dcrp_host::write_synthetic_day(FilePath_aircraft, synthetic, seed, true) != 0) {
+                cout << "ERROR - cannot write " << FilePath_aircraft << endl;
+                return 1;
+            }
+            cout << "wrote synthetic day (" << synthetic << " flights) to " << FilePath_aircraft << endl;
+        }
+    }
+    mkdir("Drone_Collisions", 0777);   // the reference needs it to pre-exist (Drone.cpp:62,236)
+
+    double* total_collisions = new double[1];
+    *total_collisions = 0;
+
+    Aircraft Aircraft;
+    Drone Drone;
+    Drone.SetSeed(seed);
+    Drone.SetPrecision(precision);
+
+    Aircraft.Set_Parameters_and_Data(FilePath_aircraft, no_col_aircraft);
+    if (!Aircraft.ok()) {
+        cout << "hint: the reference's aircraft CSV is not distributed; pass --synthetic 16 to generate a "
+                "schema-compatible stand-in" << endl;
+        return 1;
+    }
+
+    for (int i = 0; i < aircraft_total; ++i) {
+        Aircraft.Vector_Allocation(i);
+        if (Aircraft.Vector_length <= 0) { cout << "ERROR - no flight " << i << " in " << FilePath_aircraft << endl; return 1; }
+        Drone.ClearOutput(i);
+        for (int j = 0; j < drone_total; ++j) {
+            Drone.SetInitialParameters(FilePath_drone, Aircraft.Vector_length, no_col_drone, j, i, Aircraft.takeoff_t,
+                                       Aircraft.longitude_vector, Aircraft.latitude_vector, Aircraft.altitude_vector,
+                                       aircraft_radius, drone_radius);
+            Drone.Simulation(number_runs, total_collisions);
+            if (Drone.LastStatus() != 0) return 1;
+        }
+        Aircraft.Deallocation();
+    }
+    cout << "Number of collisions: " << *total_collisions << endl;
+    delete[] total_collisions;
+    dcrp_host::release_shared_engine();
+    return 0;
+}

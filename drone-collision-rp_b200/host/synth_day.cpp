@@ -1,0 +1,72 @@
+// synth_day.cpp -- see synth_day.h.
+#include "synth_day.h"
+
+#include <cstdio>
+
+namespace dcrp_host {
+
+const char* const kReferenceAircraftCsv =
+    "TAKEOFF_UTM_DEPART_A320 LHR time - 2017-06-30 04-00 to 2017-06-30 23-45.csv";
+
+namespace {
+struct SplitMix64 {
+    uint64_t s;
+    explicit SplitMix64(uint64_t seed) : s(seed) {}
+    uint64_t next()
+    {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    double unit() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    int range(int lo, int hi) { return lo + (int)(next() % (uint64_t)(hi - lo + 1)); }
+};
+}  // namespace
+
+int write_synthetic_day(const std::string& path, int n_flights, uint64_t seed, bool trailing_dummy)
+{
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return -1;
+    // 22 header cells; only columns 3, 7, 8, 13, 14, 15 are ever read (Aircraft.cpp:14-24)
+    std::fprintf(f, "index,timestamp,icao24,callsign,origin,destination,typecode,altitude,groundspeed,"
+                    "track,vertical_rate,squawk,spi,latitude,longitude,onground,last_position,hour,"
+                    "geoaltitude,alert,firstseen,lastseen\n");
+    const int total = n_flights + (trailing_dummy ? 1 : 0);
+    long row = 0;
+    for (int k = 0; k < total; ++k) {
+        SplitMix64 rng(seed * 0x100000001B3ull + (uint64_t)k * 0x9E3779B97F4A7C15ull + 1);
+        const int n = rng.range(92, 105);
+        const int ground = rng.range(24, 34);
+        const bool north = (k & 1) != 0;                      // 27R when odd, 27L when even
+        const double centre = north ? 5705983.0 : 5704545.0;  // inside the bands of Drone.cpp:135,148
+        const double northing0 = centre + (rng.unit() * 16.0 - 8.0);
+        const double accel = 2.4 + 0.4 * rng.unit();
+        const double vmax = 80.0 + 10.0 * rng.unit();
+        const double climb = 8.0 + 3.0 * rng.unit();
+        const double drift = rng.unit() - 0.5;
+        double easting = 678500.0 + (rng.unit() * 60.0 - 30.0);
+        double v = 0.0;
+        char callsign[16];
+        std::snprintf(callsign, sizeof callsign, "SYN%04d", k);
+        for (int i = 0; i < n; ++i, ++row) {
+            const bool on_ground = i < ground;
+            const double alt = on_ground ? 0.0 : climb * (double)(i - ground + 1);
+            const double northing = northing0 + (on_ground ? 0.0 : drift * (double)(i - ground + 1));
+            std::fprintf(f, "%ld,2017-06-30 %02d:%02d:%02d,4ca%03x,%s,EGLL,XXXX,A320,", row, 4 + (k / 60) % 20,
+                         k % 60, i % 60, k & 0xfff, callsign);
+            if (on_ground) std::fprintf(f, "0,");            // exactly 0: departures, Drone.cpp:47-52
+            else std::fprintf(f, "%.3f,", alt);
+            std::fprintf(f, "%.3f,270.0,%.1f,1000,False,%.3f,%.3f,%s,%ld,%d,%.3f,False,%d,%d\n", v * 1.943844,
+                         on_ground ? 0.0 : climb * 196.85, northing, easting, on_ground ? "True" : "False",
+                         1498795200L + row, 4 + (k / 60) % 20, alt, k, k + 1);
+            v += accel;
+            if (v > vmax) v = vmax;
+            easting -= v;
+        }
+    }
+    std::fclose(f);
+    return 0;
+}
+
+}  // namespace dcrp_host

@@ -1,0 +1,224 @@
+/*
+ * dcrp.h -- C ABI of the B200 Monte-Carlo collision-sampling engine (libdcrp.so).
+ *
+ * This is the drop-in boundary for the reference's trial loop.  The reference
+ * (mohittank01/drone-collision-RP) has no FFI of its own; its seam is the class
+ * API called from main() (Monte_Carlo.cpp:26-35).  The new host classes
+ * (drone-collision-rp_b200/host/{Aircraft,Drone}.{h,cpp}) keep that API and
+ * forward the per-trial work here.  Each entry point cites what it replaces.
+ *
+ * Conventions
+ *   - plain C types, caller-owned host buffers borrowed for the call,
+ *     engine-owned device memory; no torch / C++ types cross this ABI;
+ *   - every function returns DCRP_OK (0) or a negative DCRP_ERR_*;
+ *     dcrp_last_error() gives the message for the calling thread;
+ *   - never exit(), never throws, and there is NO CPU fallback: without a
+ *     usable CUDA device dcrp_engine_create fails with DCRP_ERR_NO_DEVICE;
+ *   - thread-compatible: one engine per host thread.
+ */
+#ifndef DCRP_H
+#define DCRP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCRP_ABI_VERSION 1
+
+/* status codes */
+#define DCRP_OK               0
+#define DCRP_ERR_INVALID     -1   /* bad argument                                  */
+#define DCRP_ERR_CUDA        -2   /* CUDA runtime error (message in last_error)    */
+#define DCRP_ERR_NO_DEVICE   -3   /* no usable sm_100 device: no fallback          */
+#define DCRP_ERR_RUNWAY      -4   /* latitude[0] in neither runway band            */
+#define DCRP_ERR_STATE       -5   /* call sequence error (e.g. run before upload)  */
+#define DCRP_ERR_IO          -6   /* file could not be opened / parsed             */
+
+/* arithmetic modes of the trial kernels */
+#define DCRP_PRECISION_FP64   0   /* every trial in IEEE double, reference order of operations      */
+#define DCRP_PRECISION_MIXED  1   /* fp32 packed screen of every trial + fp64 confirm of candidates:
+                                     same counts / ids / records as FP64 (default, fast)            */
+#define DCRP_PRECISION_FP32   2   /* fp32 decisions, no fp64 confirm (for fp32-vs-fp64 studies)     */
+
+/* flags */
+#define DCRP_FLAG_PER_TRIAL   1u  /* fill per-trial outputs (FP64 mode only; test aid)              */
+
+typedef struct dcrp_engine dcrp_engine;
+
+/* One aircraft track = the arrays Aircraft::Vector_Allocation produces
+ * (Aircraft.cpp:113-128: longitude_vector, latitude_vector, altitude_vector,
+ * Vector_length, takeoff_t) plus the target box Drone::CubedVolume derives from
+ * it (Drone.cpp:129-161). */
+typedef struct dcrp_track {
+    const double* x;        /* UTM easting  per sample ("longitude")             */
+    const double* y;        /* UTM northing per sample ("latitude")              */
+    const double* z;        /* altitude per sample                               */
+    int32_t n_steps;        /* Vector_length                                     */
+    int32_t takeoff_t;      /* TakeoffTime: t1st ~ U{1..takeoff_t}               */
+    double  box[6];         /* min_long,max_long,min_lat,max_lat,min_alt,max_alt */
+} dcrp_track;
+
+/* One drone start row: drone_inital_positions_*.csv columns 1..3 of row
+ * DroneIndex+1 (Drone.cpp:33-35). */
+typedef struct dcrp_drone {
+    double x0, y0, heading0;   /* heading: radians clockwise from north */
+} dcrp_drone;
+
+/* One trial's four draws (Drone.cpp:113-116, 175-187): the replay-table row. */
+typedef struct dcrp_draw {
+    int32_t t1st;
+    int32_t reserved;
+    double  tx, ty, tz;
+} dcrp_draw;
+
+/* Model constants (Monte_Carlo.cpp:13,18; Drone.cpp:54-56). */
+typedef struct dcrp_model {
+    double aircraft_radius;    /* 3.5   */
+    double drone_radius;       /* 0.19  */
+    double start_alt;          /* 100.0 */
+    double v_straight;         /* 19.0  */
+    double v_ascend;           /* 8.0   */
+} dcrp_model;
+
+/* What to run.  Trials are identified by a global 64-bit id; the draws of
+ * trial t for (track a, drone j) are Philox4x32-10(key = seed,
+ * counter = (t_lo, t_hi, drone_id_base + j, track_id_base + a)), so results do
+ * not depend on how [trial_begin, trial_begin+trial_count) -- or the drones, or
+ * the tracks -- are split across calls or GPUs.  Records and counts are indexed
+ * by the scenario-local (a, j). */
+typedef struct dcrp_run {
+    uint64_t seed;
+    uint64_t trial_begin;
+    uint64_t trial_count;      /* per (track, drone); the reference's number_runs (Drone.h:74) widened */
+    int32_t  precision;        /* DCRP_PRECISION_*                                                    */
+    uint32_t flags;            /* DCRP_FLAG_*                                                         */
+    uint32_t record_capacity;  /* max collision records kept (0 = engine default)                     */
+    uint32_t track_id_base;    /* Philox ids: scenario track a draws as track (track_id_base + a),    */
+    uint32_t drone_id_base;    /* drone j as drone (drone_id_base + j) -- lets one pair, or a shard   */
+    uint32_t reserved;         /* of the drones, reproduce exactly what the full batch draws          */
+    const dcrp_draw* replay;   /* optional HOST table [n_tracks][n_drones][trial_count]: draws are
+                                  read from it instead of Philox (replayed-draw parity runs)         */
+} dcrp_run;
+
+/* Compact collision record: what Drone::Output (Drone.cpp:233-243) needs to
+ * regenerate a block, plus the first-conflict index the reference never kept. */
+typedef struct dcrp_record {
+    uint32_t track;
+    uint32_t drone;
+    uint64_t trial;            /* global trial id                   */
+    int32_t  t1st;
+    int32_t  first_hit;        /* first index with distance < R     */
+    double   tx, ty, tz;       /* stage-2 target                    */
+    double   min_dist;         /* min separation over the track (m) */
+} dcrp_record;
+
+typedef struct dcrp_stats {
+    uint64_t trials;           /* trials simulated                                                    */
+    uint64_t tests_evaluated;  /* stage-2 (trial, index) separation tests the kernels computed:
+                                  sum over trials of (n_steps - t1st)                                 */
+    uint64_t tests_shared;     /* stage-1 tests: identical for every trial of a (track, drone), so
+                                  evaluated once per pair and shared: sum over trials of t1st        */
+    uint64_t tests_issued;     /* lane-steps actually issued by the scan loops (>= evaluated)         */
+    uint64_t drone_steps;      /* sum over trials of (n_steps - 1)                                    */
+    uint64_t candidates;       /* trials the fp32 screen passed on to the fp64 confirm                */
+    uint64_t hits;             /* total collisions                                                    */
+    uint32_t kernel_launches;  /* engine kernels launched by the call                                 */
+    uint32_t reserved;
+    float    ms_prepare;       /* stage-1 / per-pair tables                                           */
+    float    ms_trials;        /* trial kernel(s): screen or exact                                    */
+    float    ms_confirm;       /* fp64 confirm of candidates                                          */
+    float    ms_device_total;  /* first to last kernel, CUDA events on the engine stream              */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+} dcrp_stats;
+
+/* Result buffers (host, caller-owned).  counts is required; the rest optional. */
+typedef struct dcrp_result {
+    uint64_t*    counts;          /* [n_tracks*n_drones] hits, ADDED to what is there (the reference
+                                     accumulates into *total_collisions, Drone.cpp:276)              */
+    int32_t*     first_conflict;  /* [n_tracks*n_drones] min first_hit over hits, INT32_MAX if none   */
+    dcrp_record* records;         /* [record_capacity]                                                */
+    uint32_t     n_records;       /* out: records written (sorted by track, drone, trial)             */
+    int32_t      overflow;        /* out: 1 when more hits than record_capacity                       */
+    uint8_t*     trial_hit;       /* DCRP_FLAG_PER_TRIAL: [n_tracks*n_drones*trial_count]             */
+    int32_t*     trial_first_hit; /* idem                                                             */
+    double*      trial_min_dist;  /* idem                                                             */
+    dcrp_stats   stats;           /* out                                                              */
+} dcrp_result;
+
+/* ---- lifetime --------------------------------------------------------- */
+int  dcrp_abi_version(void);
+const char* dcrp_last_error(void);
+void dcrp_default_model(dcrp_model* m);
+
+/* Owns a CUDA stream, device buffers and scratch on `device`. */
+int  dcrp_engine_create(int device, dcrp_engine** out);
+int  dcrp_engine_destroy(dcrp_engine* e);
+
+/* ---- host-side helper -------------------------------------------------- */
+/* Replaces Drone::CubedVolume (Drone.cpp:129-161) + depart_or_arrive
+ * (Drone.cpp:47-52).  Unlike the reference (stale values, no else branch) an
+ * out-of-band first latitude is an error: DCRP_ERR_RUNWAY. */
+int  dcrp_target_box(double ay0, double az0, double box[6]);
+
+/* ---- the trial loop ----------------------------------------------------- */
+/* Replaces the body of Drone::Simulation (Drone.cpp:269-281) for every
+ * (track, drone) pair at once: SetInitialConditions, FirstStage, SecondStage,
+ * Collision, the hit counter and the data Output needs.  Blocking; host
+ * buffers in, host buffers out (uploads, kernels, downloads inside). */
+int  dcrp_simulate(dcrp_engine* e,
+                   const dcrp_track* tracks, int32_t n_tracks,
+                   const dcrp_drone* drones, int32_t n_drones,
+                   const dcrp_model* model, const dcrp_run* run,
+                   dcrp_result* result);
+
+/* The same in three steps, for callers that keep a scenario resident in HBM
+ * (bench, multi-GPU ranks): upload once, run many trial ranges, fetch. */
+int  dcrp_scenario_upload(dcrp_engine* e,
+                          const dcrp_track* tracks, int32_t n_tracks,
+                          const dcrp_drone* drones, int32_t n_drones,
+                          const dcrp_model* model);
+/* Asynchronous on `stream` (a cudaStream_t; NULL = the engine's own stream).
+ * d_counts: optional DEVICE buffer [n_tracks*n_drones] of uint64 that hits are
+ * atomically added to (e.g. a torch tensor that is all-reduced afterwards);
+ * NULL = engine-owned.  Clears the engine's per-run accumulators first. */
+int  dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream, uint64_t* d_counts);
+/* Waits for the run and copies counts / records / stats to the host. */
+int  dcrp_fetch(dcrp_engine* e, dcrp_result* result);
+/* Milliseconds of the last run (device time between the engine's events). */
+int  dcrp_last_run_ms(dcrp_engine* e, float* ms);
+
+/* ---- replay / records --------------------------------------------------- */
+/* The Philox draws of trials [run->trial_begin, +run->trial_count) of scenario
+ * pair (track, drone) -- seed and id bases from `run` -- generated ON DEVICE by
+ * the same code the trial kernels use: the table the reference is replayed on.
+ * out[run->trial_count]. */
+int  dcrp_dump_draws(dcrp_engine* e, int32_t track, int32_t drone, const dcrp_run* run,
+                     dcrp_draw* out);
+/* Full trajectories of recorded collisions, computed ON DEVICE in fp64 with the
+ * exact-kernel arithmetic: the rows Drone::Output writes (Drone.cpp:237-241).
+ * xyz receives, per record r, x[0..n) y[0..n) z[0..n) at xyz + r*3*stride,
+ * n = that track's n_steps, stride = max n_steps over the scenario. */
+int  dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uint32_t n_records,
+                       double* xyz, int32_t* stride_out);
+
+/* ---- measurement -------------------------------------------------------- */
+/* Device peak of an FFMA-only (which=0), packed FFMA2-only (1), DFMA-only (2)
+ * or the scan loop's own FP instruction mix (3) micro-kernel, in TFLOP/s
+ * (FMA = 2 flop): the roofline denominators MEASURED_PEAKS.json lacks. */
+int  dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms);
+/* Writes `bytes` of a scratch buffer (L2 flush between timed iterations). */
+int  dcrp_flush_l2(dcrp_engine* e, void* stream);
+/* Kernels this engine has launched since creation. */
+int  dcrp_launch_count(dcrp_engine* e, uint64_t* n);
+/* Device properties the bench reports. */
+int  dcrp_device_info(dcrp_engine* e, char* name, int name_cap, int* sm_count,
+                      int* cc_major, int* cc_minor, int* clock_khz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCRP_H */

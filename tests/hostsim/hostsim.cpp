@@ -1,0 +1,115 @@
+// hostsim.cpp -- TEST AID, never shipped: compiles the __host__ __device__ trial
+// arithmetic of drone-collision-rp_b200/csrc/dcrp_math.cuh with g++ so that the
+// CPU-only test tier can check the exact statements the kernels execute
+// (Philox, draw mapping, fp64 ray, fp32 screen set-up) against the oracle.
+// It mirrors the kernels' control flow around that header; it is not a product
+// code path and libdcrp.so contains none of it.
+#include <cmath>
+#include <cstdint>
+#include <climits>
+#include <vector>
+
+#include "dcrp_math.cuh"
+
+using namespace dcrp;
+
+extern "C" {
+
+void hs_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    U4 o = philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = o.w;
+}
+
+void hs_make_draw(uint64_t seed, uint64_t trial, uint32_t drone, uint32_t track, int32_t takeoff_t,
+                  const double box[6], Draw* out)
+{
+    *out = make_draw(seed, trial, drone, track, takeoff_t, box);
+}
+
+double hs_thr_d2(double radius)
+{
+    double c = radius * radius;
+    while (std::sqrt(c) >= radius) c = std::nextafter(c, 0.0);
+    while (std::sqrt(c) < radius) c = std::nextafter(c, INFINITY);
+    return c;
+}
+
+// k_stage1 + exact_trial for n draws of one (track, drone).
+void hs_exact(const double* ax, const double* ay, const double* az, int n_steps, int takeoff_t,
+              double x0, double y0, double heading0, double radius, double start_alt, double v_straight,
+              double v_ascend, const Draw* draws, long n, int32_t* first_out, double* min_dist_out)
+{
+    const double thr = hs_thr_d2(radius);
+    const double s1x = std::sin(heading0) * v_straight, s1y = std::cos(heading0) * v_straight;
+    std::vector<double> p1x(takeoff_t), p1y(takeoff_t), pm(takeoff_t);
+    int s1_first = INT_MAX;
+    double x = x0, y = y0, mn = INFINITY;
+    for (int i = 0; i < takeoff_t; ++i) {
+        if (i > 0) { x = DADD(x, s1x); y = DADD(y, s1y); }
+        p1x[i] = x; p1y[i] = y;
+        if (i < n_steps) {
+            const double d2 = sep2(x, y, start_alt, ax[i], ay[i], az[i]);
+            if (d2 < mn) mn = d2;
+            if (d2 < thr && s1_first == INT_MAX) s1_first = i;
+        }
+        pm[i] = mn;
+    }
+    for (long r = 0; r < n; ++r) {
+        const Draw& d = draws[r];
+        const int last = d.t1st - 1;
+        const Ray64 ray = stage2_ray(p1x[last], p1y[last], start_alt, d.tx, d.ty, d.tz, v_straight, v_ascend);
+        int first = (s1_first <= last) ? s1_first : -1;
+        double m = pm[last];
+        double px = ray.x, py = ray.y, pz = ray.z;
+        for (int i = d.t1st; i < n_steps; ++i) {
+            px = DADD(px, ray.sx); py = DADD(py, ray.sy); pz = DADD(pz, ray.sz);
+            const double d2 = sep2(px, py, pz, ax[i], ay[i], az[i]);
+            if (d2 < m) m = d2;
+            if (d2 < thr && first < 0) first = i;
+        }
+        first_out[r] = first;
+        min_dist_out[r] = DSQRT(m);
+    }
+}
+
+// The fp32 screen of k_screen for n draws of one (track, drone): min over the
+// stage-2 indices of the fp32 squared separation (scalar fmaf form of the packed
+// FFMA2/FADD2/FMUL2 sequence), relative to origin (ox, oy, oz).
+void hs_screen(const double* ax, const double* ay, const double* az, int n_steps, int takeoff_t,
+               double x0, double y0, double heading0, double start_alt, double v_straight, double v_ascend,
+               double ox, double oy, double oz, const Draw* draws, long n, float* min_d2_out)
+{
+    const double s1x = std::sin(heading0) * v_straight, s1y = std::cos(heading0) * v_straight;
+    std::vector<double> p1x(takeoff_t), p1y(takeoff_t);
+    double x = x0, y = y0;
+    for (int i = 0; i < takeoff_t; ++i) {
+        if (i > 0) { x = DADD(x, s1x); y = DADD(y, s1y); }
+        p1x[i] = x; p1y[i] = y;
+    }
+    std::vector<float> nx(n_steps), ny(n_steps), nz(n_steps);
+    for (int i = 0; i < n_steps; ++i) {
+        nx[i] = -(float)(ax[i] - ox); ny[i] = -(float)(ay[i] - oy); nz[i] = -(float)(az[i] - oz);
+    }
+    const float coef = (float)(2.0 * (v_straight - v_ascend) / DCRP_PI);
+    for (long r = 0; r < n; ++r) {
+        const Draw& d = draws[r];
+        const int last = d.t1st - 1;
+        const double xl = p1x[last], yl = p1y[last];
+        const Ray32 ray = stage2_ray32((float)DSUB(d.tx, xl), (float)DSUB(d.ty, yl), (float)DSUB(d.tz, start_alt),
+                                       (float)DSUB(xl, ox), (float)DSUB(yl, oy), (float)DSUB(start_alt, oz),
+                                       (float)last, (float)v_straight, coef);
+        float mn = 3.0e38f;
+        for (int i = d.t1st; i < n_steps; ++i) {
+            const float fi = (float)i;
+            const float dx = fmaf(fi, ray.sx, ray.bx) + nx[i];
+            const float dy = fmaf(fi, ray.sy, ray.by) + ny[i];
+            const float dz = fmaf(fi, ray.sz, ray.bz) + nz[i];
+            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            mn = fminf(mn, d2);
+        }
+        min_d2_out[r] = ray.degenerate ? 0.f : mn;
+    }
+}
+
+}  // extern "C"
