@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- separation tests/s of the Monte-Carlo trial path on N B200s.
+
+A "step" is one pass of the hot path over one batch: BASELINE.json configs[1],
+the 5 km ring (99 drones) against one LHR-style departure track, 101 011 trials
+per drone = 1.0e7 trials, DCRP_PRECISION_MIXED (fp32 packed screen + fp64
+confirm: same answers as the fp64 kernel).  With N GPUs every rank runs the same
+number of trials on a disjoint Philox trial range (weak scaling) and the per-pair
+hit counts are combined by one NCCL all-reduce per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's engine
+  python bench.py --impl reference [...]                       # the reference's CPU path
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every key.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "drone-aircraft separation tests/sec"
+UNIT = "tests/s"
+SEED = 20170630
+TRIALS_PER_DRONE = 101011          # x 99 drones = 1.0000089e7 trials  (BASELINE config 2: "1e7 trials")
+FLOP_PER_TEST = 11                 # 3 add + 3 sub + 3 mul + 2 add, FMA = 2
+SUSTAIN_TRIALS_PER_DRONE = 20_000_000   # 1.98e9 trials per launch for the steady-state figure
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload(tmp):
+    import drone_collision_rp_b200 as pk
+    from drone_collision_rp_b200 import scenario
+
+    tracks, csv = scenario.synthetic_tracks(tmp, 1)
+    ring = scenario.load_ring(pk.RING_5KM)
+    return tracks, ring, csv
+
+
+def config_dict(n_gpus, track):
+    return {
+        "workload": "BASELINE configs[1]: drone_inital_positions_5km.csv (99 drones) x 1 synthetic LHR A320 "
+                    "departure track (%d samples, takeoff_t %d; the real ADS-B CSV is not distributed) x "
+                    "%d trials/drone = %d trials per step per GPU" % (
+                        track["n_steps"], track["takeoff_t"], TRIALS_PER_DRONE, 99 * TRIALS_PER_DRONE),
+        "precision": "mixed (fp32 packed screen of every trial + fp64 confirm of candidates; results == fp64 mode)",
+        "seed": SEED,
+        "sharding": "rank g runs trials [(s*N+g)*n, +n) of every (track, drone); counts all-reduced (NCCL) per step",
+        "l2": "inputs (3.3 KB track + 2.4 KB ring) are shared-memory/L2 resident by design; a 256 MB buffer "
+              "is written between timed steps to flush L2 anyway",
+        "parallelism": "dp%d over trial ranges" % n_gpus,
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, power, reasons = [], [], [], set()
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 10:
+                continue
+            try:
+                sm.append(float(c[1])); smmax.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[6:10]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the load window"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smmax), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's CPU path (cpu_baseline leg and --impl reference): the ONLY code here that may
+# execute anything under oracle/
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(csv, ring_csv, runs_per_drone, nproc, scratch):
+    """oracle/_ref/ref_asshipped: unmodified Aircraft.cpp + Drone.cpp, as shipped, nproc processes."""
+    import oracle_api as oa
+
+    out = subprocess.run([oa.REF_ASSHIPPED, csv, "22", "0", ring_csv, "99", str(runs_per_drone), str(nproc), scratch],
+                         check=True, capture_output=True, text=True).stdout
+    j = json.loads(out.strip().split("\n")[-1])
+    tests = j["trials"] * j["vector_length"]          # Drone::Collision walks every index (Drone.cpp:254)
+    return {"trials": j["trials"], "tests": tests, "seconds": j["seconds"], "hits": j["hits"], "kind": "reference"}
+
+
+def _port_worker(args):
+    import oracle_api as oa
+    from drone_collision_rp_b200 import capi
+
+    track, ring_rows, drones, runs = args
+    o = oa.Oracle()
+    box = capi.target_box(track["y"][0], track["z"][0])
+    hits = 0
+    for j in drones:
+        h, _ = o.run_philox(track, box, ring_rows[j], SEED, j, 0, 0, runs, cap=16)
+        hits += h
+    return hits
+
+
+def cpu_port_run(track, ring, runs_per_drone, nproc):
+    """Fallback when oracle/_ref is absent: the C restatement (oracle/dcrp_oracle.c), nproc processes."""
+    import multiprocessing as mp
+
+    t0 = time.time()
+    jobs = [(track, ring, list(range(w, 99, nproc)), runs_per_drone) for w in range(nproc)]
+    with mp.get_context("fork").Pool(nproc) as pool:
+        hits = sum(pool.map(_port_worker, jobs))
+    secs = time.time() - t0
+    trials = 99 * runs_per_drone
+    return {"trials": trials, "tests": trials * track["n_steps"], "seconds": secs, "hits": hits, "kind": "port"}
+
+
+def cpu_baseline(tracks, ring, csv, runs_per_drone, tmp):
+    import drone_collision_rp_b200 as pk
+    import oracle_api as oa
+
+    nproc = os.cpu_count() or 1
+    if os.path.exists(oa.REF_ASSHIPPED):
+        r = cpu_reference_run(csv, pk.RING_5KM, runs_per_drone, nproc, os.path.join(tmp, "asshipped"))
+        what = ("unmodified reference Aircraft.cpp+Drone.cpp as shipped (std::random_device per draw), "
+                "%d processes" % nproc)
+    else:
+        r = cpu_port_run(tracks[0], ring, runs_per_drone, nproc)
+        what = "oracle/dcrp_oracle.c (C restatement, Philox draws), %d processes" % nproc
+    r["cores"] = nproc
+    r["what"] = what
+    return r
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    with tempfile.TemporaryDirectory() as tmp:
+        tracks, ring, csv = workload(tmp)
+        runs = 4000                                    # 99 x 4000 = 396 000 trials per step (bounded sample)
+        for _ in range(max(0, args.warmup)):
+            cpu_baseline(tracks, ring, csv, max(200, runs // 10), tmp)
+        secs, tests, trials, kind, what, cores = 0.0, 0, 0, None, None, 1
+        for _ in range(args.steps):
+            r = cpu_baseline(tracks, ring, csv, runs, tmp)
+            secs += r["seconds"]; tests += r["tests"]; trials += r["trials"]
+            kind, what, cores = r["kind"], r["what"], r["cores"]
+        value = tests / secs
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(config_dict(args.gpus, tracks[0]),
+                           sample="each step = 99 drones x %d trials (bounded sample of the %d-trial workload)" % (
+                               runs, 99 * TRIALS_PER_DRONE)),
+            "trials_per_s": trials / secs,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d steps x 99 drones x %d trials; %s" % (args.steps, runs, what)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# this repo's engine
+# ----------------------------------------------------------------------------------------------
+def engine_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import drone_collision_rp_b200 as pk
+    from drone_collision_rp_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    tmp_ctx = tempfile.TemporaryDirectory()
+    tmp = tmp_ctx.name
+    tracks, ring, csv = workload(tmp)
+    eng = capi.Engine(local)
+    info = eng.device_info()
+    n_pairs = len(tracks) * len(ring)
+    n = TRIALS_PER_DRONE
+    stream = torch.cuda.current_stream(dev)
+    sh = stream.cuda_stream
+
+    # ---- roofline denominators measured on this device
+    peaks = {}
+    if rank == 0:
+        for which, name in ((0, "ffma"), (1, "ffma2"), (2, "dfma"), (3, "scan_mix_11flop")):
+            tf, ms = eng.measure_peak(which)
+            peaks[name] = tf
+        log("peaks TFLOP/s:", peaks)
+
+    eng.upload(tracks, ring)
+    counts = [torch.zeros(n_pairs, dtype=torch.int64, device=dev) for _ in range(2)]
+
+    def step(s, timed):
+        c = counts[s & 1]
+        c.zero_()
+        begin = (s * world + rank) * n
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run = eng.run_async(seed=SEED, trial_begin=begin, trial_count=n, precision=capi.MIXED, stream=sh,
+                            d_counts=c.data_ptr())
+        if world > 1:
+            dist.all_reduce(c)
+        e1.record(stream)
+        return run, e0, e1
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    for s in range(args.warmup):
+        run, e0, e1 = step(s, False)
+        eng.fetch(run)
+        eng.flush_l2(sh)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    launches0 = eng.launch_count()
+    t_load0 = time.time()
+    wall0 = time.perf_counter()
+    step_ms, trial_ms, stats_sum = [], [], {"tests_evaluated": 0, "tests_shared": 0, "tests_issued": 0,
+                                            "drone_steps": 0, "trials": 0, "candidates": 0, "hits": 0}
+    flush_launches = 0
+    for s in range(args.warmup, args.warmup + args.steps):
+        run, e0, e1 = step(s, True)
+        res = eng.fetch(run)                      # syncs the stream; outside the event pair
+        step_ms.append(e0.elapsed_time(e1))
+        trial_ms.append(res.stats["ms_trials"])
+        for k in stats_sum:
+            stats_sum[k] += res.stats[k]
+        eng.flush_l2(sh)                          # between timed steps, outside the event pairs
+        flush_launches += 1
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    launches = eng.launch_count() - launches0 - flush_launches
+
+    total_ms = sum(step_ms)
+    agg = torch.tensor([total_ms, float(stats_sum["tests_evaluated"]), float(stats_sum["trials"]),
+                        float(stats_sum["drone_steps"]), float(stats_sum["tests_shared"])],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm_ = agg.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        total_ms = mx[0].item()
+        tests, trials, dsteps, shared = (sm_[i].item() for i in (1, 2, 3, 4))
+    else:
+        tests, trials, dsteps, shared = (agg[i].item() for i in (1, 2, 3, 4))
+    secs = total_ms * 1e-3
+    value = tests / secs
+
+    # ---- steady state: one long launch per rank (also gives the clock sampler something to see)
+    sustain = None
+    run = eng.run_async(seed=SEED, trial_begin=10**12 + rank * SUSTAIN_TRIALS_PER_DRONE,
+                        trial_count=SUSTAIN_TRIALS_PER_DRONE, precision=capi.MIXED, stream=sh)
+    res_s = eng.fetch(run)
+    t_load1 = time.time()
+    sustain = {"trials": res_s.stats["trials"], "ms_trials_kernel": res_s.stats["ms_trials"],
+               "tests_per_s": res_s.stats["tests_evaluated"] / (res_s.stats["ms_trials"] * 1e-3),
+               "trials_per_s": res_s.stats["trials"] / (res_s.stats["ms_trials"] * 1e-3),
+               "issued_over_evaluated": res_s.stats["tests_issued"] / max(1, res_s.stats["tests_evaluated"]),
+               "hits": res_s.stats["hits"], "candidates": res_s.stats["candidates"]}
+
+    # ---- end to end through the public C-ABI call with HOST buffers (upload + kernels + download per
+    # step), on every rank at once; aggregate = all ranks' tests / slowest rank's wall time
+    e2e_secs, e2e_tests, h2d, d2h = 0.0, 0, 0, 0
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup and world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        r = eng.simulate(tracks, ring, seed=SEED, trial_begin=(s * world + rank) * n, trial_count=n,
+                         precision=capi.MIXED)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            e2e_secs += dt
+            e2e_tests += r.stats["tests_evaluated"]
+            h2d, d2h = r.stats["h2d_bytes"], r.stats["d2h_bytes"]
+    if world > 1:
+        a = torch.tensor([e2e_secs], dtype=torch.float64, device=dev)
+        b = torch.tensor([float(e2e_tests)], dtype=torch.float64, device=dev)
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_secs, e2e_tests = a.item(), b.item()
+    e2e_value = e2e_tests / e2e_secs
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    clocks = sampler.stop(t_load0, t_load1)
+
+    # ---- roofline of the dominant kernel (k_screen), live CUDA-event durations of the timed steps
+    k_ms = sum(trial_ms) / len(trial_ms)
+    tests_per_launch = stats_sum["tests_evaluated"] / args.steps
+    achieved = tests_per_launch * FLOP_PER_TEST / (k_ms * 1e-3) * 1e-12
+    peak = peaks["ffma"]
+    roofline = {
+        "bound": "fp32", "kernel": "k_screen<4,512>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": None,
+        "peak_source": "FFMA-only micro-kernel measured on this device in this run (MEASURED_PEAKS.json has no "
+                       "FP32 figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
+        "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": tests_per_launch, "kernel_ms": k_ms,
+        "peaks_measured_tflops": peaks,
+        "frac_of_scan_mix_ceiling": achieved / peaks["scan_mix_11flop"],
+        "sustained": {"achieved": sustain["tests_per_s"] * FLOP_PER_TEST * 1e-12,
+                      "frac": sustain["tests_per_s"] * FLOP_PER_TEST * 1e-12 / peak, **sustain},
+        "hbm": {"note": "track 3.3 KB + ring tables per launch; records 56 B per hit: not HBM-bound",
+                "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0},
+    }
+
+    # ---- the reference's CPU path on this box's host cores (bounded sample)
+    base = cpu_baseline(tracks, ring, csv, 20000, tmp)
+    cpu = {"value": base["tests"] / base["seconds"], "unit": UNIT, "cores": base["cores"], "kind": base["kind"],
+           "sample": "99 drones x 20000 trials (%.1f s); %s" % (base["seconds"], base["what"]),
+           "trials_per_s": base["trials"] / base["seconds"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(world, tracks[0]),
+        "trials_per_s": trials / secs, "drone_steps_per_s": dsteps / secs,
+        "tests_per_s_incl_shared_stage1": (tests + shared) / secs,
+        "tests_evaluated_per_step": tests / args.steps, "hits_in_timed_steps": stats_sum["hits"],
+        "candidates_in_timed_steps": stats_sum["candidates"],
+        "wall_ms_timed_region": wall * 1e3,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": "dcrp_simulate (host buffers in/out: upload, stage-1, screen, confirm, download)",
+                "ms_per_step": 1e3 * e2e_secs / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "device": info,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="dcrp", choices=["dcrp", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return engine_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -54,3 +54,14 @@ def synthetic_tracks(workdir, n_flights, seed=SYNTH_DAY_SEED):
     if not os.path.exists(path):
         write_synthetic_day(path, n_flights, seed, True)
     return [load_flight(path, i) for i in range(n_flights)], path
+
+
+def partition_trials(trial_begin, trial_count, rank, world):
+    """Contiguous, disjoint, exhaustive split of [trial_begin, trial_begin+trial_count)
+    over `world` ranks; returns (begin, count) of `rank`.  Philox
+    counters carry the global trial id, so the union of the ranks' results equals
+    the single-GPU result bit for bit."""
+    base, extra = divmod(int(trial_count), int(world))
+    count = base + (1 if rank < extra else 0)
+    begin = int(trial_begin) + rank * base + min(rank, extra)
+    return begin, count

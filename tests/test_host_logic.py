@@ -1,0 +1,147 @@
+"""CPU tier: the C-ABI libraries load and export every declared symbol, the C++
+host mirror (Aircraft / Drone CSV handling, synthetic day, writer) behaves like the
+reference's, and nothing pretends to compute without a GPU."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import drone_collision_rp_b200 as pk
+from drone_collision_rp_b200 import capi, scenario
+
+ROOT = pk.REPO_ROOT
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_libraries_export_every_declared_symbol():
+    for header, libpath, listed in (("dcrp.h", pk.LIBDCRP, capi.DCRP_SYMBOLS),
+                                    ("dcrp_host.h", pk.LIBDCRP_HOST, capi.DCRP_HOST_SYMBOLS)):
+        text = open(os.path.join(ROOT, "include", header)).read()
+        declared = set(re.findall(r"\b(dcrph?_[a-z0-9_]+)\s*\(", text))
+        assert declared == set(listed), (declared ^ set(listed))
+        nm = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True, check=True).stdout
+        exported = set(re.findall(r" T (dcrph?_[a-z0-9_]+)", nm))
+        assert declared <= exported, declared - exported
+    assert capi.lib().dcrp_abi_version() == 1
+
+
+def test_abi_struct_sizes_match_header():
+    src = r'''
+    #include <stdio.h>
+    #include "dcrp.h"
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dcrp_track), sizeof(dcrp_drone), sizeof(dcrp_draw),
+      sizeof(dcrp_model), sizeof(dcrp_run), sizeof(dcrp_record), sizeof(dcrp_stats), sizeof(dcrp_result)); return 0; }'''
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(tmp, "s.c"), "-o",
+                        os.path.join(tmp, "s")], check=True)
+        sizes = [int(v) for v in subprocess.run([os.path.join(tmp, "s")], capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(capi.Track), C.sizeof(capi.Drone), C.sizeof(capi.Draw), C.sizeof(capi.Model), C.sizeof(capi.Run),
+            capi.RECORD_DTYPE.itemsize, C.sizeof(capi.Stats), C.sizeof(capi.Result)]
+    assert sizes == want
+
+
+@pytest.mark.skipif(_has_gpu(), reason="CPU-only behaviour")
+def test_no_gpu_means_loud_failure_not_fallback(tmp_path):
+    with pytest.raises(capi.DcrpError) as e:
+        capi.Engine(0)
+    assert e.value.status == capi.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    # the C++ driver too: error + non-zero exit, no collision count printed
+    for f in ("drone_inital_positions_1km.csv",):
+        os.symlink(os.path.join(pk.DATA_DIR, f), tmp_path / f)
+    r = subprocess.run([pk.MONTE_CARLO, "--synthetic", "3", "--runs", "10", "--drones", "2"], cwd=tmp_path,
+                       capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "ERROR - no CUDA device" in r.stdout and "Number of collisions" not in r.stdout
+
+
+def test_ring_rows_as_the_reference_binds_them():
+    want = json.load(open(os.path.join(GOLDEN, "ref_ring_rows.json")))
+    for name, path in (("drone_inital_positions_1km.csv", pk.RING_1KM), ("drone_inital_positions_5km.csv", pk.RING_5KM)):
+        got = scenario.load_ring(path, n=100)
+        assert np.array_equal(got, np.array(want[name]))
+        assert np.array_equal(got[99], got[0]) or np.allclose(got[99, :2], got[0, :2], atol=1e-6)   # row 99 == row 0
+    with pytest.raises(capi.DcrpError):
+        scenario.load_ring(pk.RING_1KM, n=101)          # row 101 does not exist
+    with pytest.raises(capi.DcrpError):
+        scenario.load_ring(os.path.join(pk.DATA_DIR, "nope.csv"), n=1)
+
+
+def test_synthetic_day_schema_and_determinism(tmp_path):
+    a = scenario.write_synthetic_day(str(tmp_path / "a.csv"), 5, 77, True)
+    b = scenario.write_synthetic_day(str(tmp_path / "b.csv"), 5, 77, True)
+    c = scenario.write_synthetic_day(str(tmp_path / "c.csv"), 5, 78, True)
+    assert open(a).read() == open(b).read() != open(c).read()
+    lines = open(a).read().strip().split("\n")
+    assert all(len(l.split(",")) == 22 for l in lines)                 # Monte_Carlo.cpp:12
+    assert scenario.flight_count(a) == 6                               # 5 + trailing dummy
+    for i in range(5):
+        f = scenario.load_flight(a, i)
+        assert 92 <= f["n_steps"] <= 105 and 23 <= f["takeoff_t"] <= 33
+        assert f["z"][0] == 0.0 and (f["z"][: f["takeoff_t"] + 1] == 0).all() and f["z"][f["takeoff_t"] + 1] > 0
+        box = capi.target_box(f["y"][0], f["z"][0])                    # inside a runway band
+        assert box[1] == 676819.02                                     # departure
+
+
+def test_aircraft_loader_matches_golden_and_reference(day, golden):
+    import oracle_api as oa
+
+    tracks, csv = day
+    assert scenario.flight_count(csv) == int(golden["ref_index_size"]) == 7
+    for a, t in enumerate(tracks):
+        for k in "xyz":
+            assert np.array_equal(t[k], golden["track%d_%s" % (a, k)])
+        assert t["takeoff_t"] == int(golden["track%d_takeoff_t" % a])
+    if oa.RefAircraft.available():
+        ra = oa.RefAircraft()
+        for a in range(6):
+            r = ra.load(csv, a)
+            t = scenario.load_flight(csv, a)
+            assert r["n_steps"] == t["n_steps"] and r["takeoff_t"] == t["takeoff_t"]
+            for k in ("x", "y", "z", "gs"):
+                assert np.array_equal(r[k], t[k])
+        # the reference reaches the last flight only through index == N (Aircraft.cpp:73-82);
+        # the new loader serves it at N-1 as well
+        last_ref = ra.load(csv, 7)
+        assert np.array_equal(last_ref["x"], scenario.load_flight(csv, 7)["x"])
+        assert np.array_equal(last_ref["x"], scenario.load_flight(csv, 6)["x"])
+
+
+def test_aircraft_loader_errors(tmp_path):
+    with pytest.raises(capi.DcrpError):
+        scenario.flight_count(str(tmp_path / "missing.csv"))
+    p = scenario.write_synthetic_day(str(tmp_path / "d.csv"), 2, 1, False)
+    assert scenario.flight_count(p) == 2
+    with pytest.raises(capi.DcrpError):
+        scenario.load_flight(p, 5)
+    # takeoff_t never reads past the end when the on-ground flag never flips
+    rows = open(p).read().split("\n")
+    flat = [rows[0]] + [r.replace(",False,", ",True,", 1) if False else r for r in rows[1:]]
+    open(tmp_path / "e.csv", "w").write("\n".join(flat))
+    assert scenario.load_flight(str(tmp_path / "e.csv"), 1)["n_steps"] > 0
+
+
+def test_partition_trials_is_disjoint_and_exhaustive():
+    for begin, count, world in ((0, 10, 3), (5, 101011, 8), (2**40, 7, 8), (0, 0, 4), (3, 1, 2)):
+        parts = [scenario.partition_trials(begin, count, r, world) for r in range(world)]
+        assert sum(c for _, c in parts) == count
+        pos = begin
+        for b, c in parts:
+            assert b == pos
+            pos += c
+        assert max(c for _, c in parts) - min(c for _, c in parts) <= 1

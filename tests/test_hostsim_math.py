@@ -1,0 +1,55 @@
+"""CPU tier: the __host__ __device__ arithmetic the kernels execute
+(drone-collision-rp_b200/csrc/dcrp_math.cuh, compiled here with g++ by
+tests/hostsim) against the oracle -- Philox, draw mapping, the fp64 trial, and the
+error of the fp32 screen relative to the margin the engine adds to the radius."""
+import numpy as np
+
+from drone_collision_rp_b200 import capi
+
+
+def test_philox_and_draws_equal_oracle(hostsim, oracle, tracks):
+    for ctr, key in (([0, 0, 0, 0], [0, 0]), ([1, 2, 3, 4], [5, 6]), ([0xffffffff] * 4, [0xffffffff] * 2)):
+        assert hostsim.philox(ctr, key) == oracle.philox(ctr, key)
+    t = tracks[2]
+    box = capi.target_box(t["y"][0], t["z"][0])
+    for begin in (0, 2**32 - 3, 2**45):
+        assert np.array_equal(hostsim.draws(9, begin, 2000, 17, 2, t["takeoff_t"], box),
+                              oracle.draws(9, begin, 2000, 17, 2, t["takeoff_t"], box))
+
+
+def test_exact_trial_statements_equal_reference_answers(hostsim, golden, tracks, ring1):
+    """Stage-1 tables + stage2_ray + sep2 + the sqrt-free threshold reproduce the
+    unmodified reference's flags, first-hit indices and min distances bit for bit
+    (host libm on both sides)."""
+    for p, (a, j) in enumerate(golden["pairs"]):
+        first, mind = hostsim.exact(tracks[a], ring1[j], golden["pair%d_draws" % p])
+        assert np.array_equal(first, golden["pair%d_first_hit" % p])
+        assert np.array_equal(first >= 0, golden["pair%d_hit" % p] == 1)
+        assert np.array_equal(mind, golden["pair%d_min_dist" % p])
+
+
+def test_sqrt_free_threshold_is_exact(hostsim):
+    for r in (3.69, 0.19 + 3.5, 1.0, 2.0, 1e-3, 12345.678):
+        c = hostsim.L.hs_thr_d2(r)
+        below = np.nextafter(c, 0.0)
+        assert np.sqrt(c) >= r and np.sqrt(below) < r
+
+
+def test_fp32_screen_error_is_far_inside_the_margin(hostsim, golden, tracks, ring1):
+    """|fp32 screen distance - fp64 distance| on every golden near miss (min in stage
+    2, < 25 m): the engine's margin is >= 0.02 m + 32 ulp32(extent) ~ 0.05 m."""
+    worst = 0.0
+    for p, (a, j) in enumerate(golden["pairs"]):
+        t = tracks[a]
+        draws = golden["pair%d_draws" % p]
+        mind = golden["pair%d_min_dist" % p]
+        origin = (np.floor(0.5 * (671819.02 + 678600.0)), np.floor(0.5 * (5704300.0 + 5706300.0)), 250.0)
+        s = np.sqrt(hostsim.screen(t, ring1[j], draws, origin).astype(np.float64))
+        near = mind < 25.0
+        # the screen only covers stage 2; where the fp64 minimum sits in stage 1 the screen is >= it
+        assert (s[near] >= mind[near] - 5e-3).all()
+        same = near & (np.abs(s - mind) < 1.0)
+        assert same.sum() > 0.9 * near.sum()
+        worst = max(worst, np.abs(s[same] - mind[same]).max())
+    print("worst fp32 screen error %.2e m" % worst)
+    assert worst < 5e-3
