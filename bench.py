@@ -32,7 +32,8 @@ UNIT = "tests/s"
 SEED = 20170630
 TRIALS_PER_DRONE = 101011          # x 99 drones = 1.0000089e7 trials  (BASELINE config 2: "1e7 trials")
 FLOP_PER_TEST = 11                 # 3 add + 3 sub + 3 mul + 2 add, FMA = 2
-SUSTAIN_TRIALS_PER_DRONE = 20_000_000   # 1.98e9 trials per launch for the steady-state figure
+SUSTAIN_TRIALS_PER_DRONE = 50_000_000   # 4.95e9 trials per launch for the steady-state figure
+SUSTAIN_LAUNCHES = 10
 
 
 def log(*a):
@@ -239,8 +240,12 @@ def engine_arm(args):
     info = eng.device_info()
     n_pairs = len(tracks) * len(ring)
     n = TRIALS_PER_DRONE
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-default) torch stream: the engine treats a NULL handle as "use my own
+    # stream", and torch's events must sit on the stream the kernels are launched on
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     sh = stream.cuda_stream
+    assert sh != 0
 
     # ---- roofline denominators measured on this device
     peaks = {}
@@ -317,16 +322,18 @@ def engine_arm(args):
     value = tests / secs
 
     # ---- steady state: one long launch per rank (also gives the clock sampler something to see)
-    sustain = None
-    run = eng.run_async(seed=SEED, trial_begin=10**12 + rank * SUSTAIN_TRIALS_PER_DRONE,
-                        trial_count=SUSTAIN_TRIALS_PER_DRONE, precision=capi.MIXED, stream=sh)
-    res_s = eng.fetch(run)
+    sus_ms, sus_tests, sus_trials, sus_issued, sus_hits, sus_cand = 0.0, 0, 0, 0, 0, 0
+    for k in range(SUSTAIN_LAUNCHES):
+        run = eng.run_async(seed=SEED, trial_begin=10**12 + (k * world + rank) * SUSTAIN_TRIALS_PER_DRONE,
+                            trial_count=SUSTAIN_TRIALS_PER_DRONE, precision=capi.MIXED, stream=sh)
+        res_s = eng.fetch(run)
+        sus_ms += res_s.stats["ms_trials"]; sus_tests += res_s.stats["tests_evaluated"]
+        sus_trials += res_s.stats["trials"]; sus_issued += res_s.stats["tests_issued"]
+        sus_hits += res_s.stats["hits"]; sus_cand += res_s.stats["candidates"]
     t_load1 = time.time()
-    sustain = {"trials": res_s.stats["trials"], "ms_trials_kernel": res_s.stats["ms_trials"],
-               "tests_per_s": res_s.stats["tests_evaluated"] / (res_s.stats["ms_trials"] * 1e-3),
-               "trials_per_s": res_s.stats["trials"] / (res_s.stats["ms_trials"] * 1e-3),
-               "issued_over_evaluated": res_s.stats["tests_issued"] / max(1, res_s.stats["tests_evaluated"]),
-               "hits": res_s.stats["hits"], "candidates": res_s.stats["candidates"]}
+    sustain = {"launches": SUSTAIN_LAUNCHES, "trials": sus_trials, "ms_trials_kernel": sus_ms,
+               "tests_per_s": sus_tests / (sus_ms * 1e-3), "trials_per_s": sus_trials / (sus_ms * 1e-3),
+               "issued_over_evaluated": sus_issued / max(1, sus_tests), "hits": sus_hits, "candidates": sus_cand}
 
     # ---- end to end through the public C-ABI call with HOST buffers (upload + kernels + download per
     # step), on every rank at once; aggregate = all ranks' tests / slowest rank's wall time

@@ -3,16 +3,16 @@
 // HBM layout (all engine-owned, built by dcrp_scenario_upload):
 //   tracks[n_tracks]            TrackDev: n_steps, takeoff_t, sample offset, target box
 //   ax, ay, az [sum n_steps]    fp64 SoA, tracks back to back  (exact / confirm kernels)
-//   trk32 [2 * sum n_steps]     fp32 screen copy, 32 B per sample, relative to the scenario
-//                               origin and negated, each value duplicated so that one
-//                               LDS.128 yields ready-made f32x2 operands:
-//                                 [2i]   = (-ax, -ax, -ay, -ay)
-//                                 [2i+1] = (-az, -az,  i ,  i )       (i as float)
+//   trk32 [sum n_steps]         fp32 screen copy, 16 B per sample, relative to the scenario
+//                               origin and negated: (-ax, -ay, -az, i)  (i as float); one
+//                               broadcast LDS.128 per index feeds the packed f32x2 ops through
+//                               their scalar-broadcast operand form
 //   drones[n_drones]            x0, y0, sin(h0)*v, cos(h0)*v   (fp64; trig by the host's libm,
 //                               the same one the reference links, Drone.cpp:121-122)
 //   p1x, p1y [n_drones*t_max]   stage-1 path of every drone, sequentially accumulated fp64
 //   s1_first_hit [n_pairs]      first stage-1 index in collision (INT32_MAX if none)
 //   s1_prefmin  [n_pairs*t_max] prefix minimum of the stage-1 squared separation
+//   kink [n_pairs*t_max], p1f [n_drones*t_max]  pre-subtracted kink tables of the fp32 screen
 // Stage 1 does not depend on the draws except through t1st, so it is evaluated
 // once per (track, drone) and shared by all of that pair's trials.
 #pragma once
@@ -29,6 +29,10 @@ struct TrackDev {
     uint32_t off;        // first sample of this track in ax/ay/az (and trk32 / 2)
     uint32_t pad;
     double   box[6];
+    // fast screen set-up: target = box_min + w * (extent * 2^-32), w = Philox word
+    double   wx32, wy32; // (box[1]-box[0]) * 2^-32, (box[3]-box[2]) * 2^-32
+    float    wz32;       // (box[5]-box[4]) * 2^-32
+    float    z0rel;      // box[4] - start_alt
 };
 
 struct ScenarioDev {
@@ -42,7 +46,10 @@ struct ScenarioDev {
     double*         p1y;
     int32_t*        s1_first_hit;
     double*         s1_prefmin;
+    double2*        kink;            // [n_pairs*t_max] (box.xmin - p1x[L], box.ymin - p1y[L]): fast screen set-up
+    float2*         p1f;             // [n_drones*t_max] stage-1 path relative to the origin, rounded once to fp32
     int32_t n_tracks, n_drones, t_max, n_steps_max;
+    int32_t n_sm;                    // SMs of the device (CTA stagger)
     double ox, oy, oz;               // fp32 origin
     double start_alt, v_straight, v_ascend;
     double radius;                   // R_drone + R_aircraft, summed in fp64 (Drone.cpp:260)

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <climits>
 #include <string>
@@ -63,11 +64,30 @@ struct DevBuf {            // grow-only device buffer
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// screen kernel configuration (512 threads x 4 trials, 2 CTAs / SM)
-constexpr int SCREEN_K = 4;
-constexpr int SCREEN_BLOCK = 512;
-constexpr int SCREEN_CH = SCREEN_K * SCREEN_BLOCK;
-constexpr int SCREEN_TILE_STEPS = 512;       // 16 KB per tile buffer
+struct PinnedBuf {         // grow-only pinned host buffer (async copies need page-locked memory)
+    void*  p = nullptr;
+    size_t cap = 0;
+    cudaError_t need(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = (bytes + 4095) & ~size_t(4095);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+
+// screen kernel configuration: 256 threads, 2 rounds x 2 trials per thread per item,
+// 5 CTAs per SM
+constexpr int SCREEN2_R = 2;
+constexpr int SCREEN2_BLOCK = 256;
+constexpr int SCREEN2_CH = 2 * SCREEN2_R * SCREEN2_BLOCK;
 constexpr uint32_t DEFAULT_RECORD_CAP = 1u << 16;
 constexpr uint32_t CAND_CAP = 1u << 22;
 constexpr uint64_t MAX_ITEMS_PER_LAUNCH = 1ull << 30;
@@ -86,7 +106,12 @@ struct dcrp_engine {
     dcrp_model model{};
     float ms_prepare = 0.f;
     uint64_t h2d_scenario = 0;
-    DevBuf d_tracks, d_ax, d_ay, d_az, d_trk32, d_drones, d_p1x, d_p1y, d_s1fh, d_s1pm;
+    // inputs live in ONE device arena filled by ONE H2D copy from a pinned mirror:
+    //   [tracks | ax | ay | az | trk32 | drones], each segment 256-B aligned
+    DevBuf d_scn;
+    PinnedBuf h_scn;
+    DevBuf d_p1x, d_p1y, d_s1fh, d_s1pm, d_kink, d_p1f;
+    bool prepare_timed = false;
 
     // run
     bool has_run = false;
@@ -96,17 +121,22 @@ struct dcrp_engine {
     uint32_t rec_cap = 0;
     uint32_t launches_this_run = 0;
     uint64_t h2d_run = 0;
-    DevBuf d_counts, d_first, d_records, d_small /* rec_count, cand_count, stats */, d_cands, d_replay;
+    // per-run outputs live in ONE device arena read back by ONE D2H copy into a pinned mirror:
+    //   [rec_count, cand_count, pad | stats[ST_COUNT] | counts[n_pairs] | first_conflict[n_pairs]]
+    DevBuf d_out;
+    PinnedBuf h_out;
+    size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;
+    DevBuf d_records, d_cands, d_replay;
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
     DevBuf d_scratch;    // peak kernels / draws / trajectories
     DevBuf d_flush;      // 256 MB written by dcrp_flush_l2 (> 126 MB of L2)
 };
 
-static uint32_t* small_rec_count(dcrp_engine* e) { return e->d_small.as<uint32_t>(); }
-static uint32_t* small_cand_count(dcrp_engine* e) { return e->d_small.as<uint32_t>() + 1; }
+static uint32_t* small_rec_count(dcrp_engine* e) { return e->d_out.as<uint32_t>(); }
+static uint32_t* small_cand_count(dcrp_engine* e) { return e->d_out.as<uint32_t>() + 1; }
 static unsigned long long* small_stats(dcrp_engine* e)
 {
-    return reinterpret_cast<unsigned long long*>(e->d_small.as<unsigned char>() + 16);
+    return reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + 16);
 }
 
 // ------------------------------------------------------------------ lifetime
@@ -160,11 +190,12 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     if (!e) return DCRP_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->d_tracks, &e->d_ax, &e->d_ay, &e->d_az, &e->d_trk32, &e->d_drones, &e->d_p1x,
-                      &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_counts, &e->d_first, &e->d_records,
-                      &e->d_small, &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
+    DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_out, &e->d_records,
+                      &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
                       &e->d_trial_min, &e->d_scratch, &e->d_flush};
     for (DevBuf* b : bufs) b->release();
+    e->h_scn.release();
+    e->h_out.release();
     cudaEventDestroy(e->ev_begin); cudaEventDestroy(e->ev_trials); cudaEventDestroy(e->ev_end);
     cudaEventDestroy(e->ev_a); cudaEventDestroy(e->ev_b);
     cudaStreamDestroy(e->stream);
@@ -238,6 +269,10 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         TrackDev& d = e->h_tracks[(size_t)a];
         d.n_steps = t.n_steps; d.takeoff_t = t.takeoff_t; d.off = (uint32_t)total; d.pad = 0;
         std::memcpy(d.box, t.box, sizeof d.box);
+        d.wx32 = (t.box[1] - t.box[0]) * (1.0 / 4294967296.0);
+        d.wy32 = (t.box[3] - t.box[2]) * (1.0 / 4294967296.0);
+        d.wz32 = (float)((t.box[5] - t.box[4]) * (1.0 / 4294967296.0));
+        d.z0rel = (float)(t.box[4] - model->start_alt);
         total += (uint64_t)t.n_steps;
         if (total > (1ull << 31)) return fail(DCRP_ERR_INVALID, "tracks too long in total");
         t_max = std::max(t_max, t.takeoff_t);
@@ -261,6 +296,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 
     ScenarioDev s{};
     s.n_tracks = n_tracks; s.n_drones = n_drones; s.t_max = t_max; s.n_steps_max = vl_max;
+    s.n_sm = e->prop.multiProcessorCount;
     s.ox = std::floor(0.5 * (lo[0] + hi[0]));
     s.oy = std::floor(0.5 * (lo[1] + hi[1]));
     s.oz = std::floor(0.5 * (lo[2] + hi[2]));
@@ -285,9 +321,26 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.bucket_shift = 0;
     while (((t_max - 1) >> s.bucket_shift) >= 64) ++s.bucket_shift;
 
-    // ---- host staging
-    std::vector<double> hx(total), hy(total), hz(total);
-    std::vector<float4> h32(2 * total);
+    // ---- one pinned staging arena, one H2D copy
+    const size_t n_pairs = (size_t)n_tracks * (size_t)n_drones;
+    const size_t o_tracks = 0;
+    const size_t o_ax = align256(o_tracks + sizeof(TrackDev) * (size_t)n_tracks);
+    const size_t o_ay = align256(o_ax + sizeof(double) * total);
+    const size_t o_az = align256(o_ay + sizeof(double) * total);
+    const size_t o_t32 = align256(o_az + sizeof(double) * total);
+    const size_t o_dr = align256(o_t32 + sizeof(float4) * total);
+    const size_t scn_bytes = align256(o_dr + sizeof(double4) * (size_t)n_drones);
+    cudaStream_t st = e->stream;
+    CU(cudaStreamSynchronize(st));          // the previous upload's copy has left the pinned mirror
+    CU(e->h_scn.need(scn_bytes));
+    CU(e->d_scn.need(scn_bytes));
+    unsigned char* hb = e->h_scn.as<unsigned char>();
+    std::memcpy(hb + o_tracks, e->h_tracks.data(), sizeof(TrackDev) * (size_t)n_tracks);
+    double* hx = reinterpret_cast<double*>(hb + o_ax);
+    double* hy = reinterpret_cast<double*>(hb + o_ay);
+    double* hz = reinterpret_cast<double*>(hb + o_az);
+    float4* h32 = reinterpret_cast<float4*>(hb + o_t32);
+    double4* hd = reinterpret_cast<double4*>(hb + o_dr);
     for (int a = 0; a < n_tracks; ++a) {
         const dcrp_track& t = tracks[a];
         const size_t off = e->h_tracks[(size_t)a].off;
@@ -295,11 +348,9 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
             hx[off + i] = t.x[i]; hy[off + i] = t.y[i]; hz[off + i] = t.z[i];
             const float fx = -(float)(t.x[i] - s.ox), fy = -(float)(t.y[i] - s.oy),
                         fz = -(float)(t.z[i] - s.oz);
-            h32[2 * (off + i)] = make_float4(fx, fx, fy, fy);
-            h32[2 * (off + i) + 1] = make_float4(fz, fz, (float)i, (float)i);
+            h32[off + i] = make_float4(fx, fy, fz, (float)i);
         }
     }
-    std::vector<double4> hd((size_t)n_drones);
     for (int j = 0; j < n_drones; ++j) {
         // Drone.cpp:121-122: sin(heading)*max_straight_speed, formed with the host libm
         // (the one the reference links) so stage 1 is bit-identical to the reference.
@@ -307,44 +358,34 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         const double sy = std::cos(drones[j].heading0) * model->v_straight;
         hd[(size_t)j] = make_double4(drones[j].x0, drones[j].y0, sx, sy);
     }
-
-    // ---- device buffers + upload
-    const size_t n_pairs = (size_t)n_tracks * (size_t)n_drones;
-    CU(e->d_tracks.need(sizeof(TrackDev) * (size_t)n_tracks));
-    CU(e->d_ax.need(sizeof(double) * total));
-    CU(e->d_ay.need(sizeof(double) * total));
-    CU(e->d_az.need(sizeof(double) * total));
-    CU(e->d_trk32.need(sizeof(float4) * 2 * total));
-    CU(e->d_drones.need(sizeof(double4) * (size_t)n_drones));
     CU(e->d_p1x.need(sizeof(double) * (size_t)n_drones * (size_t)t_max));
     CU(e->d_p1y.need(sizeof(double) * (size_t)n_drones * (size_t)t_max));
     CU(e->d_s1fh.need(sizeof(int32_t) * n_pairs));
     CU(e->d_s1pm.need(sizeof(double) * n_pairs * (size_t)t_max));
-    cudaStream_t st = e->stream;
+    CU(e->d_kink.need(sizeof(double2) * n_pairs * (size_t)t_max));
+    CU(e->d_p1f.need(sizeof(float2) * (size_t)n_drones * (size_t)t_max));
     CU(cudaEventRecord(e->ev_a, st));
-    CU(cudaMemcpyAsync(e->d_tracks.p, e->h_tracks.data(), sizeof(TrackDev) * (size_t)n_tracks, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_ax.p, hx.data(), sizeof(double) * total, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_ay.p, hy.data(), sizeof(double) * total, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_az.p, hz.data(), sizeof(double) * total, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_trk32.p, h32.data(), sizeof(float4) * 2 * total, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(e->d_drones.p, hd.data(), sizeof(double4) * (size_t)n_drones, cudaMemcpyHostToDevice, st));
-    e->h2d_scenario = sizeof(TrackDev) * (size_t)n_tracks + sizeof(double) * 3 * total +
-                      sizeof(float4) * 2 * total + sizeof(double4) * (size_t)n_drones;
+    CU(cudaMemcpyAsync(e->d_scn.p, hb, scn_bytes, cudaMemcpyHostToDevice, st));
+    e->h2d_scenario = scn_bytes;
 
-    s.tracks = e->d_tracks.as<TrackDev>();
-    s.ax = e->d_ax.as<double>(); s.ay = e->d_ay.as<double>(); s.az = e->d_az.as<double>();
-    s.trk32 = e->d_trk32.as<float4>();
-    s.drones = e->d_drones.as<double4>();
+    unsigned char* db = e->d_scn.as<unsigned char>();
+    s.tracks = reinterpret_cast<const TrackDev*>(db + o_tracks);
+    s.ax = reinterpret_cast<const double*>(db + o_ax);
+    s.ay = reinterpret_cast<const double*>(db + o_ay);
+    s.az = reinterpret_cast<const double*>(db + o_az);
+    s.trk32 = reinterpret_cast<const float4*>(db + o_t32);
+    s.drones = reinterpret_cast<const double4*>(db + o_dr);
     s.p1x = e->d_p1x.as<double>(); s.p1y = e->d_p1y.as<double>();
     s.s1_first_hit = e->d_s1fh.as<int32_t>();
     s.s1_prefmin = e->d_s1pm.as<double>();
+    s.kink = e->d_kink.as<double2>();
+    s.p1f = e->d_p1f.as<float2>();
 
     k_stage1<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(s);
     ++e->launches;
     CU(cudaGetLastError());
-    CU(cudaEventRecord(e->ev_b, st));
-    CU(cudaStreamSynchronize(st));      // staging vectors go out of scope
-    CU(cudaEventElapsedTime(&e->ms_prepare, e->ev_a, e->ev_b));
+    CU(cudaEventRecord(e->ev_b, st));   // no host sync here: runs queue behind it on the same stream
+    e->prepare_timed = false;
     e->sd = s;
     e->model = *model;
     e->has_scenario = true;
@@ -353,23 +394,31 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 
 // ------------------------------------------------------------------ run
 template <bool REPLAY>
-static cudaError_t launch_screen(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
-                                 cudaStream_t st)
+static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
+                                  cudaStream_t st)
 {
-    auto kern = k_screen<SCREEN_K, SCREEN_BLOCK, REPLAY>;
-    const size_t smem = (size_t)2 * SCREEN_TILE_STEPS * 32 + (size_t)SCREEN_CH * 16 + 80 * 4 + 16;
-    static bool configured[2] = {false, false};
-    if (!configured[REPLAY ? 1 : 0]) {
+    auto kern = k_screen2<SCREEN2_R, SCREEN2_BLOCK, REPLAY>;
+    const int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
+    const size_t smem = (size_t)2 * tile_steps * 16 + (size_t)SCREEN2_CH * 16 + 80 * 4 + 16;
+    static size_t configured[2] = {0, 0};
+    static int occ_cache[2] = {0, 0};
+    const int v = REPLAY ? 1 : 0;
+    if (configured[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
-        configured[REPLAY ? 1 : 0] = true;
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache[v], kern, SCREEN2_BLOCK, smem);
+        if (ce != cudaSuccess) return ce;
+        if (occ_cache[v] < 1) occ_cache[v] = 1;
+        configured[v] = smem;
     }
-    int occ = 0;
-    cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SCREEN_BLOCK, smem);
-    if (ce != cudaSuccess) return ce;
-    if (occ < 1) occ = 1;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ);
-    kern<<<grid, SCREEN_BLOCK, smem, st>>>(e->sd, r, chunks_per_pair, n_items, SCREEN_TILE_STEPS);
+    const uint32_t grid =
+        (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ_cache[v]);
+    // stagger: an item (CH trials) takes ~CH * 30 ns / occupancy-share; offset co-resident CTAs by 1/occ of it
+    static const int stagger_env = std::getenv("DCRP_STAGGER_NS") ? std::atoi(std::getenv("DCRP_STAGGER_NS")) : -1;
+    const uint32_t stagger_ns = stagger_env >= 0 ? (uint32_t)stagger_env
+                                                 : (grid > (uint32_t)e->prop.multiProcessorCount ? 6000u : 0u);
+    static const uint32_t dbg = std::getenv("DCRP_DEBUG") ? (uint32_t)std::atoi(std::getenv("DCRP_DEBUG")) : 0u;
+    kern<<<grid, SCREEN2_BLOCK, smem, st>>>(e->sd, r, chunks_per_pair, n_items, tile_steps, stagger_ns, dbg);
     ++e->launches; ++e->launches_this_run;
     return cudaGetLastError();
 }
@@ -396,11 +445,14 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     e->rec_cap = run->record_capacity ? run->record_capacity : DEFAULT_RECORD_CAP;
     e->external_counts = (d_counts != nullptr);
 
-    CU(e->d_counts.need(sizeof(uint64_t) * n_pairs));
-    CU(e->d_first.need(sizeof(int32_t) * n_pairs));
+    e->out_counts_off = align256(16 + sizeof(unsigned long long) * ST_COUNT);
+    e->out_first_off = align256(e->out_counts_off + sizeof(uint64_t) * n_pairs);
+    e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
+    CU(e->d_out.need(e->out_bytes));
+    CU(e->h_out.need(e->out_bytes));
     CU(e->d_records.need(sizeof(Record) * (size_t)e->rec_cap));
-    CU(e->d_small.need(16 + sizeof(unsigned long long) * ST_COUNT));
     CU(e->d_cands.need(sizeof(Candidate) * (size_t)CAND_CAP));
+    if (st != e->stream) CU(cudaStreamWaitEvent(st, e->ev_b, 0));   // after the scenario upload + stage 1
 
     RunDev r{};
     r.seed = run->seed; r.trial_begin = run->trial_begin; r.trial_count = run->trial_count;
@@ -413,8 +465,10 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         e->h2d_run += bytes;
         r.replay = e->d_replay.as<Draw>();
     }
-    r.counts = d_counts ? reinterpret_cast<unsigned long long*>(d_counts) : e->d_counts.as<unsigned long long>();
-    r.first_conflict = e->d_first.as<int32_t>();
+    unsigned long long* own_counts =
+        reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + e->out_counts_off);
+    r.counts = d_counts ? reinterpret_cast<unsigned long long*>(d_counts) : own_counts;
+    r.first_conflict = reinterpret_cast<int32_t*>(e->d_out.as<unsigned char>() + e->out_first_off);
     r.records = e->d_records.as<Record>();
     r.rec_count = small_rec_count(e);
     r.rec_cap = e->rec_cap;
@@ -434,13 +488,15 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     }
 
     CU(cudaEventRecord(e->ev_begin, st));
-    if (!d_counts) CU(cudaMemsetAsync(e->d_counts.p, 0, sizeof(uint64_t) * n_pairs, st));
-    CU(cudaMemsetAsync(e->d_first.p, 0x7f, sizeof(int32_t) * n_pairs, st));   // 0x7f7f7f7f: "none" marker
-    CU(cudaMemsetAsync(e->d_small.p, 0, 16 + sizeof(unsigned long long) * ST_COUNT, st));
+    // one launch clears the whole output arena (counters, stats, counts) and sets first_conflict = INT32_MAX
+    k_run_init<<<(unsigned)((e->out_bytes / 4 + 255) / 256), 256, 0, st>>>(
+        e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4));
+    ++e->launches; ++e->launches_this_run;
+    CU(cudaGetLastError());
 
     // slices keep the item count of one launch below 2^30
     const bool exact = (run->precision == DCRP_PRECISION_FP64);
-    const uint64_t per_item = exact ? (uint64_t)EXB : (uint64_t)SCREEN_CH;
+    const uint64_t per_item = exact ? (uint64_t)EXB : (uint64_t)SCREEN2_CH;
     const uint64_t max_chunks = std::max<uint64_t>(1, MAX_ITEMS_PER_LAUNCH / n_pairs);
     const uint64_t slice_max = max_chunks * per_item;
     for (uint64_t first = 0; first < run->trial_count; first += slice_max) {
@@ -456,8 +512,8 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
             ++e->launches; ++e->launches_this_run;
             CU(cudaGetLastError());
         } else {
-            cudaError_t ce = r.replay ? launch_screen<true>(e, r, chunks, n_items, st)
-                                      : launch_screen<false>(e, r, chunks, n_items, st);
+            const cudaError_t ce = r.replay ? launch_screen2<true>(e, r, chunks, n_items, st)
+                                            : launch_screen2<false>(e, r, chunks, n_items, st);
             if (ce != cudaSuccess) return fail(DCRP_ERR_CUDA, "k_screen launch: %s", cudaGetErrorString(ce));
         }
     }
@@ -491,16 +547,16 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     cudaStream_t st = e->run_stream;
     const ScenarioDev& s = e->sd;
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
+    // one D2H copy of the whole output arena into its pinned mirror
+    CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, e->out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-
-    unsigned char small[16 + sizeof(unsigned long long) * ST_COUNT];
-    CU(cudaMemcpy(small, e->d_small.p, sizeof small, cudaMemcpyDeviceToHost));
+    const unsigned char* small = e->h_out.as<unsigned char>();
     uint32_t rec_count, cand_count;
     unsigned long long stats[ST_COUNT];
     std::memcpy(&rec_count, small, 4);
     std::memcpy(&cand_count, small + 4, 4);
     std::memcpy(stats, small + 16, sizeof stats);
-    uint64_t d2h = sizeof small;
+    uint64_t d2h = e->out_bytes;
 
     if (e->run.precision == DCRP_PRECISION_MIXED && cand_count > CAND_CAP) {
         // More candidates than the list holds (absurd hit rates, e.g. a huge radius):
@@ -516,17 +572,11 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     }
 
     if (res->counts && !e->external_counts) {
-        std::vector<uint64_t> h(n_pairs);
-        CU(cudaMemcpy(h.data(), e->d_counts.p, sizeof(uint64_t) * n_pairs, cudaMemcpyDeviceToHost));
+        const uint64_t* h = reinterpret_cast<const uint64_t*>(small + e->out_counts_off);
         for (size_t i = 0; i < n_pairs; ++i) res->counts[i] += h[i];     // accumulate, Drone.cpp:276
-        d2h += sizeof(uint64_t) * n_pairs;
     }
-    if (res->first_conflict) {
-        CU(cudaMemcpy(res->first_conflict, e->d_first.p, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n_pairs; ++i)
-            if (res->first_conflict[i] == 0x7f7f7f7f) res->first_conflict[i] = INT32_MAX;
-        d2h += sizeof(int32_t) * n_pairs;
-    }
+    if (res->first_conflict)
+        std::memcpy(res->first_conflict, small + e->out_first_off, sizeof(int32_t) * n_pairs);
     res->n_records = 0;
     res->overflow = rec_count > e->rec_cap ? 1 : 0;
     if (res->records) {
@@ -552,13 +602,24 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     dcrp_stats& o = res->stats;
     std::memset(&o, 0, sizeof o);
     o.trials = (uint64_t)n_pairs * e->run.trial_count;
-    o.tests_evaluated = stats[ST_EVALUATED];
+    // the kernels accumulate sum(t1st) (= stage-1 tests shared per pair) and the issued lane-steps;
+    // evaluated stage-2 tests and drone-steps follow from the track lengths
+    uint64_t all_tests = 0, all_steps = 0;
+    for (int a = 0; a < s.n_tracks; ++a) {
+        all_tests += (uint64_t)e->h_tracks[(size_t)a].n_steps * e->run.trial_count * (uint64_t)s.n_drones;
+        all_steps += (uint64_t)(e->h_tracks[(size_t)a].n_steps - 1) * e->run.trial_count * (uint64_t)s.n_drones;
+    }
     o.tests_shared = stats[ST_SHARED];
+    o.tests_evaluated = all_tests - stats[ST_SHARED];
     o.tests_issued = stats[ST_ISSUED];
-    o.drone_steps = stats[ST_STEPS];
+    o.drone_steps = all_steps;
     o.candidates = stats[ST_CANDIDATES];
     o.hits = stats[ST_HITS];
     o.kernel_launches = e->launches_this_run;
+    if (!e->prepare_timed) {
+        CU(cudaEventElapsedTime(&e->ms_prepare, e->ev_a, e->ev_b));
+        e->prepare_timed = true;
+    }
     o.ms_prepare = e->ms_prepare;
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_trials)); o.ms_trials = ms;
@@ -644,7 +705,7 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
 extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms_out)
 {
     if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
-    if (which < 0 || which > 3) return fail(DCRP_ERR_INVALID, "which must be 0..3");
+    if (which < 0 || which > 9) return fail(DCRP_ERR_INVALID, "which must be 0..9");
     CU(cudaSetDevice(e->device));
     const int threads = 256, blocks = e->prop.multiProcessorCount * 8;
     const int iters = 2048;
@@ -656,7 +717,13 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
             case 0: k_peak_ffma<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.999f, 0.001f); break;
             case 1: k_peak_ffma2<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.999f, 0.001f); break;
             case 2: k_peak_dfma<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<double>(), iters, 0.999, 0.001); break;
-            default: k_peak_scanmix<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 3: k_peak_scanmix<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 4: k_peak_variant<4><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 5: k_peak_variant<5><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 6: k_peak_variant<6><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 7: k_peak_variant<7><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 8: k_peak_variant<8><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            default: k_peak_variant<9><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
         }
         ++e->launches;
         CU(cudaGetLastError());
@@ -671,6 +738,8 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
     if (which == 0)      flops = lanes * iters * 16.0 * 8.0 * 2.0;
     else if (which == 1) flops = lanes * iters * 16.0 * 8.0 * 4.0;
     else if (which == 2) flops = lanes * iters * 16.0 * 8.0 * 2.0;
+    else if (which == 4 || which == 5) flops = lanes * iters * 8.0 * 9.0 * 4.0 * 2.0;   // packed add/mul: 2 flop
+    else if (which == 8) flops = lanes * iters * 8.0 * 16.0;                            // FMNMX3 count, not flops
     else                 flops = lanes * iters * 8.0 * 4.0 * 2.0 * 11.0;   // 2 tests per packed pair, 11 flop each
     *tflops = flops / ((double)best * 1e-3) * 1e-12;
     if (ms_out) *ms_out = best;

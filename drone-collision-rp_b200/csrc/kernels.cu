@@ -1,7 +1,7 @@
 // kernels.cu -- hand-written sm_100a kernels of the Monte-Carlo trial path.
 //
 //   k_stage1      once per scenario: stage-1 paths + per-(track,drone) stage-1 tables
-//   k_screen      every trial, fp32 packed (FFMA2/FADD2/FMUL2/FMNMX3): Philox draws,
+//   k_screen2     every trial, fp32 packed (FFMA2/FADD2/FMUL2/FMNMX3): Philox draws,
 //                 CTA-level binning by t1st, fp64->fp32 ray set-up, scan of the track
 //                 staged in shared memory by TMA bulk copies, warp-aggregated append
 //                 of the (rare) candidates
@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
     int first = INT_MAX;
     for (int i = 0; i < s.t_max; ++i) {
         if (i > 0) { x = DADD(x, d.z); y = DADD(y, d.w); }
-        if (a == 0) { s.p1x[(size_t)j * s.t_max + i] = x; s.p1y[(size_t)j * s.t_max + i] = y; }
+        if (a == 0) {
+            s.p1x[(size_t)j * s.t_max + i] = x; s.p1y[(size_t)j * s.t_max + i] = y;
+            s.p1f[(size_t)j * s.t_max + i] = make_float2((float)DSUB(x, s.ox), (float)DSUB(y, s.oy));
+        }
+        s.kink[(size_t)pair * s.t_max + i] = make_double2(DSUB(t.box[0], x), DSUB(t.box[2], y));
         if (i < t.takeoff_t && i < t.n_steps) {
             const double d2 = sep2(x, y, s.start_alt, s.ax[t.off + i], s.ay[t.off + i], s.az[t.off + i]);
             if (d2 < mn) mn = d2;
@@ -344,15 +348,15 @@ __device__ __forceinline__ void rescan_fp32(const ScenarioDev& s, const RunDev& 
                                             int pair, int a, int j, int s1_first, uint64_t trial,
                                             const Setup32& u)
 {
-    const float4* __restrict__ g = s.trk32 + 2 * (size_t)t.off;
+    const float4* __restrict__ g = s.trk32 + (size_t)t.off;
     const int last = u.t1st - 1;
     int first = (s1_first <= last) ? s1_first : -1;
     float mn = (float)__ldg(&s.s1_prefmin[(size_t)pair * s.t_max + last]);
     for (int i = u.t1st; i < t.n_steps; ++i) {
-        const float4 p = __ldg(&g[2 * i]), q = __ldg(&g[2 * i + 1]);
-        const float dx = fmaf(q.z, u.ray.sx, u.ray.bx) + p.x;
-        const float dy = fmaf(q.z, u.ray.sy, u.ray.by) + p.z;
-        const float dz = fmaf(q.z, u.ray.sz, u.ray.bz) + q.x;
+        const float4 p = __ldg(&g[i]);                  // (-ax, -ay, -az, i)
+        const float dx = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x;
+        const float dy = fmaf(p.w, u.ray.sy, u.ray.by) + p.y;
+        const float dz = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
         const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
         mn = fminf(mn, d2);
         if (d2 < s.thr2_fp32 && first < 0) first = i;
@@ -365,23 +369,68 @@ __device__ __forceinline__ void rescan_fp32(const ScenarioDev& s, const RunDev& 
     }
 }
 
-// Shared-memory plan of k_screen (dynamic):
-//   [0, 2*tile_bytes)            two track tiles (TMA destinations), tile_steps*32 B each
-//   stage[CH]  uint4             the chunk's trials, binned by t1st
-//   hist[80]   uint32            bucket histogram / bases (65 used)
-//   bars[2]    uint64            one mbarrier per tile buffer
-template <int K, int BLOCK, bool REPLAY>
-__global__ void __launch_bounds__(BLOCK, (K <= 4 ? 2 : 1))
-k_screen(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int tile_steps)
+// =========================================================================
+// k_screen2: the fp32 packed screen, balanced rounds
+// =========================================================================
+// Same contract as k_screen (every trial screened conservatively in fp32, rare
+// candidates appended), restructured after the first ncu profile
+// (profiles/r01_*): per item a CTA bins CH = BLOCK*2*R trials by t1st, then every
+// warp runs R rounds of (set up 2 trials per lane -> scan them as ONE packed
+// pair).  Round pairs take complementary bins (short scan + long scan), so all
+// warps of a CTA do the same amount of scan work per item and do not wait for
+// each other at the next barrier; one pair in flight keeps the kernel at <= 48
+// registers so 5 CTAs of 256 threads overlap their integer (Philox/binning),
+// fp64/conversion (set-up) and FMA-pipe (scan) phases on one SM.
+struct Fast32 {
+    float bx, by, bz, sx, sy, sz;
+    int32_t t1st;
+    bool force;
+};
+
+__device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const TrackDev* __restrict__ tk, int pair,
+                                               int j, int s1_first, const uint4 q, float zlf)
 {
-    static_assert(K % 2 == 0, "trials are processed as packed f32x2 pairs");
+    const double wx32 = __ldg(&tk->wx32), wy32 = __ldg(&tk->wy32);
+    const float wz32 = __ldg(&tk->wz32), z0rel = __ldg(&tk->z0rel);
+    Fast32 o;
+    o.t1st = (int32_t)(q.w >> 12);
+    const int last = o.t1st - 1;
+    const double2 kk = __ldg(&s.kink[(size_t)pair * s.t_max + last]);
+    const float2 pl = __ldg(&s.p1f[(size_t)j * s.t_max + last]);
+    // target - kink: one fp64 FMA per coordinate, rounded once to fp32
+    const float dls = (float)fma((double)q.x, wx32, kk.x);
+    const float dbs = (float)fma((double)q.y, wy32, kk.y);
+    const float ada = fabsf(fmaf((float)q.z, wz32, z0rel));
+    const float m2 = fmaf(dls, dls, dbs * dbs);
+    const float inv_m = rsqrtf(m2);
+    const float inv_n = rsqrtf(fmaf(ada, ada, m2));
+    const float pitch = atanf(ada * inv_m);
+    const float vf = fmaf(-s.coef_f, pitch, s.v_straight_f);
+    const float lastf = (float)last;
+    o.sx = dls * inv_m * vf;
+    o.sy = dbs * inv_m * vf;
+    o.sz = ada * inv_n * vf;
+    o.bx = fmaf(-lastf, o.sx, pl.x);
+    o.by = fmaf(-lastf, o.sy, pl.y);
+    o.bz = fmaf(-lastf, o.sz, zlf);
+    o.force = !(m2 > 1e-12f) || (s1_first <= last);
+    return o;
+}
+
+template <int R, int BLOCK, bool REPLAY>
+__global__ void __launch_bounds__(BLOCK, 1280 / BLOCK)
+k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int tile_steps,
+          uint32_t stagger_ns, uint32_t dbg)
+{
+    constexpr int K = 2 * R;                 // trials per thread per item
     constexpr int CH = K * BLOCK;
-    constexpr int NP = K / 2;
+    constexpr int NW = BLOCK / 32;
+    static_assert(R % 2 == 0, "rounds come in complementary (long, short) pairs");
     static_assert(CH <= 4096, "local trial index is packed in 12 bits");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4*   tiles = reinterpret_cast<float4*>(smem_raw);
-    uint4*    stage = reinterpret_cast<uint4*>(smem_raw + (size_t)2 * tile_steps * 32);
+    uint4*    stage = reinterpret_cast<uint4*>(smem_raw + (size_t)2 * tile_steps * 16);
     uint32_t* hist  = reinterpret_cast<uint32_t*>(stage + CH);
     uint64_t* bars  = reinterpret_cast<uint64_t*>(hist + 80);
 
@@ -390,176 +439,202 @@ k_screen(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
 
-    uint32_t phase0 = 0, phase1 = 0;      // mbarrier parities (uniform across the CTA)
-    int loaded_track = -1;                // track whose single tile sits in buffer 0
-    unsigned long long ev = 0, sh = 0, is = 0, st = 0, ncand = 0;
+    uint32_t phase0 = 0, phase1 = 0;
+    int loaded_track = -1;
+    uint32_t acc_t1 = 0, acc_is = 0, ncand = 0;   // sum of t1st / issued lane-steps (flushed before overflow)
+
+    // CTAs co-resident on an SM all start at once and, doing identical work per item, would stay in
+    // phase (all in the integer/set-up phases together, then all fighting for the FMA pipe).  Offset
+    // the k-th CTA of an SM by k/occupancy of an item so that scans overlap the other phases.
+    if (stagger_ns) __nanosleep(stagger_ns * (blockIdx.x / s.n_sm));
 
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int pair = item / chunks_per_pair;
         const uint32_t c = item - pair * chunks_per_pair;
         const int a = pair / s.n_drones, j = pair - a * s.n_drones;
-        const TrackDev t = s.tracks[a];
-        const int VL = t.n_steps;
+        const TrackDev* __restrict__ tk = s.tracks + a;
+        const int VL = __ldg(&tk->n_steps);
+        const int takeoff_t = __ldg(&tk->takeoff_t);
         const int n_tiles = (VL + tile_steps - 1) / tile_steps;
-        const uint64_t chunk_first64 = r.slice_first + (uint64_t)c * CH;  // first local trial of the chunk
+        const uint64_t chunk_first64 = r.slice_first + (uint64_t)c * CH;
         const uint32_t n_valid = (uint32_t)min((uint64_t)CH, r.slice_count - (uint64_t)c * CH);
         const int s1_first = __ldg(&s.s1_first_hit[pair]);
-        const float4* __restrict__ gtrk = s.trk32 + 2 * (size_t)t.off;
+        const float4* __restrict__ gtrk = s.trk32 + (size_t)__ldg(&tk->off);
+
+        if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {        // rare: keep the 32-bit partial sums exact
+            atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
+            atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
+            acc_t1 = acc_is = 0;
+        }
 
         // ---------------- phase A: draws + histogram over t1st buckets
         for (int h = tid; h < 80; h += BLOCK) hist[h] = 0;
-        __syncthreads();      // also: every thread is done with the previous item's stage[] and tiles
+        __syncthreads();      // every thread is done with the previous item's stage[] and tiles
 
-        const bool need_load = !(n_tiles == 1 && loaded_track == a);
-        if (need_load && tid == 0) {
+        const bool single = (n_tiles == 1);
+        const bool need_load = !(single && loaded_track == a);
+        if (single && need_load && tid == 0) {
             fence_proxy_async();
-            const uint32_t b0 = (uint32_t)min(VL, tile_steps) * 32u;
+            const uint32_t b0 = (uint32_t)VL * 16u;
             mbar_arrive_expect_tx(&bars[0], b0);
             tma_bulk_g2s(tiles, gtrk, b0, &bars[0]);
-            if (n_tiles > 1) {
-                const uint32_t b1 = (uint32_t)min(VL - tile_steps, tile_steps) * 32u;
-                mbar_arrive_expect_tx(&bars[1], b1);
-                tma_bulk_g2s(tiles + 2 * (size_t)tile_steps, gtrk + 2 * (size_t)tile_steps, b1, &bars[1]);
-            }
         }
 
-        uint32_t w1[K], w2[K], w3[K], meta[K], rank[K];
+        {
+            uint32_t w1[K], w2[K], w3[K], meta[K], rank[K];
 #pragma unroll
-        for (int m = 0; m < K; ++m) {
-            const uint32_t local = (uint32_t)(m * BLOCK + tid);
-            uint32_t bucket = 64u;         // dead trials (past the end of the range) sort last
-            meta[m] = local;               // t1st == 0 marks a dead trial
-            w1[m] = w2[m] = w3[m] = 0u;
-            if (local < n_valid) {
-                int32_t t1st;
-                if (REPLAY) {
-                    t1st = r.replay[(size_t)pair * r.trial_count + chunk_first64 + local].t1st;
-                } else {
-                    const U4 w = trial_words(r.seed, r.trial_begin + chunk_first64 + local,
-                                             r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a);
-                    t1st = draw_t1st(w.x, t.takeoff_t);
-                    w1[m] = w.y; w2[m] = w.z; w3[m] = w.w;
-                }
-                bucket = (uint32_t)(t1st - 1) >> s.bucket_shift;
-                meta[m] = local | ((uint32_t)t1st << 12);
-            }
-            rank[m] = atomicAdd(&hist[bucket], 1u) | (bucket << 16);
-        }
-        __syncthreads();
-        if (warp == 0) {                   // exclusive scan of the 65 bucket counts
-            const uint32_t v0 = hist[lane], v1 = hist[lane + 32];
-            uint32_t i0 = v0, i1 = v1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u0 = __shfl_up_sync(0xffffffffu, i0, o);
-                const uint32_t u1 = __shfl_up_sync(0xffffffffu, i1, o);
-                if (lane >= o) { i0 += u0; i1 += u1; }
-            }
-            const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
-            const uint32_t tot1 = __shfl_sync(0xffffffffu, i1, 31);
-            hist[lane] = i0 - v0;
-            hist[lane + 32] = tot0 + i1 - v1;
-            if (lane == 0) hist[64] = tot0 + tot1;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int m = 0; m < K; ++m) {
-            const uint32_t slot = hist[rank[m] >> 16] + (rank[m] & 0xffffu);
-            stage[slot] = make_uint4(w1[m], w2[m], w3[m], meta[m]);
-        }
-        __syncthreads();
-
-        // ---------------- phase B: set-up of this thread's K binned trials
-        float2 BX[NP], BY[NP], BZ[NP], SX[NP], SY[NP], SZ[NP];
-        int tmin = INT_MAX;
-        bool force = false;
-        const uint32_t slot0 = (uint32_t)(warp * 32 * K + lane);
-#pragma unroll
-        for (int m = 0; m < K; ++m) {
-            const uint4 q = stage[slot0 + m * 32];
-            float bx = 1e15f, by = 1e15f, bz = 1e15f, sx = 0.f, sy = 0.f, sz = 0.f;
-            if ((q.w >> 12) != 0u) {
-                const Setup32 u = setup_trial32(s, r, t, pair, j, s1_first, chunk_first64, q);
-                bx = u.ray.bx; by = u.ray.by; bz = u.ray.bz;
-                sx = u.ray.sx; sy = u.ray.sy; sz = u.ray.sz;
-                force |= u.force;
-                tmin = min(tmin, u.t1st);
-                ev += (unsigned long long)(VL - u.t1st);
-                sh += (unsigned long long)u.t1st;
-                st += (unsigned long long)(VL - 1);
-            }
-            if (m & 1) { BX[m >> 1].y = bx; BY[m >> 1].y = by; BZ[m >> 1].y = bz;
-                         SX[m >> 1].y = sx; SY[m >> 1].y = sy; SZ[m >> 1].y = sz; }
-            else       { BX[m >> 1].x = bx; BY[m >> 1].x = by; BZ[m >> 1].x = bz;
-                         SX[m >> 1].x = sx; SY[m >> 1].x = sy; SZ[m >> 1].x = sz; }
-        }
-        const int imin = __reduce_min_sync(0xffffffffu, tmin);   // warp-uniform scan start
-        if (imin < VL) is += (unsigned long long)(VL - imin) * K;
-
-        // ---------------- scan: d2(i) = |b + i*s - a_i|^2, running min over i and the K trials
-        float mn = 3.0e38f;
-        for (int tl = 0; tl < n_tiles; ++tl) {
-            const int buf = tl & 1;
-            if (need_load) {
-                if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
-                else          { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
-            }
-            const int t0 = tl * tile_steps;
-            const int lo = max(imin, t0), hi = min(VL, t0 + tile_steps);
-            const float4* __restrict__ tp = tiles + 2 * (size_t)buf * tile_steps - 2 * (size_t)t0;
-#pragma unroll 4
-            for (int i = lo; i < hi; ++i) {
-                const float4 p = tp[2 * i];          // (-ax,-ax,-ay,-ay)
-                const float4 q = tp[2 * i + 1];      // (-az,-az,  i,  i)
-                const float2 nax = make_float2(p.x, p.y), nay = make_float2(p.z, p.w);
-                const float2 naz = make_float2(q.x, q.y), fi = make_float2(q.z, q.w);
-#pragma unroll
-                for (int pp = 0; pp < NP; ++pp) {
-                    const float2 dx = fadd2(ffma2(fi, SX[pp], BX[pp]), nax);
-                    const float2 dy = fadd2(ffma2(fi, SY[pp], BY[pp]), nay);
-                    const float2 dz = fadd2(ffma2(fi, SZ[pp], BZ[pp]), naz);
-                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
-                    mn = fmin3(mn, d2.x, d2.y);
-                }
-            }
-            if (tl + 2 < n_tiles) {                  // recycle this buffer for tile tl+2
-                __syncthreads();
-                if (tid == 0) {
-                    fence_proxy_async();
-                    const int tn = (tl + 2) * tile_steps;
-                    const uint32_t bn = (uint32_t)min(VL - tn, tile_steps) * 32u;
-                    mbar_arrive_expect_tx(&bars[buf], bn);
-                    tma_bulk_g2s(tiles + 2 * (size_t)buf * tile_steps, gtrk + 2 * (size_t)tn, bn, &bars[buf]);
-                }
-            }
-        }
-        loaded_track = (n_tiles == 1) ? a : -1;
-
-        // ---------------- rare path: hand the thread's trials on
-        const float thr = r.decide_fp32 ? s.thr2_fp32 : s.thr2_screen;
-        if (force || mn < thr) {
-#pragma unroll 1
             for (int m = 0; m < K; ++m) {
-                const uint4 q = stage[slot0 + m * 32];
-                if ((q.w >> 12) == 0u) continue;
-                const uint64_t trial = r.trial_begin + chunk_first64 + (q.w & 4095u);
-                if (!r.decide_fp32) {
-                    ++ncand;
-                    const uint32_t slot = warp_claim_slot(r.cand_count);
-                    if (slot < r.cand_cap) {
-                        Candidate cd; cd.pair = (uint32_t)pair; cd.pad = 0; cd.trial = trial;
-                        r.cands[slot] = cd;
+                const uint32_t local = (uint32_t)(m * BLOCK + tid);
+                uint32_t bucket = 64u;
+                meta[m] = local;
+                w1[m] = w2[m] = w3[m] = 0u;
+                if (local < n_valid) {
+                    int32_t t1st;
+                    if (REPLAY) {
+                        t1st = r.replay[(size_t)pair * r.trial_count + chunk_first64 + local].t1st;
+                    } else if (dbg & 4u) {      // profiling aid: no Philox (results meaningless)
+                        const uint32_t h = (uint32_t)(chunk_first64 + local) * 2654435761u;
+                        t1st = draw_t1st(h, takeoff_t);
+                        w1[m] = h ^ 0x9e3779b9u; w2[m] = h * 40503u; w3[m] = h + 0x7f4a7c15u;
+                    } else {
+                        const U4 w = trial_words(r.seed, r.trial_begin + chunk_first64 + local,
+                                                 r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a);
+                        t1st = draw_t1st(w.x, takeoff_t);
+                        w1[m] = w.y; w2[m] = w.z; w3[m] = w.w;
                     }
-                } else {
-                    const Setup32 u = setup_trial32(s, r, t, pair, j, s1_first, chunk_first64, q);
-                    rescan_fp32(s, r, t, pair, a, j, s1_first, trial, u);
+                    bucket = (uint32_t)(t1st - 1) >> s.bucket_shift;
+                    meta[m] = local | ((uint32_t)t1st << 12);
+                }
+                rank[m] = atomicAdd(&hist[bucket], 1u) | (bucket << 16);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t v0 = hist[lane], v1 = hist[lane + 32];
+                uint32_t i0 = v0, i1 = v1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u0 = __shfl_up_sync(0xffffffffu, i0, o);
+                    const uint32_t u1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) { i0 += u0; i1 += u1; }
+                }
+                const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                const uint32_t tot1 = __shfl_sync(0xffffffffu, i1, 31);
+                hist[lane] = i0 - v0;
+                hist[lane + 32] = tot0 + i1 - v1;
+                if (lane == 0) hist[64] = tot0 + tot1;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < K; ++m) {
+                const uint32_t slot = hist[rank[m] >> 16] + (rank[m] & 0xffffu);
+                stage[slot] = make_uint4(w1[m], w2[m], w3[m], meta[m]);
+            }
+        }
+        __syncthreads();
+
+        if (single && need_load) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
+        loaded_track = single ? a : -1;
+
+        const float zlf = (float)(s.start_alt - s.oz);
+        const float thr = r.decide_fp32 ? s.thr2_fp32 : s.thr2_screen;
+
+        // ---------------- R rounds: set up one packed pair, scan it
+#pragma unroll 1
+        for (int rd = 0; rd < R; ++rd) {
+            // 64-trial bins in ascending t1st order; rounds (2q, 2q+1) take bins b and its mirror
+            const int q2 = rd >> 1;
+            const int bin = (rd & 1) ? (q2 * 2 * NW + 2 * NW - 1 - warp) : (q2 * 2 * NW + warp);
+            const uint32_t slot0 = (uint32_t)(bin * 64 + lane);
+            float2 BX, BY, BZ, SX, SY, SZ;
+            int tmin = INT_MAX;
+            bool force = false;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const uint4 q = stage[slot0 + m * 32];
+                float bx = 1e15f, by = 1e15f, bz = 1e15f, sx = 0.f, sy = 0.f, sz = 0.f;
+                if ((q.w >> 12) != 0u) {
+                    int32_t t1;
+                    if (REPLAY) {
+                        const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
+                        bx = u.ray.bx; by = u.ray.by; bz = u.ray.bz; sx = u.ray.sx; sy = u.ray.sy; sz = u.ray.sz;
+                        force |= u.force; t1 = u.t1st;
+                    } else if (dbg & 2u) {      // profiling aid: no ray set-up (results meaningless)
+                        bx = __uint_as_float(q.x >> 9); by = __uint_as_float(q.y >> 9); bz = 50.f;
+                        sx = 1.f; sy = 2.f; sz = 3.f; t1 = (int32_t)(q.w >> 12);
+                    } else {
+                        const Fast32 u = setup_fast32(s, tk, pair, j, s1_first, q, zlf);
+                        bx = u.bx; by = u.by; bz = u.bz; sx = u.sx; sy = u.sy; sz = u.sz;
+                        force |= u.force; t1 = u.t1st;
+                    }
+                    tmin = min(tmin, t1);
+                    acc_t1 += (uint32_t)t1;
+                }
+                if (m) { BX.y = bx; BY.y = by; BZ.y = bz; SX.y = sx; SY.y = sy; SZ.y = sz; }
+                else   { BX.x = bx; BY.x = by; BZ.x = bz; SX.x = sx; SY.x = sy; SZ.x = sz; }
+            }
+            const int imin = __reduce_min_sync(0xffffffffu, tmin);
+            if (imin < VL) acc_is += (uint32_t)(VL - imin) * 2u;
+
+            float mn0 = 3.0e38f, mn1 = 3.0e38f;
+            for (int tl = 0; tl < n_tiles; ++tl) {
+                const int buf = single ? 0 : (tl & 1);
+                if (!single) {
+                    // long tracks: stream the tiles through both buffers, one CTA-wide hand-over per tile
+                    __syncthreads();
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        const int tn = tl * tile_steps;
+                        const uint32_t bn = (uint32_t)min(VL - tn, tile_steps) * 16u;
+                        mbar_arrive_expect_tx(&bars[buf], bn);
+                        tma_bulk_g2s(tiles + (size_t)buf * tile_steps, gtrk + (size_t)tn, bn, &bars[buf]);
+                    }
+                    if (buf == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
+                    else          { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
+                }
+                const int t0 = tl * tile_steps;
+                const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(VL, t0 + tile_steps);   // dbg 1: no scan
+                const float4* __restrict__ tp = tiles + (size_t)buf * tile_steps - (size_t)t0;
+                // one broadcast LDS.128 per index: (-ax, -ay, -az, i).  The {v, v} pairs below cost
+                // nothing: ptxas folds them into the packed ops' scalar-broadcast operand form
+                // (FFMA2 R, R.F32, R.F32x2, R.F32x2).
+#pragma unroll 4
+                for (int i = lo; i < hi; ++i) {
+                    const float4 p = tp[i];
+                    const float2 fi = make_float2(p.w, p.w);
+                    const float2 dx = fadd2(ffma2(fi, SX, BX), make_float2(p.x, p.x));
+                    const float2 dy = fadd2(ffma2(fi, SY, BY), make_float2(p.y, p.y));
+                    const float2 dz = fadd2(ffma2(fi, SZ, BZ), make_float2(p.z, p.z));
+                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                    mn0 = fminf(mn0, d2.x);
+                    mn1 = fminf(mn1, d2.y);
+                }
+            }
+
+            // ---------------- rare path: hand the two trials on
+            if (force || fminf(mn0, mn1) < thr) {
+#pragma unroll 1
+                for (int m = 0; m < 2; ++m) {
+                    const uint4 q = stage[slot0 + m * 32];
+                    if ((q.w >> 12) == 0u) continue;
+                    const uint64_t trial = r.trial_begin + chunk_first64 + (q.w & 4095u);
+                    if (!r.decide_fp32) {
+                        ++ncand;
+                        const uint32_t slot = warp_claim_slot(r.cand_count);
+                        if (slot < r.cand_cap) {
+                            Candidate cd; cd.pair = (uint32_t)pair; cd.pad = 0; cd.trial = trial;
+                            r.cands[slot] = cd;
+                        }
+                    } else {
+                        const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
+                        rescan_fp32(s, r, *tk, pair, a, j, s1_first, trial, u);
+                    }
                 }
             }
         }
     }
-    flush_stats(r, ev, sh, is, st, 0);
-    ncand = warp_sum_u64(ncand);
-    if (lane == 0 && ncand) atomicAdd(&r.stats[ST_CANDIDATES], ncand);
+    flush_stats(r, 0, acc_t1, acc_is, 0, 0);
+    const unsigned long long nc = warp_sum_u64(ncand);
+    if (lane == 0 && nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
 }
 
 // =========================================================================
@@ -681,6 +756,80 @@ __global__ void __launch_bounds__(256) k_peak_scanmix(float* out, int iters, flo
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = mn;
+}
+
+// Variants of the scan mix that isolate one instruction class each (profiling aid):
+//   V=4 FADD2 only   V=5 FMUL2 only   V=6 mix with LOP3 instead of FMNMX3
+//   V=7 mix with 2 x FMNMX instead of FMNMX3   V=8 FMNMX3 only   V=9 the mix unpacked (scalar)
+template <int V>
+__global__ void __launch_bounds__(256) k_peak_variant(float* out, int iters, float s0, float a0)
+{
+    float2 B[4], S[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        B[k] = make_float2(threadIdx.x * 0.5f + k, threadIdx.x * 0.25f - k);
+        S[k] = make_float2(s0 + k, s0 - k);
+    }
+    float2 fi = make_float2(0.f, 0.f);
+    const float2 one = make_float2(1.f, 1.f), na = make_float2(a0, a0);
+    float mn = 3.0e38f, mn2 = 2.0e38f;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (V == 4 || V == 5) {
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) B[k] = (V == 4) ? fadd2(B[k], S[k]) : fmul2(B[k], S[k]);
+                }
+            } else if (V == 8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    B[k].x = fmin3(B[k].x, S[k].x, S[k].y);
+                    B[k].y = fmin3(B[k].y, S[k].y, B[k].x);
+                    S[k].x = fmin3(S[k].x, B[k].y, mn);
+                    S[k].y = fmin3(S[k].y, B[k].x, mn2);
+                }
+            } else if (V == 9) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float dx0 = fmaf(fi.x, S[k].x, B[k].x) + na.x, dx1 = fmaf(fi.y, S[k].y, B[k].y) + na.y;
+                    const float dy0 = fmaf(fi.x, S[k].x, B[(k + 1) & 3].x) + na.x;
+                    const float dy1 = fmaf(fi.y, S[k].y, B[(k + 1) & 3].y) + na.y;
+                    const float dz0 = fmaf(fi.x, S[(k + 1) & 3].x, B[k].x) + na.x;
+                    const float dz1 = fmaf(fi.y, S[(k + 1) & 3].y, B[k].y) + na.y;
+                    const float d0 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0));
+                    const float d1 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
+                    mn = fmin3(mn, d0, d1);
+                }
+                fi = fadd2(fi, one);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 dx = fadd2(ffma2(fi, S[k], B[k]), na);
+                    const float2 dy = fadd2(ffma2(fi, S[k], B[(k + 1) & 3]), na);
+                    const float2 dz = fadd2(ffma2(fi, S[(k + 1) & 3], B[k]), na);
+                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                    if (V == 6) acc ^= __float_as_uint(d2.x) ^ __float_as_uint(d2.y);
+                    else { mn = fminf(mn, d2.x); mn2 = fminf(mn2, d2.y); }
+                }
+                fi = fadd2(fi, one);
+            }
+        }
+    }
+    float r = mn + mn2 + __uint_as_float(acc & 0x3fffffffu);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r += B[k].x + B[k].y + S[k].x + S[k].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// Clears a run's output arena: words [0, first_off) = 0 (counters, stats, counts),
+// words [first_off, n) = INT32_MAX (first-conflict index "none").
+__global__ void __launch_bounds__(256) k_run_init(uint32_t* out, uint32_t first_off, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (i < first_off) ? 0u : 0x7fffffffu;
 }
 
 __global__ void __launch_bounds__(256) k_fill(float4* p, size_t n, float v)

@@ -208,7 +208,9 @@ int  dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uint32_t n_re
 /* ---- measurement -------------------------------------------------------- */
 /* Device peak of an FFMA-only (which=0), packed FFMA2-only (1), DFMA-only (2)
  * or the scan loop's own FP instruction mix (3) micro-kernel, in TFLOP/s
- * (FMA = 2 flop): the roofline denominators MEASURED_PEAKS.json lacks. */
+ * (FMA = 2 flop): the roofline denominators MEASURED_PEAKS.json lacks.
+ * which = 4..9 are profiling variants of the mix (FADD2 only, FMUL2 only, mix
+ * with LOP3 / 2xFMNMX instead of FMNMX3, FMNMX3 only [Ginstr/s], unpacked mix). */
 int  dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms);
 /* Writes `bytes` of a scratch buffer (L2 flush between timed iterations). */
 int  dcrp_flush_l2(dcrp_engine* e, void* stream);

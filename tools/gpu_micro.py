@@ -1,0 +1,19 @@
+"""Pipe micro-benchmarks (dcrp_measure_peak 0..9) -> gpurun_out/micro.json."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from drone_collision_rp_b200 import capi
+
+names = ["ffma", "ffma2", "dfma", "scan_mix", "fadd2_only", "fmul2_only", "mix_lop3_instead_of_fmnmx3",
+         "mix_2xfmnmx", "fmnmx3_only_ginstr", "mix_unpacked"]
+eng = capi.Engine(0)
+out = {}
+for which, name in enumerate(names):
+    tf, ms = eng.measure_peak(which)
+    out[name] = {"tflops_or_ginstr": tf, "ms": ms}
+    print("%-32s %8.3f  (%.3f ms)" % (name, tf, ms), flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "micro.json"), "w"), indent=1)
