@@ -31,4 +31,4 @@ def build_native(verbose=False):
 
 from . import capi  # noqa: E402
 from . import scenario  # noqa: E402
-from .capi import DcrpError, Engine  # noqa: E402,F401
+from .capi import DcrpError, Engine, Scenario  # noqa: E402,F401

@@ -192,6 +192,15 @@ class RunResult:
         return int(self.counts.sum())
 
 
+class Scenario:
+    """Tracks + drones marshalled once into the C structs of include/dcrp.h (keeps the
+    numpy arrays the structs point into alive).  Pass it wherever (tracks, drones) go."""
+
+    def __init__(self, tracks, drones):
+        self.T, self.D, self._keep = Engine._pack(tracks, drones)
+        self.n_tracks, self.n_drones = len(self.T), len(self.D)
+
+
 class Engine:
     """One dcrp_engine on one CUDA device."""
 
@@ -250,8 +259,8 @@ class Engine:
     def _result_buffers(self, n_pairs, run):
         cap = run.record_capacity or (1 << 16)
         counts = np.zeros(n_pairs, dtype=np.uint64)
-        first = np.zeros(n_pairs, dtype=np.int32)
-        recs = np.zeros(cap, dtype=RECORD_DTYPE)
+        first = np.empty(n_pairs, dtype=np.int32)
+        recs = np.empty(cap, dtype=RECORD_DTYPE)
         res = Result()
         res.counts = counts.ctypes.data_as(C.POINTER(C.c_uint64))
         res.first_conflict = first.ctypes.data_as(C.POINTER(C.c_int32))
@@ -272,10 +281,14 @@ class Engine:
         return RunResult(counts, first, recs[:res.n_records].copy(), bool(res.overflow), res.stats.as_dict(), per)
 
     # ---- the ABI
-    def simulate(self, tracks, drones, seed=20170630, trial_begin=0, trial_count=10000, precision=MIXED,
+    def simulate(self, tracks, drones=None, seed=20170630, trial_begin=0, trial_count=10000, precision=MIXED,
                  flags=0, record_capacity=0, replay=None, model=None, track_id_base=0, drone_id_base=0):
-        """dcrp_simulate: host buffers in, host buffers out (blocking)."""
-        T, D, keep = self._pack(tracks, drones)
+        """dcrp_simulate: host buffers in, host buffers out (blocking).  `tracks` may be a
+        Scenario (then `drones` is ignored)."""
+        if isinstance(tracks, Scenario):
+            T, D = tracks.T, tracks.D
+        else:
+            T, D, keep = self._pack(tracks, drones)
         m = model or default_model()
         run = self._run_struct(seed, trial_begin, trial_count, precision, flags, record_capacity, replay,
                                track_id_base, drone_id_base)
@@ -285,8 +298,11 @@ class Engine:
         self.n_tracks, self.n_drones = len(T), len(D)
         return self._wrap(res, counts, first, recs, per, n_pairs, run.trial_count)
 
-    def upload(self, tracks, drones, model=None):
-        T, D, keep = self._pack(tracks, drones)
+    def upload(self, tracks, drones=None, model=None):
+        if isinstance(tracks, Scenario):
+            T, D = tracks.T, tracks.D
+        else:
+            T, D, keep = self._pack(tracks, drones)
         m = model or default_model()
         _check(lib().dcrp_scenario_upload(self._h, T, len(T), D, len(D), C.byref(m)))
         self.n_tracks, self.n_drones = len(T), len(D)

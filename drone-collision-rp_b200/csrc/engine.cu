@@ -84,10 +84,7 @@ struct PinnedBuf {         // grow-only pinned host buffer (async copies need pa
 static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // screen kernel configuration: 256 threads, 2 rounds x 2 trials per thread per item,
-// 5 CTAs per SM
-constexpr int SCREEN2_R = 2;
-constexpr int SCREEN2_BLOCK = 256;
-constexpr int SCREEN2_CH = 2 * SCREEN2_R * SCREEN2_BLOCK;
+// 4 CTAs per SM (63 registers, no spills): best of the sweep in profiles/r01_screen_cfg_sweep.txt
 constexpr uint32_t DEFAULT_RECORD_CAP = 1u << 16;
 constexpr uint32_t CAND_CAP = 1u << 22;
 constexpr uint64_t MAX_ITEMS_PER_LAUNCH = 1ull << 30;
@@ -310,9 +307,14 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         while (std::sqrt(c) < s.radius) c = std::nextafter(c, INFINITY);
         s.thr_d2 = c;
     }
-    // fp32 screen: per-coordinate error <= ~2 ulp32(extent) + i*|s|*2^-24; the
-    // margin below is >= 8x that bound.
-    const double margin = 0.02 + 32.0 * (double)ulp32_of(extent) +
+    // fp32 screen error budget per coordinate (DESIGN.md "screen margin"): the scan accumulates
+    // P += S for at most tile_steps indices between exact re-bases (<= tile_steps/2 ulp), plus one
+    // rounding each for the re-based start, the recentred track sample and the difference, plus the
+    // set-up (target-kink rounded once from fp64: relative 2^-24 of the flown distance).  The margin
+    // is that bound times sqrt(3) for the 3-D distance, plus a 0.02 m floor.
+    const int screen_tile = vl_max <= 128 ? 128 : 512;
+    const double ulp = (double)ulp32_of(extent);
+    const double margin = 0.02 + 1.7321 * (0.5 * screen_tile + 4.0) * ulp +
                           (double)vl_max * model->v_straight * std::ldexp(1.0, -22);
     s.thr2_screen = std::nextafterf((float)((s.radius + margin) * (s.radius + margin)), INFINITY);
     s.thr2_fp32 = (float)(s.radius * s.radius);
@@ -393,34 +395,60 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 }
 
 // ------------------------------------------------------------------ run
-template <bool REPLAY>
+// One instantiation of the screen kernel: R rounds x 2 trials per thread per item, BLOCK threads,
+// at least MINB CTAs per SM.
+struct ScreenCfg {
+    int rounds, block, minb;
+    const void* kern[2];          // [REPLAY]
+    size_t configured_smem[2];
+    int occ[2];
+};
+template <int R, int BLOCK, int MINB>
+static ScreenCfg make_cfg()
+{
+    ScreenCfg c{R, BLOCK, MINB, {(const void*)k_screen2<R, BLOCK, false, MINB>,
+                                 (const void*)k_screen2<R, BLOCK, true, MINB>}, {0, 0}, {0, 0}};
+    return c;
+}
+// [0] is the production configuration; the others exist for the tuning sweep
+// (tools/profile_target.py with DCRP_SCREEN_CFG=n) and cost nothing unless selected.
+static ScreenCfg g_cfgs[] = {make_cfg<2, 256, 4>(), make_cfg<2, 256, 5>(), make_cfg<2, 512, 2>(),
+                             make_cfg<2, 128, 10>()};
+static ScreenCfg& screen_cfg()
+{
+    static const int sel = std::getenv("DCRP_SCREEN_CFG") ? std::atoi(std::getenv("DCRP_SCREEN_CFG")) : 0;
+    const int n = (int)(sizeof g_cfgs / sizeof g_cfgs[0]);
+    return g_cfgs[(sel >= 0 && sel < n) ? sel : 0];
+}
+static uint64_t screen_chunk() { const ScreenCfg& c = screen_cfg(); return (uint64_t)2 * c.rounds * c.block; }
+
 static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                                   cudaStream_t st)
 {
-    auto kern = k_screen2<SCREEN2_R, SCREEN2_BLOCK, REPLAY>;
-    const int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
-    const size_t smem = (size_t)2 * tile_steps * 16 + (size_t)SCREEN2_CH * 16 + 80 * 4 + 16;
-    static size_t configured[2] = {0, 0};
-    static int occ_cache[2] = {0, 0};
-    const int v = REPLAY ? 1 : 0;
-    if (configured[v] != smem) {
-        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ScreenCfg& c = screen_cfg();
+    const int v = r.replay ? 1 : 0;
+    int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
+    const size_t smem = (size_t)2 * tile_steps * 16 + (size_t)screen_chunk() * 16 + 80 * 4 + 16;
+    if (c.configured_smem[v] != smem) {
+        cudaError_t ce = cudaFuncSetAttribute(c.kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache[v], kern, SCREEN2_BLOCK, smem);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.occ[v], c.kern[v], c.block, smem);
         if (ce != cudaSuccess) return ce;
-        if (occ_cache[v] < 1) occ_cache[v] = 1;
-        configured[v] = smem;
+        if (c.occ[v] < 1) c.occ[v] = 1;
+        c.configured_smem[v] = smem;
     }
-    const uint32_t grid =
-        (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ_cache[v]);
-    // stagger: an item (CH trials) takes ~CH * 30 ns / occupancy-share; offset co-resident CTAs by 1/occ of it
-    static const int stagger_env = std::getenv("DCRP_STAGGER_NS") ? std::atoi(std::getenv("DCRP_STAGGER_NS")) : -1;
-    const uint32_t stagger_ns = stagger_env >= 0 ? (uint32_t)stagger_env
-                                                 : (grid > (uint32_t)e->prop.multiProcessorCount ? 6000u : 0u);
+    static const int cta_cap = std::getenv("DCRP_MAX_CTAS") ? std::atoi(std::getenv("DCRP_MAX_CTAS")) : 0;
+    const int occ = (cta_cap > 0 && cta_cap < c.occ[v]) ? cta_cap : c.occ[v];
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ);
+    static const uint32_t stagger_ns =
+        std::getenv("DCRP_STAGGER_NS") ? (uint32_t)std::atoi(std::getenv("DCRP_STAGGER_NS")) : 0u;
     static const uint32_t dbg = std::getenv("DCRP_DEBUG") ? (uint32_t)std::atoi(std::getenv("DCRP_DEBUG")) : 0u;
-    kern<<<grid, SCREEN2_BLOCK, smem, st>>>(e->sd, r, chunks_per_pair, n_items, tile_steps, stagger_ns, dbg);
+    ScenarioDev sd = e->sd;
+    RunDev rr = r;
+    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &tile_steps, (void*)&stagger_ns, (void*)&dbg};
+    cudaError_t ce = cudaLaunchKernel(c.kern[v], dim3(grid), dim3((unsigned)c.block), args, smem, st);
     ++e->launches; ++e->launches_this_run;
-    return cudaGetLastError();
+    return ce != cudaSuccess ? ce : cudaGetLastError();
 }
 
 extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream, uint64_t* d_counts)
@@ -496,7 +524,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
 
     // slices keep the item count of one launch below 2^30
     const bool exact = (run->precision == DCRP_PRECISION_FP64);
-    const uint64_t per_item = exact ? (uint64_t)EXB : (uint64_t)SCREEN2_CH;
+    const uint64_t per_item = exact ? (uint64_t)EXB : screen_chunk();
     const uint64_t max_chunks = std::max<uint64_t>(1, MAX_ITEMS_PER_LAUNCH / n_pairs);
     const uint64_t slice_max = max_chunks * per_item;
     for (uint64_t first = 0; first < run->trial_count; first += slice_max) {
@@ -512,8 +540,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
             ++e->launches; ++e->launches_this_run;
             CU(cudaGetLastError());
         } else {
-            const cudaError_t ce = r.replay ? launch_screen2<true>(e, r, chunks, n_items, st)
-                                            : launch_screen2<false>(e, r, chunks, n_items, st);
+            const cudaError_t ce = launch_screen2(e, r, chunks, n_items, st);
             if (ce != cudaSuccess) return fail(DCRP_ERR_CUDA, "k_screen launch: %s", cudaGetErrorString(ce));
         }
     }
@@ -705,7 +732,7 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
 extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms_out)
 {
     if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
-    if (which < 0 || which > 9) return fail(DCRP_ERR_INVALID, "which must be 0..9");
+    if (which < 0 || which > 12) return fail(DCRP_ERR_INVALID, "which must be 0..12");
     CU(cudaSetDevice(e->device));
     const int threads = 256, blocks = e->prop.multiProcessorCount * 8;
     const int iters = 2048;
@@ -723,7 +750,10 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
             case 6: k_peak_variant<6><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 7: k_peak_variant<7><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 8: k_peak_variant<8><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            default: k_peak_variant<9><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 9: k_peak_variant<9><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 10: k_peak_variant2<10><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 11: k_peak_variant2<11><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            default: k_peak_variant2<12><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
         }
         ++e->launches;
         CU(cudaGetLastError());
@@ -740,6 +770,8 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
     else if (which == 2) flops = lanes * iters * 16.0 * 8.0 * 2.0;
     else if (which == 4 || which == 5) flops = lanes * iters * 8.0 * 9.0 * 4.0 * 2.0;   // packed add/mul: 2 flop
     else if (which == 8) flops = lanes * iters * 8.0 * 16.0;                            // FMNMX3 count, not flops
+    else if (which == 10) flops = lanes * iters * 8.0 * 4.0 / 10.0;                     // Philox4x32-10 calls
+    else if (which == 12) flops = lanes * iters * 8.0 * 2.0 * 2.0 * 2.0 * 11.0;         // 2 steps x 2 pairs x 2 tests
     else                 flops = lanes * iters * 8.0 * 4.0 * 2.0 * 11.0;   // 2 tests per packed pair, 11 flop each
     *tflops = flops / ((double)best * 1e-3) * 1e-12;
     if (ms_out) *ms_out = best;

@@ -417,8 +417,8 @@ __device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const Track
     return o;
 }
 
-template <int R, int BLOCK, bool REPLAY>
-__global__ void __launch_bounds__(BLOCK, 1280 / BLOCK)
+template <int R, int BLOCK, bool REPLAY, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int tile_steps,
           uint32_t stagger_ns, uint32_t dbg)
 {
@@ -594,19 +594,28 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 const int t0 = tl * tile_steps;
                 const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(VL, t0 + tile_steps);   // dbg 1: no scan
                 const float4* __restrict__ tp = tiles + (size_t)buf * tile_steps - (size_t)t0;
-                // one broadcast LDS.128 per index: (-ax, -ay, -az, i).  The {v, v} pairs below cost
-                // nothing: ptxas folds them into the packed ops' scalar-broadcast operand form
-                // (FFMA2 R, R.F32, R.F32x2, R.F32x2).
+                // Incremental form: P(lo) = B + lo*S once per tile, then per index D = P + (-A_i),
+                // d2 = |D|^2, P += S.  Every packed op then reads at most two distinct register pairs,
+                // which is what lets FFMA2/FADD2/FMUL2 issue back to back every 2 cycles (the fused
+                // P = i*S + B form reads three and measured 12% slower: profiles/r01_micro_pipes.json).
+                // The accumulated rounding (<= tile_steps/2 ulp per coordinate) is inside the screen margin.
+                // One broadcast LDS.128 per index: (-ax, -ay, -az, i); the {v, v} pairs cost nothing
+                // (ptxas folds them into the packed ops' scalar-broadcast operand form).
+                if (lo < hi) {
+                    const float lof = (float)lo;
+                    const float2 lo2 = make_float2(lof, lof);
+                    float2 PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY), PZ = ffma2(lo2, SZ, BZ);
 #pragma unroll 4
-                for (int i = lo; i < hi; ++i) {
-                    const float4 p = tp[i];
-                    const float2 fi = make_float2(p.w, p.w);
-                    const float2 dx = fadd2(ffma2(fi, SX, BX), make_float2(p.x, p.x));
-                    const float2 dy = fadd2(ffma2(fi, SY, BY), make_float2(p.y, p.y));
-                    const float2 dz = fadd2(ffma2(fi, SZ, BZ), make_float2(p.z, p.z));
-                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
-                    mn0 = fminf(mn0, d2.x);
-                    mn1 = fminf(mn1, d2.y);
+                    for (int i = lo; i < hi; ++i) {
+                        const float4 p = tp[i];
+                        const float2 dx = fadd2(PX, make_float2(p.x, p.x));
+                        const float2 dy = fadd2(PY, make_float2(p.y, p.y));
+                        const float2 dz = fadd2(PZ, make_float2(p.z, p.z));
+                        const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                        mn0 = fminf(mn0, d2.x);
+                        mn1 = fminf(mn1, d2.y);
+                        PX = fadd2(PX, SX); PY = fadd2(PY, SY); PZ = fadd2(PZ, SZ);
+                    }
                 }
             }
 
@@ -822,6 +831,83 @@ __global__ void __launch_bounds__(256) k_peak_variant(float* out, int iters, flo
 #pragma unroll
     for (int k = 0; k < 4; ++k) r += B[k].x + B[k].y + S[k].x + S[k].y;
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// More profiling variants:
+//   V=10 Philox4x32-10 only (4 independent streams per thread)         -> reported in G calls/s
+//   V=11 the scan mix with one Philox round interleaved per 4 pair-steps (software-pipelined)
+//   V=12 incremental scan mix: P += S; D = P + (-A); all packed ops with <= 2 distinct register pairs
+template <int V>
+__global__ void __launch_bounds__(256) k_peak_variant2(float* out, int iters, float s0, float a0)
+{
+    float2 B[4], S[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        B[k] = make_float2(threadIdx.x * 0.5f + k, threadIdx.x * 0.25f - k);
+        S[k] = make_float2(s0 + k, s0 - k);
+    }
+    float2 fi = make_float2(0.f, 0.f);
+    const float2 one = make_float2(1.f, 1.f), na = make_float2(a0, a0);
+    float mn = 3.0e38f, mn2 = 2.0e38f;
+    uint32_t c0[4], c1[4], c2[4], c3[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { c0[k] = threadIdx.x + k; c1[k] = blockIdx.x; c2[k] = k; c3[k] = 7; }
+    uint32_t k0 = 0x12345u, k1 = 0x6789au;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (V == 10 || V == 11) {
+                // one Philox round on stream (u & 3)
+                const int q = u & 3;
+                const uint32_t hi0 = __umulhi(0xD2511F53u, c0[q]), lo0 = 0xD2511F53u * c0[q];
+                const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2[q]), lo1 = 0xCD9E8D57u * c2[q];
+                const uint32_t n0 = hi1 ^ c1[q] ^ k0, n2 = hi0 ^ c3[q] ^ k1;
+                c0[q] = n0; c1[q] = lo1; c2[q] = n2; c3[q] = lo0;
+                k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+            }
+            if (V == 10) {
+#pragma unroll
+                for (int q = 1; q < 4; ++q) {      // three more rounds: 4 rounds per u in total
+                    const int z = (u + q) & 3;
+                    const uint32_t hi0 = __umulhi(0xD2511F53u, c0[z]), lo0 = 0xD2511F53u * c0[z];
+                    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2[z]), lo1 = 0xCD9E8D57u * c2[z];
+                    const uint32_t n0 = hi1 ^ c1[z] ^ k0, n2 = hi0 ^ c3[z] ^ k1;
+                    c0[z] = n0; c1[z] = lo1; c2[z] = n2; c3[z] = lo0;
+                }
+            }
+            if (V == 11) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 dx = fadd2(ffma2(fi, S[k], B[k]), na);
+                    const float2 dy = fadd2(ffma2(fi, S[k], B[(k + 1) & 3]), na);
+                    const float2 dz = fadd2(ffma2(fi, S[(k + 1) & 3], B[k]), na);
+                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                    mn = fminf(mn, d2.x); mn2 = fminf(mn2, d2.y);
+                }
+                fi = fadd2(fi, one);
+            }
+            if (V == 12) {
+                // 2 pairs x 3 coordinates of running positions live in B[0..3] / S[0..3] halves
+                float2 PX0 = B[0], PY0 = B[1], PZ0 = B[2], PX1 = B[3], PY1 = S[3], PZ1 = fi;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    PX0 = fadd2(PX0, S[0]); PY0 = fadd2(PY0, S[1]); PZ0 = fadd2(PZ0, S[2]);
+                    PX1 = fadd2(PX1, S[0]); PY1 = fadd2(PY1, S[1]); PZ1 = fadd2(PZ1, S[2]);
+                    const float2 dx0 = fadd2(PX0, na), dy0 = fadd2(PY0, na), dz0 = fadd2(PZ0, na);
+                    const float2 dx1 = fadd2(PX1, na), dy1 = fadd2(PY1, na), dz1 = fadd2(PZ1, na);
+                    const float2 e0 = ffma2(dz0, dz0, ffma2(dy0, dy0, fmul2(dx0, dx0)));
+                    const float2 e1 = ffma2(dz1, dz1, ffma2(dy1, dy1, fmul2(dx1, dx1)));
+                    mn = fminf(mn, e0.x); mn2 = fminf(mn2, e0.y);
+                    mn = fminf(mn, e1.x); mn2 = fminf(mn2, e1.y);
+                }
+                B[0] = PX0; B[1] = PY0; B[2] = PZ0; B[3] = PX1; S[3] = PY1; fi = PZ1;
+            }
+        }
+    }
+    float r = mn + mn2;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r += B[k].x + B[k].y + S[k].x + S[k].y + __uint_as_float((c0[k] ^ c1[k] ^ c2[k] ^ c3[k]) & 0x3fffffffu);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r + fi.x;
 }
 
 // Clears a run's output arena: words [0, first_off) = 0 (counters, stats, counts),

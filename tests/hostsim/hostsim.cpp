@@ -99,14 +99,20 @@ void hs_screen(const double* ax, const double* ay, const double* az, int n_steps
         const Ray32 ray = stage2_ray32((float)DSUB(d.tx, xl), (float)DSUB(d.ty, yl), (float)DSUB(d.tz, start_alt),
                                        (float)DSUB(xl, ox), (float)DSUB(yl, oy), (float)DSUB(start_alt, oz),
                                        (float)last, (float)v_straight, coef);
+        // k_screen2's scan: exact re-base P = lo*S + B at every tile start, then D = P + (-A), P += S
+        const int tile = n_steps <= 128 ? 128 : 512;
         float mn = 3.0e38f;
-        for (int i = d.t1st; i < n_steps; ++i) {
-            const float fi = (float)i;
-            const float dx = fmaf(fi, ray.sx, ray.bx) + nx[i];
-            const float dy = fmaf(fi, ray.sy, ray.by) + ny[i];
-            const float dz = fmaf(fi, ray.sz, ray.bz) + nz[i];
-            const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            mn = fminf(mn, d2);
+        for (int t0 = 0; t0 < n_steps; t0 += tile) {
+            const int lo = d.t1st > t0 ? d.t1st : t0, hi = (t0 + tile < n_steps) ? t0 + tile : n_steps;
+            if (lo >= hi) continue;
+            float px = fmaf((float)lo, ray.sx, ray.bx), py = fmaf((float)lo, ray.sy, ray.by),
+                  pz = fmaf((float)lo, ray.sz, ray.bz);
+            for (int i = lo; i < hi; ++i) {
+                const float dx = px + nx[i], dy = py + ny[i], dz = pz + nz[i];
+                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                mn = fminf(mn, d2);
+                px += ray.sx; py += ray.sy; pz += ray.sz;
+            }
         }
         min_d2_out[r] = ray.degenerate ? 0.f : mn;
     }

@@ -37,7 +37,8 @@ def test_sqrt_free_threshold_is_exact(hostsim):
 
 def test_fp32_screen_error_is_far_inside_the_margin(hostsim, golden, tracks, ring1):
     """|fp32 screen distance - fp64 distance| on every golden near miss (min in stage
-    2, < 25 m): the engine's margin is >= 0.02 m + 32 ulp32(extent) ~ 0.05 m."""
+    2, < 25 m).  The engine's margin is 0.02 m + sqrt(3)*(tile/2 + 4) ulp32(extent) ~ 0.08 m
+    (worst-case bound of the incremental scan); the observed error must be far inside it."""
     worst = 0.0
     for p, (a, j) in enumerate(golden["pairs"]):
         t = tracks[a]
@@ -52,4 +53,4 @@ def test_fp32_screen_error_is_far_inside_the_margin(hostsim, golden, tracks, rin
         assert same.sum() > 0.9 * near.sum()
         worst = max(worst, np.abs(s[same] - mind[same]).max())
     print("worst fp32 screen error %.2e m" % worst)
-    assert worst < 5e-3
+    assert worst < 2e-2
