@@ -40,6 +40,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL's version banner, torchrun) write to fd 1; the contract is ONE JSON line on
+# stdout.  Keep the real stdout aside, point fd 1 at stderr for the whole run, emit the line last.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def workload(tmp):
     import drone_collision_rp_b200 as pk
     from drone_collision_rp_b200 import scenario
@@ -208,7 +218,7 @@ def reference_arm(args):
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     return 0
 
 
@@ -411,7 +421,7 @@ def engine_arm(args):
         "cpu_baseline": cpu,
         "device": info,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
