@@ -54,7 +54,8 @@ class Run(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("trials", C.c_uint64), ("tests_evaluated", C.c_uint64), ("tests_shared", C.c_uint64),
-                ("tests_issued", C.c_uint64), ("drone_steps", C.c_uint64), ("candidates", C.c_uint64),
+                ("tests_issued", C.c_uint64), ("drone_steps", C.c_uint64), ("level2", C.c_uint64),
+                ("candidates", C.c_uint64),
                 ("hits", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
                 ("ms_prepare", C.c_float), ("ms_trials", C.c_float), ("ms_confirm", C.c_float),
                 ("ms_device_total", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]

@@ -74,7 +74,7 @@ struct Candidate {       // a trial the fp32 screen could not rule out
     uint64_t trial;
 };
 
-enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_COUNT };
+enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_LEVEL2, ST_COUNT };
 
 struct RunDev {
     uint64_t seed, trial_begin, trial_count;   // the whole run: trials [begin, begin+count) per pair

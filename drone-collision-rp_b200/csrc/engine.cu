@@ -641,6 +641,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     o.tests_issued = stats[ST_ISSUED];
     o.drone_steps = all_steps;
     o.candidates = stats[ST_CANDIDATES];
+    o.level2 = stats[ST_LEVEL2];
     o.hits = stats[ST_HITS];
     o.kernel_launches = e->launches_this_run;
     if (!e->prepare_timed) {

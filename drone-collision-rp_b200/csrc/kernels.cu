@@ -369,6 +369,22 @@ __device__ __forceinline__ void rescan_fp32(const ScenarioDev& s, const RunDev& 
     }
 }
 
+// Level 2 of the screen: min over the stage-2 indices of the full 3-D fp32 squared separation of ONE
+// trial (fused form P = i*S + B: no accumulation), track read through L1 from global memory.
+__device__ __forceinline__ float min3d_fp32(const ScenarioDev& s, const TrackDev& t, const Setup32& u)
+{
+    const float4* __restrict__ g = s.trk32 + (size_t)t.off;
+    float mn = 3.0e38f;
+    for (int i = u.t1st; i < t.n_steps; ++i) {
+        const float4 p = __ldg(&g[i]);                  // (-ax, -ay, -az, i)
+        const float dx = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x;
+        const float dy = fmaf(p.w, u.ray.sy, u.ray.by) + p.y;
+        const float dz = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
+        mn = fminf(mn, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+    return mn;
+}
+
 // =========================================================================
 // k_screen2: the fp32 packed screen, balanced rounds
 // =========================================================================
@@ -441,7 +457,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 
     uint32_t phase0 = 0, phase1 = 0;
     int loaded_track = -1;
-    uint32_t acc_t1 = 0, acc_is = 0, ncand = 0;   // sum of t1st / issued lane-steps (flushed before overflow)
+    uint32_t acc_t1 = 0, acc_is = 0, ncand = 0, npass = 0;   // partial sums (flushed before overflow)
 
     // CTAs co-resident on an SM all start at once and, doing identical work per item, would stay in
     // phase (all in the integer/set-up phases together, then all fighting for the FMA pipe).  Offset
@@ -545,37 +561,37 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             const int q2 = rd >> 1;
             const int bin = (rd & 1) ? (q2 * 2 * NW + 2 * NW - 1 - warp) : (q2 * 2 * NW + warp);
             const uint32_t slot0 = (uint32_t)(bin * 64 + lane);
-            float2 BX, BY, BZ, SX, SY, SZ;
+            float2 BX, BY, SX, SY;                 // level 1 needs the horizontal ray only
             int tmin = INT_MAX;
-            bool force = false;
+            uint32_t fmask = 0;                   // bit m: trial m must go to level 2 regardless of the scan
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 const uint4 q = stage[slot0 + m * 32];
-                float bx = 1e15f, by = 1e15f, bz = 1e15f, sx = 0.f, sy = 0.f, sz = 0.f;
+                float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
                 if ((q.w >> 12) != 0u) {
                     int32_t t1;
                     if (REPLAY) {
                         const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
-                        bx = u.ray.bx; by = u.ray.by; bz = u.ray.bz; sx = u.ray.sx; sy = u.ray.sy; sz = u.ray.sz;
-                        force |= u.force; t1 = u.t1st;
+                        bx = u.ray.bx; by = u.ray.by; sx = u.ray.sx; sy = u.ray.sy;
+                        fmask |= u.force ? (1u << m) : 0u; t1 = u.t1st;
                     } else if (dbg & 2u) {      // profiling aid: no ray set-up (results meaningless)
-                        bx = __uint_as_float(q.x >> 9); by = __uint_as_float(q.y >> 9); bz = 50.f;
-                        sx = 1.f; sy = 2.f; sz = 3.f; t1 = (int32_t)(q.w >> 12);
+                        bx = __uint_as_float(q.x >> 9); by = __uint_as_float(q.y >> 9);
+                        sx = 1.f; sy = 2.f; t1 = (int32_t)(q.w >> 12);
                     } else {
                         const Fast32 u = setup_fast32(s, tk, pair, j, s1_first, q, zlf);
-                        bx = u.bx; by = u.by; bz = u.bz; sx = u.sx; sy = u.sy; sz = u.sz;
-                        force |= u.force; t1 = u.t1st;
+                        bx = u.bx; by = u.by; sx = u.sx; sy = u.sy;
+                        fmask |= u.force ? (1u << m) : 0u; t1 = u.t1st;
                     }
                     tmin = min(tmin, t1);
                     acc_t1 += (uint32_t)t1;
                 }
-                if (m) { BX.y = bx; BY.y = by; BZ.y = bz; SX.y = sx; SY.y = sy; SZ.y = sz; }
-                else   { BX.x = bx; BY.x = by; BZ.x = bz; SX.x = sx; SY.x = sy; SZ.x = sz; }
+                if (m) { BX.y = bx; BY.y = by; SX.y = sx; SY.y = sy; }
+                else   { BX.x = bx; BY.x = by; SX.x = sx; SY.x = sy; }
             }
             const int imin = __reduce_min_sync(0xffffffffu, tmin);
             if (imin < VL) acc_is += (uint32_t)(VL - imin) * 2u;
 
-            float mn0 = 3.0e38f, mn1 = 3.0e38f;
+            float mn0 = 3.0e38f, mn1 = 3.0e38f;     // running min of the horizontal d2 of trial 0 / 1
             for (int tl = 0; tl < n_tiles; ++tl) {
                 const int buf = single ? 0 : (tl & 1);
                 if (!single) {
@@ -594,56 +610,64 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 const int t0 = tl * tile_steps;
                 const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(VL, t0 + tile_steps);   // dbg 1: no scan
                 const float4* __restrict__ tp = tiles + (size_t)buf * tile_steps - (size_t)t0;
-                // Incremental form: P(lo) = B + lo*S once per tile, then per index D = P + (-A_i),
-                // d2 = |D|^2, P += S.  Every packed op then reads at most two distinct register pairs,
-                // which is what lets FFMA2/FADD2/FMUL2 issue back to back every 2 cycles (the fused
-                // P = i*S + B form reads three and measured 12% slower: profiles/r01_micro_pipes.json).
-                // The accumulated rounding (<= tile_steps/2 ulp per coordinate) is inside the screen margin.
-                // One broadcast LDS.128 per index: (-ax, -ay, -az, i); the {v, v} pairs cost nothing
-                // (ptxas folds them into the packed ops' scalar-broadcast operand form).
+                // LEVEL 1, horizontal screen: d2xy(i) = |Pxy(i) - Axy(i)|^2 <= d2(i), so a trial whose
+                // horizontal separation never drops below R + margin cannot collide at any index, whatever
+                // the altitudes.  6 packed ops per pair-step instead of 9.
+                // Incremental form: P(lo) = B + lo*S once per tile, then per index D = P + (-A_i), P += S:
+                // every packed op reads at most two distinct register pairs, which is what lets
+                // FFMA2/FADD2/FMUL2 issue back to back every 2 cycles (the fused P = i*S + B form reads
+                // three and measured 12% slower: profiles/r01_micro_pipes.json).  The accumulated rounding
+                // (<= tile_steps/2 ulp per coordinate) is inside the screen margin.
+                // One broadcast LDS per index: (-ax, -ay, -az, i); the {v, v} pairs cost nothing (ptxas
+                // folds them into the packed ops' scalar-broadcast operand form).
                 if (lo < hi) {
                     const float lof = (float)lo;
                     const float2 lo2 = make_float2(lof, lof);
-                    float2 PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY), PZ = ffma2(lo2, SZ, BZ);
+                    float2 PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);
 #pragma unroll 4
                     for (int i = lo; i < hi; ++i) {
-                        const float4 p = tp[i];
+                        const float2 p = *reinterpret_cast<const float2*>(&tp[i]);
                         const float2 dx = fadd2(PX, make_float2(p.x, p.x));
                         const float2 dy = fadd2(PY, make_float2(p.y, p.y));
-                        const float2 dz = fadd2(PZ, make_float2(p.z, p.z));
-                        const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+                        const float2 d2 = ffma2(dy, dy, fmul2(dx, dx));
                         mn0 = fminf(mn0, d2.x);
                         mn1 = fminf(mn1, d2.y);
-                        PX = fadd2(PX, SX); PY = fadd2(PY, SY); PZ = fadd2(PZ, SZ);
+                        PX = fadd2(PX, SX); PY = fadd2(PY, SY);
                     }
                 }
             }
 
-            // ---------------- rare path: hand the two trials on
-            if (force || fminf(mn0, mn1) < thr) {
+            // ---------------- rare path (~1e-3 of trials): LEVEL 2, the full 3-D fp32 distance of the
+            // flagged trial alone; what survives goes to the fp64 confirm (LEVEL 3)
+            if (mn0 < thr) fmask |= 1u;
+            if (mn1 < thr) fmask |= 2u;
+            if (fmask) {
 #pragma unroll 1
                 for (int m = 0; m < 2; ++m) {
+                    if (!((fmask >> m) & 1u)) continue;
                     const uint4 q = stage[slot0 + m * 32];
                     if ((q.w >> 12) == 0u) continue;
+                    ++npass;
                     const uint64_t trial = r.trial_begin + chunk_first64 + (q.w & 4095u);
-                    if (!r.decide_fp32) {
+                    const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
+                    if (r.decide_fp32) {
+                        rescan_fp32(s, r, *tk, pair, a, j, s1_first, trial, u);
+                    } else if (u.force || min3d_fp32(s, *tk, u) < s.thr2_screen) {
                         ++ncand;
                         const uint32_t slot = warp_claim_slot(r.cand_count);
                         if (slot < r.cand_cap) {
                             Candidate cd; cd.pair = (uint32_t)pair; cd.pad = 0; cd.trial = trial;
                             r.cands[slot] = cd;
                         }
-                    } else {
-                        const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
-                        rescan_fp32(s, r, *tk, pair, a, j, s1_first, trial, u);
                     }
                 }
             }
         }
     }
     flush_stats(r, 0, acc_t1, acc_is, 0, 0);
-    const unsigned long long nc = warp_sum_u64(ncand);
+    const unsigned long long nc = warp_sum_u64(ncand), np = warp_sum_u64(npass);
     if (lane == 0 && nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
+    if (lane == 0 && np) atomicAdd(&r.stats[ST_LEVEL2], np);
 }
 
 // =========================================================================

@@ -123,7 +123,9 @@ typedef struct dcrp_stats {
                                   evaluated once per pair and shared: sum over trials of t1st        */
     uint64_t tests_issued;     /* lane-steps actually issued by the scan loops (>= evaluated)         */
     uint64_t drone_steps;      /* sum over trials of (n_steps - 1)                                    */
-    uint64_t candidates;       /* trials the fp32 screen passed on to the fp64 confirm                */
+    uint64_t level2;           /* trials the horizontal fp32 screen (level 1) passed to the 3-D fp32
+                                  re-scan (level 2)                                                   */
+    uint64_t candidates;       /* trials level 2 passed on to the fp64 confirm (level 3)              */
     uint64_t hits;             /* total collisions                                                    */
     uint32_t kernel_launches;  /* engine kernels launched by the call                                 */
     uint32_t reserved;

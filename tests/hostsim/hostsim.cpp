@@ -73,12 +73,15 @@ void hs_exact(const double* ax, const double* ay, const double* az, int n_steps,
     }
 }
 
-// The fp32 screen of k_screen for n draws of one (track, drone): min over the
-// stage-2 indices of the fp32 squared separation (scalar fmaf form of the packed
-// FFMA2/FADD2/FMUL2 sequence), relative to origin (ox, oy, oz).
+// The fp32 screen of k_screen2 for n draws of one (track, drone), scalar form of the packed
+// sequence, relative to origin (ox, oy, oz):
+//   level 1  min over stage-2 indices of the HORIZONTAL squared separation, incremental scan
+//            (exact re-base P = lo*S + B at every tile start, then D = P + (-A), P += S)
+//   level 2  min of the full 3-D squared separation, fused form P = i*S + B
 void hs_screen(const double* ax, const double* ay, const double* az, int n_steps, int takeoff_t,
                double x0, double y0, double heading0, double start_alt, double v_straight, double v_ascend,
-               double ox, double oy, double oz, const Draw* draws, long n, float* min_d2_out)
+               double ox, double oy, double oz, const Draw* draws, long n, float* min_d2xy_out,
+               float* min_d2_out)
 {
     const double s1x = std::sin(heading0) * v_straight, s1y = std::cos(heading0) * v_straight;
     std::vector<double> p1x(takeoff_t), p1y(takeoff_t);
@@ -92,6 +95,7 @@ void hs_screen(const double* ax, const double* ay, const double* az, int n_steps
         nx[i] = -(float)(ax[i] - ox); ny[i] = -(float)(ay[i] - oy); nz[i] = -(float)(az[i] - oz);
     }
     const float coef = (float)(2.0 * (v_straight - v_ascend) / DCRP_PI);
+    const int tile = n_steps <= 128 ? 128 : 512;
     for (long r = 0; r < n; ++r) {
         const Draw& d = draws[r];
         const int last = d.t1st - 1;
@@ -99,22 +103,26 @@ void hs_screen(const double* ax, const double* ay, const double* az, int n_steps
         const Ray32 ray = stage2_ray32((float)DSUB(d.tx, xl), (float)DSUB(d.ty, yl), (float)DSUB(d.tz, start_alt),
                                        (float)DSUB(xl, ox), (float)DSUB(yl, oy), (float)DSUB(start_alt, oz),
                                        (float)last, (float)v_straight, coef);
-        // k_screen2's scan: exact re-base P = lo*S + B at every tile start, then D = P + (-A), P += S
-        const int tile = n_steps <= 128 ? 128 : 512;
-        float mn = 3.0e38f;
+        float mn2 = 3.0e38f, mn3 = 3.0e38f;
         for (int t0 = 0; t0 < n_steps; t0 += tile) {
             const int lo = d.t1st > t0 ? d.t1st : t0, hi = (t0 + tile < n_steps) ? t0 + tile : n_steps;
             if (lo >= hi) continue;
-            float px = fmaf((float)lo, ray.sx, ray.bx), py = fmaf((float)lo, ray.sy, ray.by),
-                  pz = fmaf((float)lo, ray.sz, ray.bz);
+            float px = fmaf((float)lo, ray.sx, ray.bx), py = fmaf((float)lo, ray.sy, ray.by);
             for (int i = lo; i < hi; ++i) {
-                const float dx = px + nx[i], dy = py + ny[i], dz = pz + nz[i];
-                const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                mn = fminf(mn, d2);
-                px += ray.sx; py += ray.sy; pz += ray.sz;
+                const float dx = px + nx[i], dy = py + ny[i];
+                mn2 = fminf(mn2, fmaf(dy, dy, dx * dx));
+                px += ray.sx; py += ray.sy;
             }
         }
-        min_d2_out[r] = ray.degenerate ? 0.f : mn;
+        for (int i = d.t1st; i < n_steps; ++i) {
+            const float fi = (float)i;
+            const float dx = fmaf(fi, ray.sx, ray.bx) + nx[i];
+            const float dy = fmaf(fi, ray.sy, ray.by) + ny[i];
+            const float dz = fmaf(fi, ray.sz, ray.bz) + nz[i];
+            mn3 = fminf(mn3, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        }
+        min_d2xy_out[r] = ray.degenerate ? 0.f : mn2;
+        min_d2_out[r] = ray.degenerate ? 0.f : mn3;
     }
 }
 

@@ -203,7 +203,8 @@ class HostSim:
         L.hs_thr_d2.argtypes = [C.c_double]
         L.hs_exact.argtypes = [dp, dp, dp, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_void_p, C.c_long,
                                                                                    C.c_void_p, C.c_void_p]
-        L.hs_screen.argtypes = [dp, dp, dp, C.c_int, C.c_int] + [C.c_double] * 9 + [C.c_void_p, C.c_long, C.c_void_p]
+        L.hs_screen.argtypes = [dp, dp, dp, C.c_int, C.c_int] + [C.c_double] * 9 + [C.c_void_p, C.c_long, C.c_void_p,
+                                                                                    C.c_void_p]
         self.L = L
 
     def philox(self, ctr, key):
@@ -235,8 +236,8 @@ class HostSim:
         x, y, z = (np.ascontiguousarray(trk[k], dtype=np.float64) for k in "xyz")
         draws = np.ascontiguousarray(draws, dtype=DRAW_DTYPE)
         n = len(draws)
-        out = np.zeros(n, np.float32)
+        out2, out3 = np.zeros(n, np.float32), np.zeros(n, np.float32)
         self.L.hs_screen(_d(x), _d(y), _d(z), len(x), int(trk["takeoff_t"]), float(drone[0]), float(drone[1]),
                          float(drone[2]), start_alt, v_straight, v_ascend, float(origin[0]), float(origin[1]),
-                         float(origin[2]), draws.ctypes.data, n, out.ctypes.data)
-        return out
+                         float(origin[2]), draws.ctypes.data, n, out2.ctypes.data, out3.ctypes.data)
+        return out2, out3

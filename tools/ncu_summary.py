@@ -63,7 +63,7 @@ for r in rows[hi + 1:]:
 tot = sum(int(r[iE]) for r in data)
 totS = sum(int(r[iN]) for r in data)
 ops, ops_s, st = collections.Counter(), collections.Counter(), collections.Counter()
-reg, regs = 0, collections.defaultdict(lambda: [0, 0, collections.Counter()])
+reg, regs = 0, collections.defaultdict(lambda: [0, 0, collections.Counter(), collections.Counter()])
 for r in data:
     src_ = r[iS].strip()
     tok = src_.split()
@@ -75,6 +75,7 @@ for r in data:
     ops_s[op] += n
     regs[reg][0] += e
     regs[reg][1] += n
+    regs[reg][3][op] += e
     for h in stalls:
         try:
             v = int(r[hdr.index(h)])
@@ -94,3 +95,4 @@ for k, v in regs.items():
         t = sum(v[2].values()) or 1
         print("   region %d: %5.1f%% %5.1f%%  %s" % (k, 100 * v[0] / tot, 100 * v[1] / totS,
               ", ".join("%s %.0f%%" % (h, 100 * c / t) for h, c in v[2].most_common(5))))
+        print("        ops: " + ", ".join("%s %.1f%%" % (o, 100 * c / tot) for o, c in v[3].most_common(12)))

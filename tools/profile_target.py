@@ -19,9 +19,9 @@ sizes = [101011] * 5 + ([] if "--short" in sys.argv else [10_000_000])
 for i, n in enumerate(sizes):
     run = eng.run_async(seed=20170630, trial_begin=i * 101011, trial_count=n, precision=prec)
     r = eng.fetch(run)
-    print(i, "trials %.3e ms_trials %.4f  tests/s %.4e  TFLOP11 %.2f  issued/eval %.4f hits %d cand %d" % (
+    print(i, "trials %.3e ms_trials %.4f  tests/s %.4e  TFLOP11 %.2f  issued/eval %.4f hits %d cand %d level2 %d" % (
         r.stats["trials"], r.stats["ms_trials"], r.stats["tests_evaluated"] / (r.stats["ms_trials"] * 1e-3),
         r.stats["tests_evaluated"] * 11 / (r.stats["ms_trials"] * 1e-3) * 1e-12,
         r.stats["tests_issued"] / max(1, r.stats["tests_evaluated"]), r.stats["hits"],
-        r.stats["candidates"]), flush=True)
+        r.stats["candidates"], r.stats["level2"]), flush=True)
 eng.close()
