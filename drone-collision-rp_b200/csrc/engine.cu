@@ -428,7 +428,8 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     ScreenCfg& c = screen_cfg();
     const int v = r.replay ? 1 : 0;
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
-    const size_t smem = (size_t)2 * tile_steps * 16 + (size_t)screen_chunk() * 16 + 80 * 4 + 16;
+    const size_t smem = (size_t)2 * tile_steps * 16 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
+                        (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2));
     if (c.configured_smem[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(c.kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;

@@ -397,41 +397,42 @@ __device__ __forceinline__ float min3d_fp32(const ScenarioDev& s, const TrackDev
 // each other at the next barrier; one pair in flight keeps the kernel at <= 48
 // registers so 5 CTAs of 256 threads overlap their integer (Philox/binning),
 // fp64/conversion (set-up) and FMA-pipe (scan) phases on one SM.
-struct Fast32 {
-    float bx, by, bz, sx, sy, sz;
+struct Fast32 {          // horizontal ray of one trial for level 1: position(i) = b + i*s
+    float bx, by, sx, sy;
     int32_t t1st;
     bool force;
 };
 
-__device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const TrackDev* __restrict__ tk, int pair,
-                                               int j, int s1_first, const uint4 q, float zlf)
+// kk / pl point at this pair's kink tables (shared memory when takeoff_t <= SCREEN_TAB, else global).
+__device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const TrackDev* __restrict__ tk,
+                                               const double2* __restrict__ kk_tab,
+                                               const float2* __restrict__ pl_tab, int s1_first, const uint4 q)
 {
     const double wx32 = __ldg(&tk->wx32), wy32 = __ldg(&tk->wy32);
     const float wz32 = __ldg(&tk->wz32), z0rel = __ldg(&tk->z0rel);
     Fast32 o;
     o.t1st = (int32_t)(q.w >> 12);
     const int last = o.t1st - 1;
-    const double2 kk = __ldg(&s.kink[(size_t)pair * s.t_max + last]);
-    const float2 pl = __ldg(&s.p1f[(size_t)j * s.t_max + last]);
+    const double2 kk = kk_tab[last];
+    const float2 pl = pl_tab[last];
     // target - kink: one fp64 FMA per coordinate, rounded once to fp32
     const float dls = (float)fma((double)q.x, wx32, kk.x);
     const float dbs = (float)fma((double)q.y, wy32, kk.y);
     const float ada = fabsf(fmaf((float)q.z, wz32, z0rel));
     const float m2 = fmaf(dls, dls, dbs * dbs);
     const float inv_m = rsqrtf(m2);
-    const float inv_n = rsqrtf(fmaf(ada, ada, m2));
-    const float pitch = atanf(ada * inv_m);
-    const float vf = fmaf(-s.coef_f, pitch, s.v_straight_f);
+    const float pitch = atanf(ada * inv_m);                     // Drone.cpp:218
+    const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
     const float lastf = (float)last;
-    o.sx = dls * inv_m * vf;
-    o.sy = dbs * inv_m * vf;
-    o.sz = ada * inv_n * vf;
+    o.sx = dls * k;
+    o.sy = dbs * k;
     o.bx = fmaf(-lastf, o.sx, pl.x);
     o.by = fmaf(-lastf, o.sy, pl.y);
-    o.bz = fmaf(-lastf, o.sz, zlf);
     o.force = !(m2 > 1e-12f) || (s1_first <= last);
     return o;
 }
+
+constexpr int SCREEN_TAB = 128;     // kink-table entries kept in shared memory per CTA
 
 template <int R, int BLOCK, bool REPLAY, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -449,6 +450,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     uint4*    stage = reinterpret_cast<uint4*>(smem_raw + (size_t)2 * tile_steps * 16);
     uint32_t* hist  = reinterpret_cast<uint32_t*>(stage + CH);
     uint64_t* bars  = reinterpret_cast<uint64_t*>(hist + 80);
+    double2*  tabk  = reinterpret_cast<double2*>(bars + 2);            // this pair's kink tables
+    float2*   tabp  = reinterpret_cast<float2*>(tabk + SCREEN_TAB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -464,10 +467,14 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     // the k-th CTA of an SM by k/occupancy of an item so that scans overlap the other phases.
     if (stagger_ns) __nanosleep(stagger_ns * (blockIdx.x / s.n_sm));
 
+    // (pair, chunk) of the item, carried along the grid-stride loop: divisions only when a pair ends
+    int pair = (int)(blockIdx.x / chunks_per_pair);
+    uint32_t c = blockIdx.x - (uint32_t)pair * chunks_per_pair;
+    int a = pair / s.n_drones, j = pair - a * s.n_drones;
+    int tab_pair = -1;
+    const bool tab_smem = s.t_max <= SCREEN_TAB;
+
     for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int pair = item / chunks_per_pair;
-        const uint32_t c = item - pair * chunks_per_pair;
-        const int a = pair / s.n_drones, j = pair - a * s.n_drones;
         const TrackDev* __restrict__ tk = s.tracks + a;
         const int VL = __ldg(&tk->n_steps);
         const int takeoff_t = __ldg(&tk->takeoff_t);
@@ -486,6 +493,16 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         // ---------------- phase A: draws + histogram over t1st buckets
         for (int h = tid; h < 80; h += BLOCK) hist[h] = 0;
         __syncthreads();      // every thread is done with the previous item's stage[] and tiles
+
+        if (tab_smem && tab_pair != pair) {       // after the barrier above: nobody reads the old tables
+            if (tid < takeoff_t) {
+                tabk[tid] = __ldg(&s.kink[(size_t)pair * s.t_max + tid]);
+                tabp[tid] = __ldg(&s.p1f[(size_t)j * s.t_max + tid]);
+            }
+            tab_pair = pair;
+        }
+        const double2* __restrict__ kk_tab = tab_smem ? tabk : s.kink + (size_t)pair * s.t_max;
+        const float2* __restrict__ pl_tab = tab_smem ? tabp : s.p1f + (size_t)j * s.t_max;
 
         const bool single = (n_tiles == 1);
         const bool need_load = !(single && loaded_track == a);
@@ -551,7 +568,6 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         if (single && need_load) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
         loaded_track = single ? a : -1;
 
-        const float zlf = (float)(s.start_alt - s.oz);
         const float thr = r.decide_fp32 ? s.thr2_fp32 : s.thr2_screen;
 
         // ---------------- R rounds: set up one packed pair, scan it
@@ -578,7 +594,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                         bx = __uint_as_float(q.x >> 9); by = __uint_as_float(q.y >> 9);
                         sx = 1.f; sy = 2.f; t1 = (int32_t)(q.w >> 12);
                     } else {
-                        const Fast32 u = setup_fast32(s, tk, pair, j, s1_first, q, zlf);
+                        const Fast32 u = setup_fast32(s, tk, kk_tab, pl_tab, s1_first, q);
                         bx = u.bx; by = u.by; sx = u.sx; sy = u.sy;
                         fmask |= u.force ? (1u << m) : 0u; t1 = u.t1st;
                     }
@@ -662,6 +678,15 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     }
                 }
             }
+        }
+
+        c += gridDim.x;                           // next item of this CTA
+        if (c >= chunks_per_pair) {
+            const uint32_t adv = c / chunks_per_pair;
+            c -= adv * chunks_per_pair;
+            pair += (int)adv;
+            a = pair / s.n_drones;
+            j = pair - a * s.n_drones;
         }
     }
     flush_stats(r, 0, acc_t1, acc_is, 0, 0);
