@@ -52,6 +52,12 @@ class Run(C.Structure):
                 ("replay", C.c_void_p)]
 
 
+class AllPairsRun(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("ray_begin", C.c_uint64), ("ray_count", C.c_uint64),
+                ("ref_takeoff_t", C.c_int32), ("record_capacity", C.c_uint32), ("drone_id_base", C.c_uint32),
+                ("reserved", C.c_uint32), ("ref_box", C.c_double * 6)]
+
+
 class Stats(C.Structure):
     _fields_ = [("trials", C.c_uint64), ("tests_evaluated", C.c_uint64), ("tests_shared", C.c_uint64),
                 ("tests_issued", C.c_uint64), ("drone_steps", C.c_uint64), ("level2", C.c_uint64),
@@ -84,7 +90,7 @@ _host = None
 DCRP_SYMBOLS = [
     "dcrp_abi_version", "dcrp_last_error", "dcrp_default_model", "dcrp_engine_create",
     "dcrp_engine_destroy", "dcrp_target_box", "dcrp_simulate", "dcrp_scenario_upload",
-    "dcrp_run_async", "dcrp_fetch", "dcrp_last_run_ms", "dcrp_dump_draws", "dcrp_trajectories",
+    "dcrp_run_async", "dcrp_fetch", "dcrp_last_run_ms", "dcrp_allpairs", "dcrp_dump_draws", "dcrp_trajectories",
     "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_launch_count", "dcrp_device_info",
 ]
 DCRP_HOST_SYMBOLS = [
@@ -114,6 +120,7 @@ def lib():
                                            C.c_int32, C.POINTER(Model)]
         L.dcrp_run_async.argtypes = [C.c_void_p, C.POINTER(Run), C.c_void_p, C.c_void_p]
         L.dcrp_fetch.argtypes = [C.c_void_p, C.POINTER(Result)]
+        L.dcrp_allpairs.argtypes = [C.c_void_p, C.POINTER(AllPairsRun), C.POINTER(Result)]
         L.dcrp_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dcrp_dump_draws.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Run), C.c_void_p]
         L.dcrp_trajectories.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, c_double_p, C.POINTER(C.c_int32)]
@@ -321,6 +328,19 @@ class Engine:
         n_pairs = self.n_tracks * self.n_drones
         res, counts, first, recs, per = self._result_buffers(n_pairs, run)
         _check(lib().dcrp_fetch(self._h, C.byref(res)))
+        return self._wrap(res, counts, first, recs, per, n_pairs, run.trial_count)
+
+    def allpairs(self, seed, ray_begin, ray_count, ref_takeoff_t, ref_box, record_capacity=0, drone_id_base=0):
+        """dcrp_allpairs on the uploaded scenario: every ray against every track."""
+        ar = AllPairsRun()
+        ar.seed, ar.ray_begin, ar.ray_count = int(seed), int(ray_begin), int(ray_count)
+        ar.ref_takeoff_t, ar.record_capacity, ar.drone_id_base = int(ref_takeoff_t), int(record_capacity), int(drone_id_base)
+        for k in range(6):
+            ar.ref_box[k] = float(ref_box[k])
+        run = self._run_struct(seed, ray_begin, ray_count, MIXED, 0, record_capacity)
+        n_pairs = self.n_tracks * self.n_drones
+        res, counts, first, recs, per = self._result_buffers(n_pairs, run)
+        _check(lib().dcrp_allpairs(self._h, C.byref(ar), C.byref(res)))
         return self._wrap(res, counts, first, recs, per, n_pairs, run.trial_count)
 
     def last_run_ms(self):

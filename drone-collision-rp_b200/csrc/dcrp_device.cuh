@@ -74,6 +74,25 @@ struct Candidate {       // a trial the fp32 screen could not rule out
     uint64_t trial;
 };
 
+// All-pairs stress run (BASELINE config 5): every ray against every track.
+struct AllPairsDev {
+    uint64_t seed, ray_begin, ray_count;       // rays [begin, begin+count) of every drone
+    uint32_t drone_base;
+    int32_t  ref_takeoff_t;
+    double   ref_box[6];
+    double   wx32, wy32;                       // ref box extents * 2^-32 (fast set-up)
+    float    wz32, z0rel;
+    uint32_t* hist;                            // [n_drones * ref_takeoff_t] rays per (drone, t1st); then bases
+    uint32_t* rank;                            // [n_drones * ray_count]
+    float4*   ray;                             // [n_drones * ray_count] (bx, by, sx, sy), per drone sorted by t1st
+    uint2*    meta;                            // [n_drones * ray_count] (t1st | degenerate << 31, ray_local)
+    uint2*    l2;                              // level-2 list: (track, drone * ray_count + slot)
+    uint32_t* l2_count;
+    uint32_t  l2_cap;
+    uint32_t  blocks_per_drone;                // ray blocks of AP_RAYS rays
+    uint32_t  tracks_per_chunk, n_tchunks;
+};
+
 enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_LEVEL2, ST_COUNT };
 
 struct RunDev {

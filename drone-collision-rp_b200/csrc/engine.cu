@@ -125,6 +125,9 @@ struct dcrp_engine {
     size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;
     DevBuf d_records, d_cands, d_replay;
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
+    bool allpairs_run = false;
+    uint64_t ap_rays = 0;
+    DevBuf d_ap_hist, d_ap_rank, d_ap_ray, d_ap_meta, d_ap_l2;
     DevBuf d_scratch;    // peak kernels / draws / trajectories
     DevBuf d_flush;      // 256 MB written by dcrp_flush_l2 (> 126 MB of L2)
 };
@@ -189,7 +192,8 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_out, &e->d_records,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
-                      &e->d_trial_min, &e->d_scratch, &e->d_flush};
+                      &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_ray,
+                      &e->d_ap_meta, &e->d_ap_l2};
     for (DevBuf* b : bufs) b->release();
     e->h_scn.release();
     e->h_out.release();
@@ -297,8 +301,11 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.ox = std::floor(0.5 * (lo[0] + hi[0]));
     s.oy = std::floor(0.5 * (lo[1] + hi[1]));
     s.oz = std::floor(0.5 * (lo[2] + hi[2]));
+    // + the distance flown inside one scan tile: the incremental scan's rounding is bounded by the
+    // ulp of the largest coordinate met since the tile's exact re-base
     const double extent = std::max({hi[0] - s.ox, s.ox - lo[0], hi[1] - s.oy, s.oy - lo[1],
-                                    hi[2] - s.oz, s.oz - lo[2]}) + 1.0;
+                                    hi[2] - s.oz, s.oz - lo[2]}) + 1.0 +
+                          model->v_straight * (vl_max <= 128 ? 128.0 : 512.0);
     s.start_alt = model->start_alt; s.v_straight = model->v_straight; s.v_ascend = model->v_ascend;
     s.radius = model->drone_radius + model->aircraft_radius;          // Drone.cpp:260
     {   // sqrt_rn(d2) < R  <=>  d2 < c, c = smallest double whose rounded root reaches R
@@ -468,6 +475,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
 
     e->run = *run;
+    e->allpairs_run = false;
     e->run_stream = st;
     e->launches_this_run = 0;
     e->h2d_run = 0;
@@ -629,7 +637,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
 
     dcrp_stats& o = res->stats;
     std::memset(&o, 0, sizeof o);
-    o.trials = (uint64_t)n_pairs * e->run.trial_count;
+    o.trials = e->allpairs_run ? e->ap_rays : (uint64_t)n_pairs * e->run.trial_count;
     // the kernels accumulate sum(t1st) (= stage-1 tests shared per pair) and the issued lane-steps;
     // evaluated stage-2 tests and drone-steps follow from the track lengths
     uint64_t all_tests = 0, all_steps = 0;
@@ -641,6 +649,11 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     o.tests_evaluated = all_tests - stats[ST_SHARED];
     o.tests_issued = stats[ST_ISSUED];
     o.drone_steps = all_steps;
+    if (e->allpairs_run) {            // every ray against every track: the scan kernel counted them
+        o.tests_evaluated = stats[ST_EVALUATED];
+        o.tests_shared = 0;
+        o.drone_steps = 0;
+    }
     o.candidates = stats[ST_CANDIDATES];
     o.level2 = stats[ST_LEVEL2];
     o.hits = stats[ST_HITS];
@@ -671,6 +684,132 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
     rc = dcrp_fetch(e, result);
     if (rc != DCRP_OK) return rc;
     result->stats.h2d_bytes += e->h2d_scenario;
+    return DCRP_OK;
+}
+
+// ------------------------------------------------------------------ all-pairs stress
+extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_result* result)
+{
+    if (!e || !run || !result) return fail(DCRP_ERR_INVALID, "dcrp_allpairs: NULL argument");
+    if (!result->counts) return fail(DCRP_ERR_INVALID, "dcrp_allpairs: result->counts is required");
+    if (!e->has_scenario) return fail(DCRP_ERR_STATE, "dcrp_allpairs before dcrp_scenario_upload");
+    const ScenarioDev& s = e->sd;
+    if (run->ref_takeoff_t < 1 || run->ref_takeoff_t > s.t_max)
+        return fail(DCRP_ERR_INVALID, "ref_takeoff_t=%d must be in [1, %d] (largest takeoff_t of the scenario)",
+                    run->ref_takeoff_t, s.t_max);
+    for (int k = 0; k < 3; ++k)
+        if (!(run->ref_box[2 * k] <= run->ref_box[2 * k + 1]))
+            return fail(DCRP_ERR_INVALID, "ref_box is inverted or NaN");
+    const uint64_t n_rays = (uint64_t)s.n_drones * run->ray_count;
+    if (n_rays >= (1ull << 32)) return fail(DCRP_ERR_INVALID, "at most 2^32 rays per call");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
+
+    dcrp_run as_run{};                      // what dcrp_fetch reports against
+    as_run.seed = run->seed; as_run.trial_begin = run->ray_begin; as_run.trial_count = run->ray_count;
+    as_run.precision = DCRP_PRECISION_MIXED; as_run.record_capacity = run->record_capacity;
+    e->run = as_run;
+    e->allpairs_run = true;
+    e->ap_rays = n_rays;
+    e->run_stream = st;
+    e->launches_this_run = 0;
+    e->h2d_run = 0;
+    e->external_counts = false;
+    e->rec_cap = run->record_capacity ? run->record_capacity : DEFAULT_RECORD_CAP;
+
+    e->out_counts_off = align256(16 + sizeof(unsigned long long) * ST_COUNT);
+    e->out_first_off = align256(e->out_counts_off + sizeof(uint64_t) * n_pairs);
+    e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
+    CU(e->d_out.need(e->out_bytes));
+    CU(e->h_out.need(e->out_bytes));
+    CU(e->d_records.need(sizeof(Record) * (size_t)e->rec_cap));
+    constexpr uint32_t L2_CAP = 1u << 22;
+    const size_t hist_bytes = sizeof(uint32_t) * ((size_t)s.n_drones * run->ref_takeoff_t + 1);
+    CU(e->d_ap_hist.need(hist_bytes));
+    CU(e->d_ap_rank.need(sizeof(uint32_t) * std::max<uint64_t>(1, n_rays)));
+    CU(e->d_ap_ray.need(sizeof(float4) * std::max<uint64_t>(1, n_rays)));
+    CU(e->d_ap_meta.need(sizeof(uint2) * std::max<uint64_t>(1, n_rays)));
+    CU(e->d_ap_l2.need(sizeof(uint2) * (size_t)L2_CAP));
+
+    RunDev r{};
+    r.seed = run->seed; r.trial_begin = run->ray_begin; r.trial_count = run->ray_count;
+    r.drone_base = run->drone_id_base;
+    r.counts = reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + e->out_counts_off);
+    r.first_conflict = reinterpret_cast<int32_t*>(e->d_out.as<unsigned char>() + e->out_first_off);
+    r.records = e->d_records.as<Record>();
+    r.rec_count = small_rec_count(e);
+    r.rec_cap = e->rec_cap;
+    r.cand_count = small_cand_count(e);
+    r.stats = small_stats(e);
+
+    AllPairsDev ap{};
+    ap.seed = run->seed; ap.ray_begin = run->ray_begin; ap.ray_count = run->ray_count;
+    ap.drone_base = run->drone_id_base;
+    ap.ref_takeoff_t = run->ref_takeoff_t;
+    std::memcpy(ap.ref_box, run->ref_box, sizeof ap.ref_box);
+    ap.wx32 = (run->ref_box[1] - run->ref_box[0]) * (1.0 / 4294967296.0);
+    ap.wy32 = (run->ref_box[3] - run->ref_box[2]) * (1.0 / 4294967296.0);
+    ap.wz32 = (float)((run->ref_box[5] - run->ref_box[4]) * (1.0 / 4294967296.0));
+    ap.z0rel = (float)(run->ref_box[4] - s.start_alt);
+    ap.hist = e->d_ap_hist.as<uint32_t>();
+    ap.rank = e->d_ap_rank.as<uint32_t>();
+    ap.ray = e->d_ap_ray.as<float4>();
+    ap.meta = e->d_ap_meta.as<uint2>();
+    ap.l2 = e->d_ap_l2.as<uint2>();
+    ap.l2_count = ap.hist + (size_t)s.n_drones * run->ref_takeoff_t;      // last word of the hist buffer
+    ap.l2_cap = L2_CAP;
+    ap.blocks_per_drone = (uint32_t)((run->ray_count + AP_RAYS - 1) / AP_RAYS);
+
+    CU(cudaEventRecord(e->ev_begin, st));
+    k_run_init<<<(unsigned)((e->out_bytes / 4 + 255) / 256), 256, 0, st>>>(
+        e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4));
+    ++e->launches; ++e->launches_this_run;
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(ap.hist, 0, hist_bytes, st));
+    if (n_rays) {
+        const unsigned rb = (unsigned)((n_rays + 255) / 256);
+        k_ap_count<<<rb, 256, 0, st>>>(s, ap);
+        k_ap_scan<<<(unsigned)s.n_drones, 32, 0, st>>>(s, ap);
+        k_ap_scatter<<<rb, 256, 0, st>>>(s, ap);
+        e->launches += 3; e->launches_this_run += 3;
+        CU(cudaGetLastError());
+
+        const size_t smem = (size_t)AP_STAGES * AP_TILE * 16 + 2 * AP_STAGES * sizeof(uint64_t);
+        static int occ = 0;
+        if (occ == 0) {
+            CU(cudaFuncSetAttribute(k_ap_scan_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ap_scan_tracks, AP_BLOCK, smem));
+            if (occ < 1) occ = 1;
+        }
+        const uint64_t n_rblocks = (uint64_t)s.n_drones * ap.blocks_per_drone;
+        const uint64_t resident = (uint64_t)e->prop.multiProcessorCount * occ;
+        // enough items to balance the persistent CTAs: split the tracks when there are few ray blocks
+        uint64_t tchunks = std::max<uint64_t>(1, (4 * resident + n_rblocks - 1) / n_rblocks);
+        tchunks = std::min<uint64_t>(tchunks, (uint64_t)s.n_tracks);
+        ap.tracks_per_chunk = (uint32_t)(((uint64_t)s.n_tracks + tchunks - 1) / tchunks);
+        ap.n_tchunks = (uint32_t)(((uint64_t)s.n_tracks + ap.tracks_per_chunk - 1) / ap.tracks_per_chunk);
+        const uint64_t n_items = n_rblocks * ap.n_tchunks;
+        if (n_items >= (1ull << 32)) return fail(DCRP_ERR_INVALID, "too many all-pairs work items");
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, resident);
+        k_ap_scan_tracks<<<grid, AP_BLOCK, smem, st>>>(s, r, ap, (uint32_t)n_items);
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e->ev_trials, st));
+    if (n_rays) {
+        k_ap_resolve<<<e->prop.multiProcessorCount * 4, 128, 0, st>>>(s, r, ap);
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(e->ev_end, st));
+    e->has_run = true;
+    uint32_t l2n = 0;
+    CU(cudaMemcpyAsync(&l2n, ap.l2_count, sizeof l2n, cudaMemcpyDeviceToHost, st));
+    int rc = dcrp_fetch(e, result);
+    if (rc != DCRP_OK) return rc;
+    if (l2n > L2_CAP)
+        return fail(DCRP_ERR_STATE, "level-2 list overflow (%u > %u entries): lower ray_count per call", l2n, L2_CAP);
     return DCRP_OK;
 }
 

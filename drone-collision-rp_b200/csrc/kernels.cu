@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
             s.p1f[(size_t)j * s.t_max + i] = make_float2((float)DSUB(x, s.ox), (float)DSUB(y, s.oy));
         }
         s.kink[(size_t)pair * s.t_max + i] = make_double2(DSUB(t.box[0], x), DSUB(t.box[2], y));
-        if (i < t.takeoff_t && i < t.n_steps) {
+        if (i < t.n_steps) {      // all i < t_max: all-pairs rays may kink later than this track's takeoff_t
             const double d2 = sep2(x, y, s.start_alt, s.ax[t.off + i], s.ay[t.off + i], s.az[t.off + i]);
             if (d2 < mn) mn = d2;
             if (d2 < s.thr_d2 && first == INT_MAX) first = i;
@@ -693,6 +693,246 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     const unsigned long long nc = warp_sum_u64(ncand), np = warp_sum_u64(npass);
     if (lane == 0 && nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
     if (lane == 0 && np) atomicAdd(&r.stats[ST_LEVEL2], np);
+}
+
+// =========================================================================
+// all-pairs stress path (BASELINE config 5): n_drones x ray_count rays, drawn ONCE against a
+// reference box / takeoff time, each tested against EVERY track of the scenario.  Not in the
+// reference (it only ever pairs one aircraft with one drone's trials); same kinematics, same
+// three-level decision (horizontal fp32 -> 3-D fp32 -> fp64 reference arithmetic).
+// =========================================================================
+constexpr uint32_t AP_TRACK_ID = 0xFFFFFFFFu;   // Philox track id of all-pairs rays (no MC trial uses it)
+constexpr int AP_BLOCK = 256;
+constexpr int AP_RAYS = 2 * AP_BLOCK;           // rays per CTA: one packed pair per lane
+constexpr int AP_TILE = 512;                    // track samples per shared-memory tile (8 KB)
+constexpr int AP_STAGES = 3;
+
+__device__ __forceinline__ Draw ap_draw(const AllPairsDev& ap, uint32_t j, uint32_t ray_local)
+{
+    return make_draw(ap.seed, ap.ray_begin + ray_local, ap.drone_base + j, AP_TRACK_ID, ap.ref_takeoff_t,
+                     ap.ref_box);
+}
+
+// pass 1: t1st of every ray, rank within its (drone, t1st) class
+__global__ void __launch_bounds__(256) k_ap_count(const ScenarioDev s, const AllPairsDev ap)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)s.n_drones * ap.ray_count) return;
+    const uint32_t j = (uint32_t)(idx / ap.ray_count), rl = (uint32_t)(idx - (uint64_t)j * ap.ray_count);
+    const U4 w = trial_words(ap.seed, ap.ray_begin + rl, ap.drone_base + j, AP_TRACK_ID);
+    const int t1st = draw_t1st(w.x, ap.ref_takeoff_t);
+    ap.rank[idx] = atomicAdd(&ap.hist[(size_t)j * ap.ref_takeoff_t + (t1st - 1)], 1u);
+}
+
+// pass 2: per drone, exclusive prefix over t1st classes (one warp per drone)
+__global__ void __launch_bounds__(32) k_ap_scan(const ScenarioDev s, const AllPairsDev ap)
+{
+    const int j = blockIdx.x;
+    uint32_t carry = 0;
+    for (int base = 0; base < ap.ref_takeoff_t; base += 32) {
+        const int i = base + (int)threadIdx.x;
+        const uint32_t v = i < ap.ref_takeoff_t ? ap.hist[(size_t)j * ap.ref_takeoff_t + i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)threadIdx.x >= o) inc += u;
+        }
+        if (i < ap.ref_takeoff_t) ap.hist[(size_t)j * ap.ref_takeoff_t + i] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// pass 3: ray set-up (the level-1 horizontal ray), written at its sorted slot
+__global__ void __launch_bounds__(256) k_ap_scatter(const ScenarioDev s, const AllPairsDev ap)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)s.n_drones * ap.ray_count) return;
+    const uint32_t j = (uint32_t)(idx / ap.ray_count), rl = (uint32_t)(idx - (uint64_t)j * ap.ray_count);
+    const U4 w = trial_words(ap.seed, ap.ray_begin + rl, ap.drone_base + j, AP_TRACK_ID);
+    const int t1st = draw_t1st(w.x, ap.ref_takeoff_t);
+    const int last = t1st - 1;
+    const double xl = s.p1x[(size_t)j * s.t_max + last], yl = s.p1y[(size_t)j * s.t_max + last];
+    const float2 pl = s.p1f[(size_t)j * s.t_max + last];
+    const float dls = (float)fma((double)w.y, ap.wx32, ap.ref_box[0] - xl);
+    const float dbs = (float)fma((double)w.z, ap.wy32, ap.ref_box[2] - yl);
+    const float ada = fabsf(fmaf((float)w.w, ap.wz32, ap.z0rel));
+    const float m2 = fmaf(dls, dls, dbs * dbs);
+    const float inv_m = rsqrtf(m2);
+    const float k = inv_m * fmaf(-s.coef_f, atanf(ada * inv_m), s.v_straight_f);
+    const float sx = dls * k, sy = dbs * k, lastf = (float)last;
+    const uint32_t slot = ap.hist[(size_t)j * ap.ref_takeoff_t + last] + ap.rank[idx];
+    const size_t o = (size_t)j * ap.ray_count + slot;
+    ap.ray[o] = make_float4(fmaf(-lastf, sx, pl.x), fmaf(-lastf, sy, pl.y), sx, sy);
+    ap.meta[o] = make_uint2((uint32_t)t1st | (!(m2 > 1e-12f) ? 0x80000000u : 0u), rl);
+}
+
+// The scan: a CTA keeps AP_RAYS sorted rays of one drone in registers (one packed pair per lane) and
+// streams the samples of a chunk of tracks through a 3-stage TMA/mbarrier ring.  Per track the
+// running horizontal minimum is reset, and a (ray, track) pair that comes within R + margin
+// horizontally is appended (warp-aggregated) to the level-2 list.
+__global__ void __launch_bounds__(AP_BLOCK, 3)
+k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint32_t n_items)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4*   tiles = reinterpret_cast<float4*>(smem_raw);                        // AP_STAGES x AP_TILE
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + (size_t)AP_STAGES * AP_TILE * 16);
+    uint64_t* empty = full + AP_STAGES;
+    constexpr int NW = AP_BLOCK / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int b = 0; b < AP_STAGES; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t G = 0;                       // tiles consumed so far by this CTA (ring position, all items)
+    unsigned long long ev = 0, is = 0, nl2 = 0;
+
+    for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t rb = item / ap.n_tchunks, tc = item - rb * ap.n_tchunks;
+        const uint32_t j = rb / ap.blocks_per_drone, blk = rb - j * ap.blocks_per_drone;
+        const int a_begin = (int)(tc * ap.tracks_per_chunk);
+        const int a_end = min(s.n_tracks, a_begin + (int)ap.tracks_per_chunk);
+
+        // ---- this lane's packed pair of rays
+        float2 BX, BY, SX, SY;
+        int t1[2];
+        uint32_t rid[2];
+        bool degen[2];
+        int tmin = INT_MAX;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const uint32_t slot = blk * AP_RAYS + (uint32_t)(warp * 64 + m * 32 + lane);
+            float4 q = make_float4(1e15f, 1e15f, 0.f, 0.f);
+            t1[m] = INT_MAX; rid[m] = 0xFFFFFFFFu; degen[m] = false;
+            if (slot < ap.ray_count) {
+                const size_t o = (size_t)j * ap.ray_count + slot;
+                q = __ldg(&ap.ray[o]);
+                const uint2 mt = __ldg(&ap.meta[o]);
+                t1[m] = (int)(mt.x & 0x7fffffffu); degen[m] = (mt.x >> 31) != 0u; rid[m] = (uint32_t)o;
+                tmin = min(tmin, t1[m]);
+            }
+            if (m) { BX.y = q.x; BY.y = q.y; SX.y = q.z; SY.y = q.w; }
+            else   { BX.x = q.x; BY.x = q.y; SX.x = q.z; SY.x = q.w; }
+        }
+        const int imin = __reduce_min_sync(0xffffffffu, tmin);
+
+        // ---- tile sequence of the item: tracks a_begin..a_end-1, each ceil(n_steps / AP_TILE) tiles.
+        // Producer cursor (thread 0) runs AP_STAGES-1 tiles ahead of the consumer cursor (all threads).
+        int pa = a_begin, pt = 0;                     // producer: next tile to load
+        uint32_t PG = G;                              // its ring position
+        auto produce = [&]() {
+            if (pa >= a_end) return;
+            const int VLp = __ldg(&s.tracks[pa].n_steps);
+            const uint32_t off = __ldg(&s.tracks[pa].off);
+            const int b = (int)(PG % AP_STAGES);
+            if (PG >= (uint32_t)AP_STAGES) mbar_wait(&empty[b], ((PG / AP_STAGES) - 1u) & 1u);
+            fence_proxy_async();
+            const uint32_t bytes = (uint32_t)min(AP_TILE, VLp - pt * AP_TILE) * 16u;
+            mbar_arrive_expect_tx(&full[b], bytes);
+            tma_bulk_g2s(tiles + (size_t)b * AP_TILE, s.trk32 + off + (size_t)pt * AP_TILE, bytes, &full[b]);
+            ++PG;
+            if ((pt + 1) * AP_TILE >= VLp) { ++pa; pt = 0; } else { ++pt; }
+        };
+        if (tid == 0) {
+#pragma unroll 1
+            for (int k = 0; k < AP_STAGES - 1; ++k) produce();
+        }
+
+        float mn0 = 3.0e38f, mn1 = 3.0e38f;
+        for (int a = a_begin; a < a_end; ++a) {
+            const int VL = __ldg(&s.tracks[a].n_steps);
+            const int n_tiles = (VL + AP_TILE - 1) / AP_TILE;
+            const int s1f = __ldg(&s.s1_first_hit[(size_t)a * s.n_drones + j]);
+            for (int tl = 0; tl < n_tiles; ++tl) {
+                if (tid == 0) produce();
+                const int b = (int)(G % AP_STAGES);
+                mbar_wait(&full[b], (G / AP_STAGES) & 1u);
+                const int t0 = tl * AP_TILE;
+                const int lo = max(imin, t0), hi = min(VL, t0 + AP_TILE);
+                if (lo < hi) {
+                    const float4* __restrict__ tp = tiles + (size_t)b * AP_TILE - (size_t)t0;
+                    const float lof = (float)lo;
+                    const float2 lo2 = make_float2(lof, lof);
+                    float2 PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);     // exact re-base per tile
+#pragma unroll 4
+                    for (int i = lo; i < hi; ++i) {
+                        const float2 p = *reinterpret_cast<const float2*>(&tp[i]);
+                        const float2 dx = fadd2(PX, make_float2(p.x, p.x));
+                        const float2 dy = fadd2(PY, make_float2(p.y, p.y));
+                        const float2 d2 = ffma2(dy, dy, fmul2(dx, dx));
+                        mn0 = fminf(mn0, d2.x);
+                        mn1 = fminf(mn1, d2.y);
+                        PX = fadd2(PX, SX); PY = fadd2(PY, SY);
+                    }
+                    is += (unsigned long long)(hi - lo) * 2ull;
+                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[b])) : "memory");
+                ++G;
+            }
+            // ---- end of track a: bookkeeping + rare level-2 append, then reset the minima
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                if (t1[m] == INT_MAX) continue;
+                ev += (unsigned long long)max(0, VL - t1[m]);
+                const float mn = m ? mn1 : mn0;
+                if (mn < s.thr2_screen || degen[m] || s1f <= t1[m] - 1) {
+                    ++nl2;
+                    const uint32_t slot = warp_claim_slot(ap.l2_count);
+                    if (slot < ap.l2_cap) ap.l2[slot] = make_uint2((uint32_t)a, rid[m]);
+                }
+            }
+            mn0 = 3.0e38f; mn1 = 3.0e38f;
+        }
+    }
+    ev = warp_sum_u64(ev); is = warp_sum_u64(is); nl2 = warp_sum_u64(nl2);
+    if (lane == 0) {
+        if (ev) atomicAdd(&r.stats[ST_EVALUATED], ev);
+        if (is) atomicAdd(&r.stats[ST_ISSUED], is);
+        if (nl2) atomicAdd(&r.stats[ST_LEVEL2], nl2);
+    }
+}
+
+// Levels 2 and 3 of the all-pairs path: one thread per (track, ray) entry of the level-2 list.
+__global__ void __launch_bounds__(128) k_ap_resolve(const ScenarioDev s, const RunDev r, const AllPairsDev ap)
+{
+    const uint32_t n = min(*ap.l2_count, ap.l2_cap);
+    unsigned long long hits = 0, ncand = 0;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const uint2 e = ap.l2[idx];
+        const int a = (int)e.x;
+        const uint32_t j = (uint32_t)(e.y / ap.ray_count);
+        const uint2 mt = ap.meta[e.y];
+        const TrackDev t = s.tracks[a];
+        const int pair = a * s.n_drones + (int)j;
+        const Draw d = ap_draw(ap, j, mt.y);
+        const int last = d.t1st - 1;
+        const int s1f = s.s1_first_hit[pair];
+        bool go = (mt.x >> 31) != 0u || s1f <= last;
+        if (!go) {                                    // level 2: 3-D fp32, fused form
+            const double xl = s.p1x[(size_t)j * s.t_max + last], yl = s.p1y[(size_t)j * s.t_max + last];
+            Setup32 u;
+            u.t1st = d.t1st;
+            u.ray = stage2_ray32((float)DSUB(d.tx, xl), (float)DSUB(d.ty, yl), (float)DSUB(d.tz, s.start_alt),
+                                 (float)DSUB(xl, s.ox), (float)DSUB(yl, s.oy), (float)DSUB(s.start_alt, s.oz),
+                                 (float)last, s.v_straight_f, s.coef_f);
+            go = u.ray.degenerate || min3d_fp32(s, t, u) < s.thr2_screen;
+        }
+        if (!go) continue;
+        ++ncand;                                      // level 3: fp64, reference order of operations
+        const TrialOut o = exact_trial(s, pair, (int)j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
+        if (o.first >= 0) {
+            ++hits;
+            publish_hit(s, r, pair, a, (int)j, ap.ray_begin + mt.y, d, o);
+        }
+    }
+    hits = warp_sum_u64(hits); ncand = warp_sum_u64(ncand);
+    if (lane_id() == 0) {
+        if (hits) atomicAdd(&r.stats[ST_HITS], hits);
+        if (ncand) atomicAdd(&r.stats[ST_CANDIDATES], ncand);
+    }
 }
 
 // =========================================================================

@@ -193,6 +193,26 @@ int  dcrp_fetch(dcrp_engine* e, dcrp_result* result);
 /* Milliseconds of the last run (device time between the engine's events). */
 int  dcrp_last_run_ms(dcrp_engine* e, float* ms);
 
+/* ---- all-pairs stress (BASELINE config 5; an extension, not in the reference) ---------- */
+/* Every ray against every track.  A ray is one trial's flight -- drone j, t1st ~ U{1..ref_takeoff_t},
+ * target uniform in ref_box -- drawn ONCE from Philox(key = seed, counter = (ray_lo, ray_hi,
+ * drone_id_base + j, 0xFFFFFFFF)) and then tested, with the kinematics and the separation test of
+ * Drone.cpp:107-127,164-231,253-265, against EVERY track of the uploaded scenario (the reference
+ * only ever pairs one aircraft with one drone's own trials).  ref_takeoff_t must not exceed the
+ * largest takeoff_t of the scenario.  result->counts[a * n_drones + j] += rays of drone j that
+ * collide with track a; records carry trial = ray id.  Blocking. */
+typedef struct dcrp_allpairs_run {
+    uint64_t seed;
+    uint64_t ray_begin;        /* rays [ray_begin, ray_begin + ray_count) of every drone */
+    uint64_t ray_count;
+    int32_t  ref_takeoff_t;
+    uint32_t record_capacity;
+    uint32_t drone_id_base;
+    uint32_t reserved;
+    double   ref_box[6];
+} dcrp_allpairs_run;
+int  dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_result* result);
+
 /* ---- replay / records --------------------------------------------------- */
 /* The Philox draws of trials [run->trial_begin, +run->trial_count) of scenario
  * pair (track, drone) -- seed and id bases from `run` -- generated ON DEVICE by
