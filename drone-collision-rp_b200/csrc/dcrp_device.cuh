@@ -84,7 +84,13 @@ struct AllPairsDev {
     float    wz32, z0rel;
     uint32_t* hist;                            // [n_drones * ref_takeoff_t] rays per (drone, t1st); then bases
     uint32_t* rank;                            // [n_drones * ray_count]
-    float4*   ray;                             // [n_drones * ray_count] (bx, by, sx, sy), per drone sorted by t1st
+    // rays per drone sorted by t1st and stored pair-interleaved, so that a lane's two rays arrive as
+    // ready-made aligned f32x2 register pairs: group g = slot/64 holds 32 lane records,
+    //   rayA[(j*groups + g)*32 + lane] = (bx0, bx1, by0, by1),  rayB[...] = (sx0, sx1, sy0, sy1)
+    // with ray m of the lane = sorted slot g*64 + m*32 + lane (slots >= ray_count are dead: b = 1e15)
+    float*    rayA;
+    float*    rayB;
+    uint32_t  groups;                          // ceil(ray_count / 64)
     uint2*    meta;                            // [n_drones * ray_count] (t1st | degenerate << 31, ray_local)
     uint2*    l2;                              // level-2 list: (track, drone * ray_count + slot)
     uint32_t* l2_count;

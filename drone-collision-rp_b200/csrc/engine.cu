@@ -127,7 +127,7 @@ struct dcrp_engine {
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
     bool allpairs_run = false;
     uint64_t ap_rays = 0;
-    DevBuf d_ap_hist, d_ap_rank, d_ap_ray, d_ap_meta, d_ap_l2;
+    DevBuf d_ap_hist, d_ap_rank, d_ap_rayA, d_ap_rayB, d_ap_meta, d_ap_l2;
     DevBuf d_scratch;    // peak kernels / draws / trajectories
     DevBuf d_flush;      // 256 MB written by dcrp_flush_l2 (> 126 MB of L2)
 };
@@ -192,8 +192,8 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_out, &e->d_records,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
-                      &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_ray,
-                      &e->d_ap_meta, &e->d_ap_l2};
+                      &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
+                      &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2};
     for (DevBuf* b : bufs) b->release();
     e->h_scn.release();
     e->h_out.release();
@@ -728,7 +728,10 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     const size_t hist_bytes = sizeof(uint32_t) * ((size_t)s.n_drones * run->ref_takeoff_t + 1);
     CU(e->d_ap_hist.need(hist_bytes));
     CU(e->d_ap_rank.need(sizeof(uint32_t) * std::max<uint64_t>(1, n_rays)));
-    CU(e->d_ap_ray.need(sizeof(float4) * std::max<uint64_t>(1, n_rays)));
+    const uint32_t groups = (uint32_t)((run->ray_count + 63) / 64);
+    const size_t ray_bytes = sizeof(float) * 4 * 32 * std::max<size_t>(1, (size_t)s.n_drones * groups);
+    CU(e->d_ap_rayA.need(ray_bytes));
+    CU(e->d_ap_rayB.need(ray_bytes));
     CU(e->d_ap_meta.need(sizeof(uint2) * std::max<uint64_t>(1, n_rays)));
     CU(e->d_ap_l2.need(sizeof(uint2) * (size_t)L2_CAP));
 
@@ -754,7 +757,9 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     ap.z0rel = (float)(run->ref_box[4] - s.start_alt);
     ap.hist = e->d_ap_hist.as<uint32_t>();
     ap.rank = e->d_ap_rank.as<uint32_t>();
-    ap.ray = e->d_ap_ray.as<float4>();
+    ap.rayA = e->d_ap_rayA.as<float>();
+    ap.rayB = e->d_ap_rayB.as<float>();
+    ap.groups = groups;
     ap.meta = e->d_ap_meta.as<uint2>();
     ap.l2 = e->d_ap_l2.as<uint2>();
     ap.l2_count = ap.hist + (size_t)s.n_drones * run->ref_takeoff_t;      // last word of the hist buffer
@@ -771,7 +776,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         const unsigned rb = (unsigned)((n_rays + 255) / 256);
         k_ap_count<<<rb, 256, 0, st>>>(s, ap);
         k_ap_scan<<<(unsigned)s.n_drones, 32, 0, st>>>(s, ap);
-        k_ap_scatter<<<rb, 256, 0, st>>>(s, ap);
+        k_ap_scatter<<<(unsigned)(((uint64_t)s.n_drones * groups * 64 + 255) / 256), 256, 0, st>>>(s, ap);
         e->launches += 3; e->launches_this_run += 3;
         CU(cudaGetLastError());
 

@@ -71,6 +71,40 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
     return *reinterpret_cast<float2*>(&rd);
 }
+// The same on opaque 64-bit handles: a value that lives in ONE aligned register pair for its whole
+// life.  (Assembling a float2 from two unrelated scalars lets ptxas re-pack it with MOVs inside the
+// hot loop; a mov.b64 pack done once outside does not.)
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t pk2(float lo, float hi)
+{
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 up2(f2_t v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f2_t ffma2(f2_t a, f2_t b, f2_t c)
+{
+    f2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2_t fadd2(f2_t a, f2_t b)
+{
+    f2_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t fmul2(f2_t a, f2_t b)
+{
+    f2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 {
     float d;
@@ -577,7 +611,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             const int q2 = rd >> 1;
             const int bin = (rd & 1) ? (q2 * 2 * NW + 2 * NW - 1 - warp) : (q2 * 2 * NW + warp);
             const uint32_t slot0 = (uint32_t)(bin * 64 + lane);
-            float2 BX, BY, SX, SY;                 // level 1 needs the horizontal ray only
+            float bxs[2], bys[2], sxs[2], sys[2];  // level 1 needs the horizontal ray only
             int tmin = INT_MAX;
             uint32_t fmask = 0;                   // bit m: trial m must go to level 2 regardless of the scan
 #pragma unroll
@@ -601,9 +635,10 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     tmin = min(tmin, t1);
                     acc_t1 += (uint32_t)t1;
                 }
-                if (m) { BX.y = bx; BY.y = by; SX.y = sx; SY.y = sy; }
-                else   { BX.x = bx; BY.x = by; SX.x = sx; SY.x = sy; }
+                bxs[m] = bx; bys[m] = by; sxs[m] = sx; sys[m] = sy;
             }
+            const f2_t BX = pk2(bxs[0], bxs[1]), BY = pk2(bys[0], bys[1]);
+            const f2_t SX = pk2(sxs[0], sxs[1]), SY = pk2(sys[0], sys[1]);
             const int imin = __reduce_min_sync(0xffffffffu, tmin);
             if (imin < VL) acc_is += (uint32_t)(VL - imin) * 2u;
 
@@ -638,14 +673,14 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 // folds them into the packed ops' scalar-broadcast operand form).
                 if (lo < hi) {
                     const float lof = (float)lo;
-                    const float2 lo2 = make_float2(lof, lof);
-                    float2 PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);
+                    const f2_t lo2 = pk2(lof, lof);
+                    f2_t PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);
 #pragma unroll 4
                     for (int i = lo; i < hi; ++i) {
                         const float2 p = *reinterpret_cast<const float2*>(&tp[i]);
-                        const float2 dx = fadd2(PX, make_float2(p.x, p.x));
-                        const float2 dy = fadd2(PY, make_float2(p.y, p.y));
-                        const float2 d2 = ffma2(dy, dy, fmul2(dx, dx));
+                        const f2_t dx = fadd2(PX, pk2(p.x, p.x));
+                        const f2_t dy = fadd2(PY, pk2(p.y, p.y));
+                        const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
                         mn0 = fminf(mn0, d2.x);
                         mn1 = fminf(mn1, d2.y);
                         PX = fadd2(PX, SX); PY = fadd2(PY, SY);
@@ -743,28 +778,39 @@ __global__ void __launch_bounds__(32) k_ap_scan(const ScenarioDev s, const AllPa
     }
 }
 
-// pass 3: ray set-up (the level-1 horizontal ray), written at its sorted slot
+// pass 3: ray set-up (the level-1 horizontal ray), written at its sorted slot; threads past
+// ray_count fill the dead slots of the last 64-ray group
 __global__ void __launch_bounds__(256) k_ap_scatter(const ScenarioDev s, const AllPairsDev ap)
 {
+    const uint64_t padded = (uint64_t)ap.groups * 64;
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)s.n_drones * ap.ray_count) return;
-    const uint32_t j = (uint32_t)(idx / ap.ray_count), rl = (uint32_t)(idx - (uint64_t)j * ap.ray_count);
-    const U4 w = trial_words(ap.seed, ap.ray_begin + rl, ap.drone_base + j, AP_TRACK_ID);
-    const int t1st = draw_t1st(w.x, ap.ref_takeoff_t);
-    const int last = t1st - 1;
-    const double xl = s.p1x[(size_t)j * s.t_max + last], yl = s.p1y[(size_t)j * s.t_max + last];
-    const float2 pl = s.p1f[(size_t)j * s.t_max + last];
-    const float dls = (float)fma((double)w.y, ap.wx32, ap.ref_box[0] - xl);
-    const float dbs = (float)fma((double)w.z, ap.wy32, ap.ref_box[2] - yl);
-    const float ada = fabsf(fmaf((float)w.w, ap.wz32, ap.z0rel));
-    const float m2 = fmaf(dls, dls, dbs * dbs);
-    const float inv_m = rsqrtf(m2);
-    const float k = inv_m * fmaf(-s.coef_f, atanf(ada * inv_m), s.v_straight_f);
-    const float sx = dls * k, sy = dbs * k, lastf = (float)last;
-    const uint32_t slot = ap.hist[(size_t)j * ap.ref_takeoff_t + last] + ap.rank[idx];
-    const size_t o = (size_t)j * ap.ray_count + slot;
-    ap.ray[o] = make_float4(fmaf(-lastf, sx, pl.x), fmaf(-lastf, sy, pl.y), sx, sy);
-    ap.meta[o] = make_uint2((uint32_t)t1st | (!(m2 > 1e-12f) ? 0x80000000u : 0u), rl);
+    if (idx >= (uint64_t)s.n_drones * padded) return;
+    const uint32_t j = (uint32_t)(idx / padded), rl = (uint32_t)(idx - (uint64_t)j * padded);
+    uint32_t slot = rl;
+    float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
+    if (rl < ap.ray_count) {
+        const U4 w = trial_words(ap.seed, ap.ray_begin + rl, ap.drone_base + j, AP_TRACK_ID);
+        const int t1st = draw_t1st(w.x, ap.ref_takeoff_t);
+        const int last = t1st - 1;
+        const double xl = s.p1x[(size_t)j * s.t_max + last], yl = s.p1y[(size_t)j * s.t_max + last];
+        const float2 pl = s.p1f[(size_t)j * s.t_max + last];
+        const float dls = (float)fma((double)w.y, ap.wx32, ap.ref_box[0] - xl);
+        const float dbs = (float)fma((double)w.z, ap.wy32, ap.ref_box[2] - yl);
+        const float ada = fabsf(fmaf((float)w.w, ap.wz32, ap.z0rel));
+        const float m2 = fmaf(dls, dls, dbs * dbs);
+        const float inv_m = rsqrtf(m2);
+        const float k = inv_m * fmaf(-s.coef_f, atanf(ada * inv_m), s.v_straight_f);
+        const float lastf = (float)last;
+        sx = dls * k; sy = dbs * k;
+        bx = fmaf(-lastf, sx, pl.x); by = fmaf(-lastf, sy, pl.y);
+        slot = ap.hist[(size_t)j * ap.ref_takeoff_t + last] + ap.rank[(size_t)j * ap.ray_count + rl];
+        ap.meta[(size_t)j * ap.ray_count + slot] =
+            make_uint2((uint32_t)t1st | (!(m2 > 1e-12f) ? 0x80000000u : 0u), rl);
+    }
+    const uint32_t g = slot >> 6, m = (slot >> 5) & 1u, ln = slot & 31u;
+    const size_t rec = (((size_t)j * ap.groups + g) * 32 + ln) * 4;
+    ap.rayA[rec + m] = bx; ap.rayA[rec + 2 + m] = by;
+    ap.rayB[rec + m] = sx; ap.rayB[rec + 2 + m] = sy;
 }
 
 // The scan: a CTA keeps AP_RAYS sorted rays of one drone in registers (one packed pair per lane) and
@@ -795,26 +841,28 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
         const int a_begin = (int)(tc * ap.tracks_per_chunk);
         const int a_end = min(s.n_tracks, a_begin + (int)ap.tracks_per_chunk);
 
-        // ---- this lane's packed pair of rays
-        float2 BX, BY, SX, SY;
-        int t1[2];
-        uint32_t rid[2];
-        bool degen[2];
+        // ---- this lane's packed pair of rays: two 16-byte loads deliver aligned f32x2 pairs
+        const uint32_t g = blk * (AP_RAYS / 64) + (uint32_t)warp;          // 64-ray group of this warp
+        f2_t BX = pk2(1e15f, 1e15f), BY = BX, SX = pk2(0.f, 0.f), SY = SX;
+        int t1[2] = {INT_MAX, INT_MAX};
+        uint32_t rid[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        bool degen[2] = {false, false};
         int tmin = INT_MAX;
+        if (g < ap.groups) {
+            const size_t rec = ((size_t)j * ap.groups + g) * 32 + lane;
+            const ulonglong2 qa = __ldg(reinterpret_cast<const ulonglong2*>(ap.rayA) + rec);
+            const ulonglong2 qb = __ldg(reinterpret_cast<const ulonglong2*>(ap.rayB) + rec);
+            BX = qa.x; BY = qa.y; SX = qb.x; SY = qb.y;
 #pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            const uint32_t slot = blk * AP_RAYS + (uint32_t)(warp * 64 + m * 32 + lane);
-            float4 q = make_float4(1e15f, 1e15f, 0.f, 0.f);
-            t1[m] = INT_MAX; rid[m] = 0xFFFFFFFFu; degen[m] = false;
-            if (slot < ap.ray_count) {
-                const size_t o = (size_t)j * ap.ray_count + slot;
-                q = __ldg(&ap.ray[o]);
-                const uint2 mt = __ldg(&ap.meta[o]);
-                t1[m] = (int)(mt.x & 0x7fffffffu); degen[m] = (mt.x >> 31) != 0u; rid[m] = (uint32_t)o;
-                tmin = min(tmin, t1[m]);
+            for (int m = 0; m < 2; ++m) {
+                const uint32_t slot = g * 64 + (uint32_t)(m * 32 + lane);
+                if (slot < ap.ray_count) {
+                    const size_t o = (size_t)j * ap.ray_count + slot;
+                    const uint2 mt = __ldg(&ap.meta[o]);
+                    t1[m] = (int)(mt.x & 0x7fffffffu); degen[m] = (mt.x >> 31) != 0u; rid[m] = (uint32_t)o;
+                    tmin = min(tmin, t1[m]);
+                }
             }
-            if (m) { BX.y = q.x; BY.y = q.y; SX.y = q.z; SY.y = q.w; }
-            else   { BX.x = q.x; BY.x = q.y; SX.x = q.z; SY.x = q.w; }
         }
         const int imin = __reduce_min_sync(0xffffffffu, tmin);
 
@@ -854,14 +902,14 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
                 if (lo < hi) {
                     const float4* __restrict__ tp = tiles + (size_t)b * AP_TILE - (size_t)t0;
                     const float lof = (float)lo;
-                    const float2 lo2 = make_float2(lof, lof);
-                    float2 PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);     // exact re-base per tile
+                    const f2_t lo2 = pk2(lof, lof);
+                    f2_t PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);        // exact re-base per tile
 #pragma unroll 4
                     for (int i = lo; i < hi; ++i) {
                         const float2 p = *reinterpret_cast<const float2*>(&tp[i]);
-                        const float2 dx = fadd2(PX, make_float2(p.x, p.x));
-                        const float2 dy = fadd2(PY, make_float2(p.y, p.y));
-                        const float2 d2 = ffma2(dy, dy, fmul2(dx, dx));
+                        const f2_t dx = fadd2(PX, pk2(p.x, p.x));
+                        const f2_t dy = fadd2(PY, pk2(p.y, p.y));
+                        const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
                         mn0 = fminf(mn0, d2.x);
                         mn1 = fminf(mn1, d2.y);
                         PX = fadd2(PX, SX); PY = fadd2(PY, SY);
