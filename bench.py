@@ -299,7 +299,7 @@ def engine_arm(args):
     t_load0 = time.time()
     wall0 = time.perf_counter()
     step_ms, trial_ms, stats_sum = [], [], {"tests_evaluated": 0, "tests_shared": 0, "tests_issued": 0,
-                                            "drone_steps": 0, "trials": 0, "candidates": 0, "hits": 0}
+                                            "drone_steps": 0, "trials": 0, "candidates": 0, "hits": 0, "level2": 0}
     flush_launches = 0
     for s in range(args.warmup, args.warmup + args.steps):
         run, e0, e1 = step(s, True)
@@ -381,14 +381,25 @@ def engine_arm(args):
     tests_per_launch = stats_sum["tests_evaluated"] / args.steps
     achieved = tests_per_launch * FLOP_PER_TEST / (k_ms * 1e-3) * 1e-12
     peak = peaks["ffma"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
     roofline = {
-        "bound": "fp32", "kernel": "k_screen<4,512>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "bound": "fp32", "kernel": "k_screen2<2,256,false,4>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": traffic,
+        "traffic_note": "DRAM bytes per launch from one ncu --set full capture (profiles/r01_traffic.json); the "
+                        "kernel is FMA-pipe bound, its inputs (~4 KB) live in shared memory",
+        "executed_fp32_flop_per_test": 7,
+        "levels": "level 1 (every test): horizontal fp32 separation, 7 executed flop (2 add advance + 2 sub + mul + "
+                  "fma); level 2 (3-D fp32) on ~5e-5 of trials; level 3 (fp64, reference arithmetic) on ~3e-7. "
+                  "`achieved` counts the ALGORITHMIC 11 flop per decided test (SURVEY 8(d)); executed = 7/11 of it",
         "peak_source": "FFMA-only micro-kernel measured on this device in this run (MEASURED_PEAKS.json has no "
                        "FP32 figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
         "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": tests_per_launch, "kernel_ms": k_ms,
         "peaks_measured_tflops": peaks,
-        "frac_of_scan_mix_ceiling": achieved / peaks["scan_mix_11flop"],
+        "achieved_executed": achieved * 7.0 / 11.0, "frac_executed": achieved * 7.0 / 11.0 / peak,
         "sustained": {"achieved": sustain["tests_per_s"] * FLOP_PER_TEST * 1e-12,
                       "frac": sustain["tests_per_s"] * FLOP_PER_TEST * 1e-12 / peak, **sustain},
         "hbm": {"note": "track 3.3 KB + ring tables per launch; records 56 B per hit: not HBM-bound",
@@ -410,7 +421,7 @@ def engine_arm(args):
         "trials_per_s": trials / secs, "drone_steps_per_s": dsteps / secs,
         "tests_per_s_incl_shared_stage1": (tests + shared) / secs,
         "tests_evaluated_per_step": tests / args.steps, "hits_in_timed_steps": stats_sum["hits"],
-        "candidates_in_timed_steps": stats_sum["candidates"],
+        "candidates_in_timed_steps": stats_sum["candidates"], "level2_in_timed_steps": stats_sum["level2"],
         "wall_ms_timed_region": wall * 1e3,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
