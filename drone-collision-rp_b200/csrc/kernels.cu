@@ -675,9 +675,11 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     const float lof = (float)lo;
                     const f2_t lo2 = pk2(lof, lof);
                     f2_t PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);
+                    const float4* __restrict__ tq = tp + lo;      // plain base + immediate offsets in the loop
+                    const int nq = hi - lo;
 #pragma unroll 4
-                    for (int i = lo; i < hi; ++i) {
-                        const float2 p = *reinterpret_cast<const float2*>(&tp[i]);
+                    for (int k = 0; k < nq; ++k) {
+                        const float2 p = *reinterpret_cast<const float2*>(&tq[k]);
                         const f2_t dx = fadd2(PX, pk2(p.x, p.x));
                         const f2_t dy = fadd2(PY, pk2(p.y, p.y));
                         const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
@@ -904,9 +906,11 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
                     const float lof = (float)lo;
                     const f2_t lo2 = pk2(lof, lof);
                     f2_t PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);        // exact re-base per tile
+                    const float4* __restrict__ tq = tp + lo;      // plain base + immediate offsets in the loop
+                    const int nq = hi - lo;
 #pragma unroll 4
-                    for (int i = lo; i < hi; ++i) {
-                        const float2 p = *reinterpret_cast<const float2*>(&tp[i]);
+                    for (int k = 0; k < nq; ++k) {
+                        const float2 p = *reinterpret_cast<const float2*>(&tq[k]);
                         const f2_t dx = fadd2(PX, pk2(p.x, p.x));
                         const f2_t dy = fadd2(PY, pk2(p.y, p.y));
                         const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));

@@ -1,0 +1,100 @@
+// Batch.cpp -- see Batch.h.
+#include "Batch.h"
+
+#include <fstream>
+#include <memory>
+#include <vector>
+
+#include "Aircraft.h"
+#include "Drone.h"
+
+namespace dcrp_host {
+
+BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols, int aircraft_begin,
+                              int aircraft_end, const std::string& drone_csv, int drone_cols, int drone_total,
+                              uint64_t number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
+                              int precision, const std::string& out_dir)
+{
+    BatchResult out;
+    auto fail = [&](int status, const std::string& what) { out.status = status; out.error = what; return out; };
+    if (aircraft_end <= aircraft_begin || drone_total <= 0) return fail(DCRP_ERR_INVALID, "empty aircraft or drone range");
+
+    // ---- inputs through the same loaders the per-pair path uses
+    Aircraft aircraft;
+    aircraft.Set_Parameters_and_Data(aircraft_csv, aircraft_cols);
+    if (!aircraft.ok()) return fail(DCRP_ERR_IO, aircraft.last_error());
+    const int n_tracks = aircraft_end - aircraft_begin;
+    std::vector<std::vector<double>> xs(n_tracks), ys(n_tracks), zs(n_tracks);
+    std::vector<dcrp_track> tracks(n_tracks);
+    for (int k = 0; k < n_tracks; ++k) {
+        aircraft.Vector_Allocation(aircraft_begin + k);
+        if (aircraft.Vector_length <= 0) return fail(DCRP_ERR_INVALID, "no flight " + std::to_string(aircraft_begin + k));
+        xs[k].assign(aircraft.longitude_vector, aircraft.longitude_vector + aircraft.Vector_length);
+        ys[k].assign(aircraft.latitude_vector, aircraft.latitude_vector + aircraft.Vector_length);
+        zs[k].assign(aircraft.altitude_vector, aircraft.altitude_vector + aircraft.Vector_length);
+        tracks[k].x = xs[k].data(); tracks[k].y = ys[k].data(); tracks[k].z = zs[k].data();
+        tracks[k].n_steps = aircraft.Vector_length;
+        tracks[k].takeoff_t = aircraft.takeoff_t;
+        const int rc = dcrp_target_box(ys[k][0], zs[k][0], tracks[k].box);
+        aircraft.Deallocation();
+        if (rc != DCRP_OK) return fail(rc, "flight " + std::to_string(aircraft_begin + k) + ": " + dcrp_last_error());
+    }
+    std::vector<dcrp_drone> drones(drone_total);
+    {
+        Drone probe;
+        double one = 0.0, row[3];
+        for (int j = 0; j < drone_total; ++j) {
+            probe.SetInitialParameters(drone_csv, 1, drone_cols, j, 0, 1, &one, &one, &one, aircraft_radius, drone_radius);
+            if (probe.LastStatus() != 0) return fail(probe.LastStatus(), probe.LastError());
+            probe.InitialRow(row);
+            drones[j] = dcrp_drone{row[0], row[1], row[2]};
+        }
+    }
+
+    // ---- one launch for everything
+    std::string err;
+    dcrp_engine* eng = shared_engine(&err);
+    if (!eng) return fail(DCRP_ERR_NO_DEVICE, err);
+    dcrp_model model;
+    dcrp_default_model(&model);
+    model.aircraft_radius = aircraft_radius;
+    model.drone_radius = drone_radius;
+    dcrp_run run{};
+    run.seed = seed; run.trial_begin = 0; run.trial_count = number_runs; run.precision = precision;
+    run.record_capacity = 1u << 20;
+    run.track_id_base = (uint32_t)aircraft_begin;       // same Philox ids as Drone::Simulation(i, j)
+    std::vector<uint64_t> counts((size_t)n_tracks * drone_total, 0);
+    std::vector<dcrp_record> records(run.record_capacity);
+    dcrp_result res{};
+    res.counts = counts.data();
+    res.records = records.data();
+    int rc = dcrp_simulate(eng, tracks.data(), n_tracks, drones.data(), drone_total, &model, &run, &res);
+    if (rc != DCRP_OK) return fail(rc, dcrp_last_error());
+    for (uint64_t c : counts) out.collisions += c;
+    out.trials = (uint64_t)n_tracks * drone_total * number_runs;
+    out.stats = res.stats;
+    if (res.overflow) return fail(DCRP_ERR_STATE, "more collisions than the record buffer holds; lower number_runs per call");
+
+    // ---- collision blocks, one file per aircraft (records arrive sorted by track, drone, trial)
+    int stride = 0;
+    std::vector<double> xyz;
+    if (res.n_records) {
+        rc = dcrp_trajectories(eng, nullptr, 0, nullptr, &stride);
+        if (rc != DCRP_OK) return fail(rc, dcrp_last_error());
+        xyz.assign((size_t)res.n_records * 3 * (size_t)stride, 0.0);
+        rc = dcrp_trajectories(eng, records.data(), res.n_records, xyz.data(), &stride);
+        if (rc != DCRP_OK) return fail(rc, dcrp_last_error());
+    }
+    uint32_t k = 0;
+    for (int a = 0; a < n_tracks; ++a) {
+        std::ofstream f(out_dir + "/Drone_coords_" + std::to_string(aircraft_begin + a) + ".csv",
+                        std::ofstream::out | std::ofstream::trunc);          // ClearOutput, Drone.cpp:59-64
+        for (; k < res.n_records && (int)records[k].track == a; ++k) {
+            const double* x = xyz.data() + (size_t)k * 3 * (size_t)stride;
+            if (f) write_block(f, x, x + stride, x + 2 * (size_t)stride, tracks[a].n_steps, (long)records[k].trial);
+        }
+    }
+    return out;
+}
+
+}  // namespace dcrp_host

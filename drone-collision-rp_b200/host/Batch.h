@@ -1,0 +1,31 @@
+// Batch.h -- whole-day driver on the batch ABI (extension; the reference loops one (aircraft, drone)
+// pair at a time, Monte_Carlo.cpp:28-34).  Every flight [aircraft_begin, aircraft_end) of the CSV and
+// every drone [0, drone_total) go to the GPU in ONE dcrp_simulate call; results are identical to the
+// per-pair loop (same Philox ids) and the collision files are written in the reference's format and
+// order (Drone.cpp:233-243: blocks by drone, then run).
+#ifndef DCRP_HOST_BATCH_H
+#define DCRP_HOST_BATCH_H
+
+#include <cstdint>
+#include <string>
+
+#include "dcrp.h"
+
+namespace dcrp_host {
+
+struct BatchResult {
+    uint64_t collisions = 0;
+    uint64_t trials = 0;
+    int status = 0;
+    std::string error;
+    dcrp_stats stats{};
+};
+
+BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols, int aircraft_begin,
+                              int aircraft_end, const std::string& drone_csv, int drone_cols, int drone_total,
+                              uint64_t number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
+                              int precision, const std::string& out_dir);
+
+}  // namespace dcrp_host
+
+#endif

@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 
 #include "Aircraft.h"
+#include "Batch.h"
 #include "Drone.h"
 #include "synth_day.h"
 
@@ -21,7 +22,7 @@ using namespace std;
 static void usage(const char* argv0)
 {
     cout << "usage: " << argv0 << " [--aircraft-csv F] [--drone-csv F] [--aircraft N] [--drones N]\n"
-            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS]\n"
+            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS] [--batch]\n"
             "defaults are the reference's constants (Monte_Carlo.cpp:11-18,28,33)\n";
 }
 
@@ -40,6 +41,7 @@ int main(int argc, char** argv)
     uint64_t seed = 20170630ull;
     int precision = DCRP_PRECISION_MIXED;
     int synthetic = 0;
+    bool batch = false;          // one GPU launch for all (aircraft, drone) pairs instead of one per pair
 
     for (int i = 1; i < argc; ++i) {
         const string a = argv[i];
@@ -54,6 +56,7 @@ int main(int argc, char** argv)
         else if (a == "--runs") number_runs = atoi(next("--runs"));
         else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
         else if (a == "--synthetic") synthetic = atoi(next("--synthetic"));
+        else if (a == "--batch") batch = true;
         else if (a == "--precision") {
             const string p = next("--precision");
             if (p == "fp64") precision = DCRP_PRECISION_FP64;
@@ -74,6 +77,16 @@ int main(int argc, char** argv)
         }
     }
     mkdir("Drone_Collisions", 0777);   // the reference needs it to pre-exist (Drone.cpp:62,236)
+
+    if (batch) {
+        const dcrp_host::BatchResult r = dcrp_host::monte_carlo_batch(
+            FilePath_aircraft, no_col_aircraft, 0, aircraft_total, FilePath_drone, no_col_drone, drone_total,
+            (uint64_t)number_runs, aircraft_radius, drone_radius, seed, precision, "Drone_Collisions");
+        if (r.status != 0) { cout << "ERROR - " << r.error << endl; return 1; }
+        cout << "Number of collisions: " << (double)r.collisions << endl;
+        dcrp_host::release_shared_engine();
+        return 0;
+    }
 
     double* total_collisions = new double[1];
     *total_collisions = 0;

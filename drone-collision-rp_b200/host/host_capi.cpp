@@ -5,6 +5,7 @@
 #include <string>
 
 #include "Aircraft.h"
+#include "Batch.h"
 #include "Drone.h"
 #include "synth_day.h"
 
@@ -95,6 +96,21 @@ extern "C" int dcrph_monte_carlo(const char* aircraft_csv, int aircraft_cols, in
         aircraft.Deallocation();                                              // :35
     }
     if (exact_total) *exact_total = drone.ExactCollisions();
+    return 0;
+}
+
+extern "C" int dcrph_monte_carlo_batch(const char* aircraft_csv, int aircraft_cols, int aircraft_begin,
+                                       int aircraft_end, const char* drone_csv, int drone_cols, int drone_total,
+                                       uint64_t number_runs, double aircraft_radius, double drone_radius,
+                                       uint64_t seed, int precision, const char* out_dir,
+                                       uint64_t* total_collisions)
+{
+    if (!aircraft_csv || !drone_csv || !total_collisions) { g_host_err = "NULL argument"; return -1; }
+    const dcrp_host::BatchResult r = dcrp_host::monte_carlo_batch(
+        aircraft_csv, aircraft_cols, aircraft_begin, aircraft_end, drone_csv, drone_cols, drone_total, number_runs,
+        aircraft_radius, drone_radius, seed, precision, (out_dir && *out_dir) ? out_dir : "Drone_Collisions");
+    if (r.status != 0) { g_host_err = r.error; return r.status; }
+    *total_collisions = r.collisions;
     return 0;
 }
 

@@ -44,6 +44,13 @@ int dcrph_monte_carlo(const char* aircraft_csv, int aircraft_cols, int aircraft_
                       double aircraft_radius, double drone_radius, uint64_t seed, int precision,
                       const char* out_dir, double* total_collisions, uint64_t* exact_total);
 
+/* The same workload in ONE dcrp_simulate call (all flights x all drones; extension).  Identical counts
+ * and files to dcrph_monte_carlo with the same seed. */
+int dcrph_monte_carlo_batch(const char* aircraft_csv, int aircraft_cols, int aircraft_begin, int aircraft_end,
+                            const char* drone_csv, int drone_cols, int drone_total, uint64_t number_runs,
+                            double aircraft_radius, double drone_radius, uint64_t seed, int precision,
+                            const char* out_dir, uint64_t* total_collisions);
+
 /* Drone::Output's row format (Drone.cpp:237-241) applied to one trajectory;
  * appends to `path`. */
 int dcrph_write_block(const char* path, const double* x, const double* y, const double* z, int n,

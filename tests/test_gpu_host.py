@@ -63,6 +63,27 @@ def test_monte_carlo_loop_matches_batch_and_oracle(engine, oracle, day, ring1, t
     assert want == batch.hits
 
 
+def test_batch_driver_equals_per_pair_loop(day, tmp_path):
+    """One launch for the whole day (Batch.cpp) == the reference-style per-pair loop: same count,
+    byte-identical collision files."""
+    tracks, csv = day
+    loop_dir, batch_dir = tmp_path / "loop", tmp_path / "batch"
+    loop_dir.mkdir(); batch_dir.mkdir()
+    total = C.c_double(0.0)
+    exact = C.c_uint64(0)
+    capi._hcheck(capi.host().dcrph_monte_carlo(csv.encode(), 22, 1, 4, pk.RING_1KM.encode(), 4, 99, 8000, 3.5, 0.19,
+                                               SEED, capi.MIXED, str(loop_dir).encode(), C.byref(total),
+                                               C.byref(exact)))
+    btotal = C.c_uint64(0)
+    capi._hcheck(capi.host().dcrph_monte_carlo_batch(csv.encode(), 22, 1, 4, pk.RING_1KM.encode(), 4, 99, 8000, 3.5,
+                                                     0.19, SEED, capi.MIXED, str(batch_dir).encode(),
+                                                     C.byref(btotal)))
+    assert btotal.value == exact.value > 0
+    for a in (1, 2, 3):
+        name = "Drone_coords_%d.csv" % a
+        assert open(loop_dir / name).read() == open(batch_dir / name).read()
+
+
 def test_monte_carlo_binary_as_the_reference_is_run(engine, tracks, ring1, tmp_path):
     """./Monte_Carlo in a directory laid out like the reference checkout: default
     constants (first flight, 1 km ring, 99 drones, 10 000 runs), stdout line, file."""
@@ -75,12 +96,15 @@ def test_monte_carlo_binary_as_the_reference_is_run(engine, tracks, ring1, tmp_p
     assert int(m.group(1)) == batch.hits
     blocks = _parse_blocks(open(tmp_path / "Drone_Collisions" / "Drone_coords_0.csv").read())
     assert len(blocks) == batch.hits
-    # repeated Simulation calls on one pair continue the trial stream instead of replaying it
+    # other constants through flags (the reference needs a recompile for these), fp64 kernel
     r2 = subprocess.run([pk.MONTE_CARLO, "--synthetic", "6", "--precision", "fp64", "--runs", "2500", "--drones", "60"],
                         cwd=tmp_path, capture_output=True, text=True, timeout=300)
     assert r2.returncode == 0
     part = engine.simulate(tracks[:1], ring1[:60], seed=SEED, trial_count=2500, precision=capi.FP64)
     assert int(re.search(r"Number of collisions: (\d+)", r2.stdout).group(1)) == part.hits
+    r3 = subprocess.run([pk.MONTE_CARLO, "--synthetic", "6", "--batch"], cwd=tmp_path, capture_output=True, text=True,
+                        timeout=300)
+    assert r3.returncode == 0 and int(re.search(r"Number of collisions: (\d+)", r3.stdout).group(1)) == batch.hits
 
 
 def test_out_of_band_runway_is_an_error_not_stale_values(engine, tracks, ring1, tmp_path):
