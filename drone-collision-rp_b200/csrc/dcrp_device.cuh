@@ -7,6 +7,8 @@
 //                               origin and negated: (-ax, -ay, -az, i)  (i as float); one
 //                               broadcast LDS.128 per index feeds the packed f32x2 ops through
 //                               their scalar-broadcast operand form
+//   trkxy [sum even(n_steps)]   the horizontal part alone, 8 B per sample: what level 1 streams
+//                               (one broadcast LDS.128 feeds TWO indices)
 //   drones[n_drones]            x0, y0, sin(h0)*v, cos(h0)*v   (fp64; trig by the host's libm,
 //                               the same one the reference links, Drone.cpp:121-122)
 //   p1x, p1y [n_drones*t_max]   stage-1 path of every drone, sequentially accumulated fp64
@@ -26,8 +28,8 @@ namespace dcrp {
 struct TrackDev {
     int32_t  n_steps;
     int32_t  takeoff_t;
-    uint32_t off;        // first sample of this track in ax/ay/az (and trk32 / 2)
-    uint32_t pad;
+    uint32_t off;        // first sample of this track in ax/ay/az and trk32
+    uint32_t off_xy;     // first sample of this track in trkxy (even: every track starts 16-B aligned)
     double   box[6];
     // fast screen set-up: target = box_min + w * (extent * 2^-32), w = Philox word
     double   wx32, wy32; // (box[1]-box[0]) * 2^-32, (box[3]-box[2]) * 2^-32
@@ -41,6 +43,7 @@ struct ScenarioDev {
     const double*   ay;
     const double*   az;
     const float4*   trk32;
+    const float2*   trkxy;           // level-1 copy: (-ax', -ay') only, 8 B per sample, tracks padded to even
     const double4*  drones;
     double*         p1x;
     double*         p1y;

@@ -247,7 +247,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 
     // ---- validate, offsets, extents
     e->h_tracks.assign((size_t)n_tracks, TrackDev{});
-    uint64_t total = 0;
+    uint64_t total = 0, total_xy = 0;
     int t_max = 0, vl_max = 0;
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     auto grow = [&](double x, double y, double z) {
@@ -268,7 +268,8 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
             if (!(t.box[2 * k] <= t.box[2 * k + 1]))
                 return fail(DCRP_ERR_INVALID, "track %d: target box is inverted or NaN", a);
         TrackDev& d = e->h_tracks[(size_t)a];
-        d.n_steps = t.n_steps; d.takeoff_t = t.takeoff_t; d.off = (uint32_t)total; d.pad = 0;
+        d.n_steps = t.n_steps; d.takeoff_t = t.takeoff_t; d.off = (uint32_t)total; d.off_xy = (uint32_t)total_xy;
+        total_xy += (uint64_t)((t.n_steps + 1) & ~1);
         std::memcpy(d.box, t.box, sizeof d.box);
         d.wx32 = (t.box[1] - t.box[0]) * (1.0 / 4294967296.0);
         d.wy32 = (t.box[3] - t.box[2]) * (1.0 / 4294967296.0);
@@ -337,7 +338,8 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     const size_t o_ay = align256(o_ax + sizeof(double) * total);
     const size_t o_az = align256(o_ay + sizeof(double) * total);
     const size_t o_t32 = align256(o_az + sizeof(double) * total);
-    const size_t o_dr = align256(o_t32 + sizeof(float4) * total);
+    const size_t o_txy = align256(o_t32 + sizeof(float4) * total);
+    const size_t o_dr = align256(o_txy + sizeof(float2) * total_xy);
     const size_t scn_bytes = align256(o_dr + sizeof(double4) * (size_t)n_drones);
     cudaStream_t st = e->stream;
     CU(cudaStreamSynchronize(st));          // the previous upload's copy has left the pinned mirror
@@ -349,6 +351,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     double* hy = reinterpret_cast<double*>(hb + o_ay);
     double* hz = reinterpret_cast<double*>(hb + o_az);
     float4* h32 = reinterpret_cast<float4*>(hb + o_t32);
+    float2* hxy = reinterpret_cast<float2*>(hb + o_txy);
     double4* hd = reinterpret_cast<double4*>(hb + o_dr);
     for (int a = 0; a < n_tracks; ++a) {
         const dcrp_track& t = tracks[a];
@@ -358,7 +361,9 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
             const float fx = -(float)(t.x[i] - s.ox), fy = -(float)(t.y[i] - s.oy),
                         fz = -(float)(t.z[i] - s.oz);
             h32[off + i] = make_float4(fx, fy, fz, (float)i);
+            hxy[e->h_tracks[(size_t)a].off_xy + i] = make_float2(fx, fy);
         }
+        if (t.n_steps & 1) hxy[e->h_tracks[(size_t)a].off_xy + t.n_steps] = make_float2(1e15f, 1e15f);   // pad
     }
     for (int j = 0; j < n_drones; ++j) {
         // Drone.cpp:121-122: sin(heading)*max_straight_speed, formed with the host libm
@@ -383,6 +388,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.ay = reinterpret_cast<const double*>(db + o_ay);
     s.az = reinterpret_cast<const double*>(db + o_az);
     s.trk32 = reinterpret_cast<const float4*>(db + o_t32);
+    s.trkxy = reinterpret_cast<const float2*>(db + o_txy);
     s.drones = reinterpret_cast<const double4*>(db + o_dr);
     s.p1x = e->d_p1x.as<double>(); s.p1y = e->d_p1y.as<double>();
     s.s1_first_hit = e->d_s1fh.as<int32_t>();
@@ -435,7 +441,7 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     ScreenCfg& c = screen_cfg();
     const int v = r.replay ? 1 : 0;
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
-    const size_t smem = (size_t)2 * tile_steps * 16 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
+    const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2));
     if (c.configured_smem[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(c.kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -764,7 +770,9 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     ap.l2 = e->d_ap_l2.as<uint2>();
     ap.l2_count = ap.hist + (size_t)s.n_drones * run->ref_takeoff_t;      // last word of the hist buffer
     ap.l2_cap = L2_CAP;
-    ap.blocks_per_drone = (uint32_t)((run->ray_count + AP_RAYS - 1) / AP_RAYS);
+    static const int ap_np = (std::getenv("DCRP_AP_NP") && std::atoi(std::getenv("DCRP_AP_NP")) == 1) ? 1 : 2;
+    const uint32_t ap_rays = (uint32_t)(2 * ap_np * AP_BLOCK);         // rays per CTA
+    ap.blocks_per_drone = (uint32_t)((run->ray_count + ap_rays - 1) / ap_rays);
 
     CU(cudaEventRecord(e->ev_begin, st));
     k_run_init<<<(unsigned)((e->out_bytes / 4 + 255) / 256), 256, 0, st>>>(
@@ -780,11 +788,12 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         e->launches += 3; e->launches_this_run += 3;
         CU(cudaGetLastError());
 
-        const size_t smem = (size_t)AP_STAGES * AP_TILE * 16 + 2 * AP_STAGES * sizeof(uint64_t);
+        const size_t smem = (size_t)AP_STAGES * AP_TILE * 8 + 2 * AP_STAGES * sizeof(uint64_t);
+        const void* kern = ap_np == 1 ? (const void*)k_ap_scan_tracks<1> : (const void*)k_ap_scan_tracks<2>;
         static int occ = 0;
         if (occ == 0) {
-            CU(cudaFuncSetAttribute(k_ap_scan_tracks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ap_scan_tracks, AP_BLOCK, smem));
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AP_BLOCK, smem));
             if (occ < 1) occ = 1;
         }
         const uint64_t n_rblocks = (uint64_t)s.n_drones * ap.blocks_per_drone;
@@ -797,7 +806,10 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         const uint64_t n_items = n_rblocks * ap.n_tchunks;
         if (n_items >= (1ull << 32)) return fail(DCRP_ERR_INVALID, "too many all-pairs work items");
         const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, resident);
-        k_ap_scan_tracks<<<grid, AP_BLOCK, smem, st>>>(s, r, ap, (uint32_t)n_items);
+        uint32_t n_items32 = (uint32_t)n_items;
+        ScenarioDev sd = s;
+        void* args[] = {&sd, &r, &ap, &n_items32};
+        CU(cudaLaunchKernel(kern, dim3(grid), dim3(AP_BLOCK), args, smem, st));
         ++e->launches; ++e->launches_this_run;
         CU(cudaGetLastError());
     }
@@ -878,10 +890,16 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
 extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms_out)
 {
     if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
-    if (which < 0 || which > 12) return fail(DCRP_ERR_INVALID, "which must be 0..12");
+    if (which < 0 || which > 15) return fail(DCRP_ERR_INVALID, "which must be 0..15");
     CU(cudaSetDevice(e->device));
-    const int threads = 256, blocks = e->prop.multiProcessorCount * 8;
-    const int iters = 2048;
+    const int threads = 256;
+    int blocks = e->prop.multiProcessorCount * 8;
+    int iters = 2048;
+    if (which >= 13) {                // the real kernels' residency: 3-4 CTAs of 256 threads per SM
+        static const int per_sm = std::getenv("DCRP_PEAK_CTAS") ? std::atoi(std::getenv("DCRP_PEAK_CTAS")) : 4;
+        blocks = e->prop.multiProcessorCount * per_sm;
+        iters = 64;
+    }
     CU(e->d_scratch.need(sizeof(double) * (size_t)threads * blocks));
     float best = 1e30f;
     for (int rep = 0; rep < 5; ++rep) {
@@ -899,7 +917,10 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
             case 9: k_peak_variant<9><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 10: k_peak_variant2<10><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 11: k_peak_variant2<11><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            default: k_peak_variant2<12><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 12: k_peak_variant2<12><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 13: k_peak_scan2d<13><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 14: k_peak_scan2d<14><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            default: k_peak_scan2d<15><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
         }
         ++e->launches;
         CU(cudaGetLastError());
@@ -918,6 +939,7 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
     else if (which == 8) flops = lanes * iters * 8.0 * 16.0;                            // FMNMX3 count, not flops
     else if (which == 10) flops = lanes * iters * 8.0 * 4.0 / 10.0;                     // Philox4x32-10 calls
     else if (which == 12) flops = lanes * iters * 8.0 * 2.0 * 2.0 * 2.0 * 11.0;         // 2 steps x 2 pairs x 2 tests
+    else if (which >= 13) flops = lanes * iters * 512.0 * 2.0 * 11.0;                   // 512 steps x 2 tests
     else                 flops = lanes * iters * 8.0 * 4.0 * 2.0 * 11.0;   // 2 tests per packed pair, 11 flop each
     *tflops = flops / ((double)best * 1e-3) * 1e-12;
     if (ms_out) *ms_out = best;

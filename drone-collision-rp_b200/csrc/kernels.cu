@@ -156,6 +156,52 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
     } while (!ok);
 }
 
+// Level-1 scan of one tile for NP packed pairs.  `txy` points at the tile's first sample (an EVEN track
+// index t0), [lo, hi) are absolute indices inside the tile.  Incremental form: D = P + (-A_i), P += S,
+// so every packed op reads at most two distinct register pairs and FFMA2/FADD2/FMUL2 issue back to back
+// every 2 cycles (the fused P = i*S + B form reads three and measured 12 % slower).  One broadcast
+// LDS.128 feeds two indices; the {v, v} pairs cost nothing (ptxas folds them into the packed ops'
+// scalar-broadcast operand form).
+template <int NP>
+__device__ __forceinline__ void scan_tile_xy(const float2* __restrict__ txy, int t0, int lo, int hi,
+                                             f2_t (&PX)[NP], f2_t (&PY)[NP], const f2_t (&SX)[NP],
+                                             const f2_t (&SY)[NP], float (&mn)[2 * NP])
+{
+#define DCRP_STEP(vx, vy)                                                     \
+    {                                                                         \
+        const f2_t cx_ = pk2((vx), (vx)), cy_ = pk2((vy), (vy));              \
+        _Pragma("unroll") for (int p_ = 0; p_ < NP; ++p_) {                   \
+            const f2_t dx_ = fadd2(PX[p_], cx_);                              \
+            const f2_t dy_ = fadd2(PY[p_], cy_);                              \
+            const float2 d2_ = up2(ffma2(dy_, dy_, fmul2(dx_, dx_)));         \
+            mn[2 * p_] = fminf(mn[2 * p_], d2_.x);                            \
+            mn[2 * p_ + 1] = fminf(mn[2 * p_ + 1], d2_.y);                    \
+            PX[p_] = fadd2(PX[p_], SX[p_]);                                   \
+            PY[p_] = fadd2(PY[p_], SY[p_]);                                   \
+        }                                                                     \
+    }
+    int i = lo;
+    if (i & 1) {                                   // odd start: one single step to reach an even index
+        const float2 c = txy[i - t0];
+        DCRP_STEP(c.x, c.y)
+        ++i;
+    }
+    const int npair = (hi - i) >> 1;
+    const float4* __restrict__ q4 = reinterpret_cast<const float4*>(txy + (i - t0));
+#pragma unroll 2
+    for (int k = 0; k < npair; ++k) {
+        const float4 c = q4[k];
+        DCRP_STEP(c.x, c.y)
+        DCRP_STEP(c.z, c.w)
+    }
+    i += 2 * npair;
+    if (i < hi) {
+        const float2 c = txy[i - t0];
+        DCRP_STEP(c.x, c.y)
+    }
+#undef DCRP_STEP
+}
+
 // =========================================================================
 // stage 1: once per scenario
 // =========================================================================
@@ -438,12 +484,17 @@ struct Fast32 {          // horizontal ray of one trial for level 1: position(i)
 };
 
 // kk / pl point at this pair's kink tables (shared memory when takeoff_t <= SCREEN_TAB, else global).
-__device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const TrackDev* __restrict__ tk,
+struct TrackScale {      // per-track constants of the fast set-up, fetched once per item
+    double wx32, wy32;
+    float  wz32, z0rel;
+};
+
+__device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const TrackScale& ts,
                                                const double2* __restrict__ kk_tab,
                                                const float2* __restrict__ pl_tab, int s1_first, const uint4 q)
 {
-    const double wx32 = __ldg(&tk->wx32), wy32 = __ldg(&tk->wy32);
-    const float wz32 = __ldg(&tk->wz32), z0rel = __ldg(&tk->z0rel);
+    const double wx32 = ts.wx32, wy32 = ts.wy32;
+    const float wz32 = ts.wz32, z0rel = ts.z0rel;
     Fast32 o;
     o.t1st = (int32_t)(q.w >> 12);
     const int last = o.t1st - 1;
@@ -480,8 +531,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     static_assert(CH <= 4096, "local trial index is packed in 12 bits");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4*   tiles = reinterpret_cast<float4*>(smem_raw);
-    uint4*    stage = reinterpret_cast<uint4*>(smem_raw + (size_t)2 * tile_steps * 16);
+    float2*   tiles = reinterpret_cast<float2*>(smem_raw);                          // 2 x tile_steps (x, y)
+    uint4*    stage = reinterpret_cast<uint4*>(smem_raw + (size_t)2 * tile_steps * 8);
     uint32_t* hist  = reinterpret_cast<uint32_t*>(stage + CH);
     uint64_t* bars  = reinterpret_cast<uint64_t*>(hist + 80);
     double2*  tabk  = reinterpret_cast<double2*>(bars + 2);            // this pair's kink tables
@@ -516,7 +567,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         const uint64_t chunk_first64 = r.slice_first + (uint64_t)c * CH;
         const uint32_t n_valid = (uint32_t)min((uint64_t)CH, r.slice_count - (uint64_t)c * CH);
         const int s1_first = __ldg(&s.s1_first_hit[pair]);
-        const float4* __restrict__ gtrk = s.trk32 + (size_t)__ldg(&tk->off);
+        const float2* __restrict__ gtrk = s.trkxy + (size_t)__ldg(&tk->off_xy);
 
         if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {        // rare: keep the 32-bit partial sums exact
             atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
@@ -535,14 +586,15 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             }
             tab_pair = pair;
         }
-        const double2* __restrict__ kk_tab = tab_smem ? tabk : s.kink + (size_t)pair * s.t_max;
-        const float2* __restrict__ pl_tab = tab_smem ? tabp : s.p1f + (size_t)j * s.t_max;
+        TrackScale ts;
+        ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32);
+        ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
 
         const bool single = (n_tiles == 1);
         const bool need_load = !(single && loaded_track == a);
         if (single && need_load && tid == 0) {
             fence_proxy_async();
-            const uint32_t b0 = (uint32_t)VL * 16u;
+            const uint32_t b0 = (uint32_t)((VL + 1) & ~1) * 8u;       // whole 16-B units (tracks are padded)
             mbar_arrive_expect_tx(&bars[0], b0);
             tma_bulk_g2s(tiles, gtrk, b0, &bars[0]);
         }
@@ -628,7 +680,11 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                         bx = __uint_as_float(q.x >> 9); by = __uint_as_float(q.y >> 9);
                         sx = 1.f; sy = 2.f; t1 = (int32_t)(q.w >> 12);
                     } else {
-                        const Fast32 u = setup_fast32(s, tk, kk_tab, pl_tab, s1_first, q);
+                        // two calls so that each sees a typed (shared / global) table pointer, not a generic one
+                        const Fast32 u = tab_smem
+                            ? setup_fast32(s, ts, tabk, tabp, s1_first, q)
+                            : setup_fast32(s, ts, s.kink + (size_t)pair * s.t_max, s.p1f + (size_t)j * s.t_max,
+                                           s1_first, q);
                         bx = u.bx; by = u.by; sx = u.sx; sy = u.sy;
                         fmask |= u.force ? (1u << m) : 0u; t1 = u.t1st;
                     }
@@ -638,11 +694,11 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 bxs[m] = bx; bys[m] = by; sxs[m] = sx; sys[m] = sy;
             }
             const f2_t BX = pk2(bxs[0], bxs[1]), BY = pk2(bys[0], bys[1]);
-            const f2_t SX = pk2(sxs[0], sxs[1]), SY = pk2(sys[0], sys[1]);
+            const f2_t SX[1] = {pk2(sxs[0], sxs[1])}, SY[1] = {pk2(sys[0], sys[1])};
             const int imin = __reduce_min_sync(0xffffffffu, tmin);
             if (imin < VL) acc_is += (uint32_t)(VL - imin) * 2u;
 
-            float mn0 = 3.0e38f, mn1 = 3.0e38f;     // running min of the horizontal d2 of trial 0 / 1
+            float mn[2] = {3.0e38f, 3.0e38f};       // running min of the horizontal d2 of trial 0 / 1
             for (int tl = 0; tl < n_tiles; ++tl) {
                 const int buf = single ? 0 : (tl & 1);
                 if (!single) {
@@ -651,7 +707,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     if (tid == 0) {
                         fence_proxy_async();
                         const int tn = tl * tile_steps;
-                        const uint32_t bn = (uint32_t)min(VL - tn, tile_steps) * 16u;
+                        const uint32_t bn = (uint32_t)((min(VL - tn, tile_steps) + 1) & ~1) * 8u;
                         mbar_arrive_expect_tx(&bars[buf], bn);
                         tma_bulk_g2s(tiles + (size_t)buf * tile_steps, gtrk + (size_t)tn, bn, &bars[buf]);
                     }
@@ -660,40 +716,23 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 }
                 const int t0 = tl * tile_steps;
                 const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(VL, t0 + tile_steps);   // dbg 1: no scan
-                const float4* __restrict__ tp = tiles + (size_t)buf * tile_steps - (size_t)t0;
                 // LEVEL 1, horizontal screen: d2xy(i) = |Pxy(i) - Axy(i)|^2 <= d2(i), so a trial whose
                 // horizontal separation never drops below R + margin cannot collide at any index, whatever
-                // the altitudes.  6 packed ops per pair-step instead of 9.
-                // Incremental form: P(lo) = B + lo*S once per tile, then per index D = P + (-A_i), P += S:
-                // every packed op reads at most two distinct register pairs, which is what lets
-                // FFMA2/FADD2/FMUL2 issue back to back every 2 cycles (the fused P = i*S + B form reads
-                // three and measured 12% slower: profiles/r01_micro_pipes.json).  The accumulated rounding
-                // (<= tile_steps/2 ulp per coordinate) is inside the screen margin.
-                // One broadcast LDS per index: (-ax, -ay, -az, i); the {v, v} pairs cost nothing (ptxas
-                // folds them into the packed ops' scalar-broadcast operand form).
+                // the altitudes.  6 packed ops per pair-step instead of 9.  P(lo) = B + lo*S is re-based
+                // exactly at every tile start; the rounding accumulated inside a tile (<= tile_steps/2 ulp
+                // per coordinate) is inside the screen margin.
                 if (lo < hi) {
                     const float lof = (float)lo;
                     const f2_t lo2 = pk2(lof, lof);
-                    f2_t PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);
-                    const float4* __restrict__ tq = tp + lo;      // plain base + immediate offsets in the loop
-                    const int nq = hi - lo;
-#pragma unroll 4
-                    for (int k = 0; k < nq; ++k) {
-                        const float2 p = *reinterpret_cast<const float2*>(&tq[k]);
-                        const f2_t dx = fadd2(PX, pk2(p.x, p.x));
-                        const f2_t dy = fadd2(PY, pk2(p.y, p.y));
-                        const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
-                        mn0 = fminf(mn0, d2.x);
-                        mn1 = fminf(mn1, d2.y);
-                        PX = fadd2(PX, SX); PY = fadd2(PY, SY);
-                    }
+                    f2_t PX[1] = {ffma2(lo2, SX[0], BX)}, PY[1] = {ffma2(lo2, SY[0], BY)};
+                    scan_tile_xy<1>(tiles + (size_t)buf * tile_steps, t0, lo, hi, PX, PY, SX, SY, mn);
                 }
             }
 
             // ---------------- rare path (~1e-3 of trials): LEVEL 2, the full 3-D fp32 distance of the
             // flagged trial alone; what survives goes to the fp64 confirm (LEVEL 3)
-            if (mn0 < thr) fmask |= 1u;
-            if (mn1 < thr) fmask |= 2u;
+            if (mn[0] < thr) fmask |= 1u;
+            if (mn[1] < thr) fmask |= 2u;
             if (fmask) {
 #pragma unroll 1
                 for (int m = 0; m < 2; ++m) {
@@ -740,7 +779,6 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 // =========================================================================
 constexpr uint32_t AP_TRACK_ID = 0xFFFFFFFFu;   // Philox track id of all-pairs rays (no MC trial uses it)
 constexpr int AP_BLOCK = 256;
-constexpr int AP_RAYS = 2 * AP_BLOCK;           // rays per CTA: one packed pair per lane
 constexpr int AP_TILE = 512;                    // track samples per shared-memory tile (8 KB)
 constexpr int AP_STAGES = 3;
 
@@ -815,16 +853,17 @@ __global__ void __launch_bounds__(256) k_ap_scatter(const ScenarioDev s, const A
     ap.rayB[rec + m] = sx; ap.rayB[rec + 2 + m] = sy;
 }
 
-// The scan: a CTA keeps AP_RAYS sorted rays of one drone in registers (one packed pair per lane) and
+// The scan: a CTA keeps NP*512 sorted rays of one drone in registers (NP packed pairs per lane) and
 // streams the samples of a chunk of tracks through a 3-stage TMA/mbarrier ring.  Per track the
-// running horizontal minimum is reset, and a (ray, track) pair that comes within R + margin
+// running horizontal minima are reset, and a (ray, track) pair that comes within R + margin
 // horizontally is appended (warp-aggregated) to the level-2 list.
-__global__ void __launch_bounds__(AP_BLOCK, 3)
+template <int NP>
+__global__ void __launch_bounds__(AP_BLOCK, (NP == 1 ? 3 : 2))
 k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint32_t n_items)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4*   tiles = reinterpret_cast<float4*>(smem_raw);                        // AP_STAGES x AP_TILE
-    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + (size_t)AP_STAGES * AP_TILE * 16);
+    float2*   tiles = reinterpret_cast<float2*>(smem_raw);                        // AP_STAGES x AP_TILE (x, y)
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem_raw + (size_t)AP_STAGES * AP_TILE * 8);
     uint64_t* empty = full + AP_STAGES;
     constexpr int NW = AP_BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -843,26 +882,34 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
         const int a_begin = (int)(tc * ap.tracks_per_chunk);
         const int a_end = min(s.n_tracks, a_begin + (int)ap.tracks_per_chunk);
 
-        // ---- this lane's packed pair of rays: two 16-byte loads deliver aligned f32x2 pairs
-        const uint32_t g = blk * (AP_RAYS / 64) + (uint32_t)warp;          // 64-ray group of this warp
-        f2_t BX = pk2(1e15f, 1e15f), BY = BX, SX = pk2(0.f, 0.f), SY = SX;
-        int t1[2] = {INT_MAX, INT_MAX};
-        uint32_t rid[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        bool degen[2] = {false, false};
+        // ---- this lane's NP packed pairs of rays: 16-byte loads deliver aligned f32x2 pairs
+        f2_t BX[NP], BY[NP], SX[NP], SY[NP];
+        int t1[2 * NP];
+        uint32_t rid[2 * NP];
+        uint32_t degen = 0;
         int tmin = INT_MAX;
-        if (g < ap.groups) {
-            const size_t rec = ((size_t)j * ap.groups + g) * 32 + lane;
-            const ulonglong2 qa = __ldg(reinterpret_cast<const ulonglong2*>(ap.rayA) + rec);
-            const ulonglong2 qb = __ldg(reinterpret_cast<const ulonglong2*>(ap.rayB) + rec);
-            BX = qa.x; BY = qa.y; SX = qb.x; SY = qb.y;
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const uint32_t slot = g * 64 + (uint32_t)(m * 32 + lane);
-                if (slot < ap.ray_count) {
-                    const size_t o = (size_t)j * ap.ray_count + slot;
-                    const uint2 mt = __ldg(&ap.meta[o]);
-                    t1[m] = (int)(mt.x & 0x7fffffffu); degen[m] = (mt.x >> 31) != 0u; rid[m] = (uint32_t)o;
-                    tmin = min(tmin, t1[m]);
+        for (int p = 0; p < NP; ++p) {
+            const uint32_t g = (blk * NW + (uint32_t)warp) * NP + p;      // 64-ray group
+            BX[p] = pk2(1e15f, 1e15f); BY[p] = BX[p]; SX[p] = pk2(0.f, 0.f); SY[p] = SX[p];
+            t1[2 * p] = t1[2 * p + 1] = INT_MAX;
+            rid[2 * p] = rid[2 * p + 1] = 0xFFFFFFFFu;
+            if (g < ap.groups) {
+                const size_t rec = ((size_t)j * ap.groups + g) * 32 + lane;
+                const ulonglong2 qa = __ldg(reinterpret_cast<const ulonglong2*>(ap.rayA) + rec);
+                const ulonglong2 qb = __ldg(reinterpret_cast<const ulonglong2*>(ap.rayB) + rec);
+                BX[p] = qa.x; BY[p] = qa.y; SX[p] = qb.x; SY[p] = qb.y;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const uint32_t slot = g * 64 + (uint32_t)(m * 32 + lane);
+                    if (slot < ap.ray_count) {
+                        const size_t o = (size_t)j * ap.ray_count + slot;
+                        const uint2 mt = __ldg(&ap.meta[o]);
+                        t1[2 * p + m] = (int)(mt.x & 0x7fffffffu);
+                        degen |= (mt.x >> 31) << (2 * p + m);
+                        rid[2 * p + m] = (uint32_t)o;
+                        tmin = min(tmin, t1[2 * p + m]);
+                    }
                 }
             }
         }
@@ -875,13 +922,13 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
         auto produce = [&]() {
             if (pa >= a_end) return;
             const int VLp = __ldg(&s.tracks[pa].n_steps);
-            const uint32_t off = __ldg(&s.tracks[pa].off);
+            const uint32_t off = __ldg(&s.tracks[pa].off_xy);
             const int b = (int)(PG % AP_STAGES);
             if (PG >= (uint32_t)AP_STAGES) mbar_wait(&empty[b], ((PG / AP_STAGES) - 1u) & 1u);
             fence_proxy_async();
-            const uint32_t bytes = (uint32_t)min(AP_TILE, VLp - pt * AP_TILE) * 16u;
+            const uint32_t bytes = (uint32_t)((min(AP_TILE, VLp - pt * AP_TILE) + 1) & ~1) * 8u;
             mbar_arrive_expect_tx(&full[b], bytes);
-            tma_bulk_g2s(tiles + (size_t)b * AP_TILE, s.trk32 + off + (size_t)pt * AP_TILE, bytes, &full[b]);
+            tma_bulk_g2s(tiles + (size_t)b * AP_TILE, s.trkxy + off + (size_t)pt * AP_TILE, bytes, &full[b]);
             ++PG;
             if ((pt + 1) * AP_TILE >= VLp) { ++pa; pt = 0; } else { ++pt; }
         };
@@ -890,7 +937,9 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
             for (int k = 0; k < AP_STAGES - 1; ++k) produce();
         }
 
-        float mn0 = 3.0e38f, mn1 = 3.0e38f;
+        float mn[2 * NP];
+#pragma unroll
+        for (int q = 0; q < 2 * NP; ++q) mn[q] = 3.0e38f;
         for (int a = a_begin; a < a_end; ++a) {
             const int VL = __ldg(&s.tracks[a].n_steps);
             const int n_tiles = (VL + AP_TILE - 1) / AP_TILE;
@@ -902,23 +951,15 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
                 const int t0 = tl * AP_TILE;
                 const int lo = max(imin, t0), hi = min(VL, t0 + AP_TILE);
                 if (lo < hi) {
-                    const float4* __restrict__ tp = tiles + (size_t)b * AP_TILE - (size_t)t0;
                     const float lof = (float)lo;
                     const f2_t lo2 = pk2(lof, lof);
-                    f2_t PX = ffma2(lo2, SX, BX), PY = ffma2(lo2, SY, BY);        // exact re-base per tile
-                    const float4* __restrict__ tq = tp + lo;      // plain base + immediate offsets in the loop
-                    const int nq = hi - lo;
-#pragma unroll 4
-                    for (int k = 0; k < nq; ++k) {
-                        const float2 p = *reinterpret_cast<const float2*>(&tq[k]);
-                        const f2_t dx = fadd2(PX, pk2(p.x, p.x));
-                        const f2_t dy = fadd2(PY, pk2(p.y, p.y));
-                        const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
-                        mn0 = fminf(mn0, d2.x);
-                        mn1 = fminf(mn1, d2.y);
-                        PX = fadd2(PX, SX); PY = fadd2(PY, SY);
+                    f2_t PX[NP], PY[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {                 // exact re-base per tile
+                        PX[p] = ffma2(lo2, SX[p], BX[p]); PY[p] = ffma2(lo2, SY[p], BY[p]);
                     }
-                    is += (unsigned long long)(hi - lo) * 2ull;
+                    scan_tile_xy<NP>(tiles + (size_t)b * AP_TILE, t0, lo, hi, PX, PY, SX, SY, mn);
+                    is += (unsigned long long)(hi - lo) * (2ull * NP);
                 }
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[b])) : "memory");
@@ -926,17 +967,17 @@ k_ap_scan_tracks(const ScenarioDev s, const RunDev r, const AllPairsDev ap, uint
             }
             // ---- end of track a: bookkeeping + rare level-2 append, then reset the minima
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                if (t1[m] == INT_MAX) continue;
-                ev += (unsigned long long)max(0, VL - t1[m]);
-                const float mn = m ? mn1 : mn0;
-                if (mn < s.thr2_screen || degen[m] || s1f <= t1[m] - 1) {
-                    ++nl2;
-                    const uint32_t slot = warp_claim_slot(ap.l2_count);
-                    if (slot < ap.l2_cap) ap.l2[slot] = make_uint2((uint32_t)a, rid[m]);
+            for (int q = 0; q < 2 * NP; ++q) {
+                if (t1[q] != INT_MAX) {
+                    ev += (unsigned long long)max(0, VL - t1[q]);
+                    if (mn[q] < s.thr2_screen || ((degen >> q) & 1u) || s1f <= t1[q] - 1) {
+                        ++nl2;
+                        const uint32_t slot = warp_claim_slot(ap.l2_count);
+                        if (slot < ap.l2_cap) ap.l2[slot] = make_uint2((uint32_t)a, rid[q]);
+                    }
                 }
+                mn[q] = 3.0e38f;
             }
-            mn0 = 3.0e38f; mn1 = 3.0e38f;
         }
     }
     ev = warp_sum_u64(ev); is = warp_sum_u64(is); nl2 = warp_sum_u64(nl2);
@@ -1249,6 +1290,44 @@ __global__ void __launch_bounds__(256) k_peak_variant2(float* out, int iters, fl
 #pragma unroll
     for (int k = 0; k < 4; ++k) r += B[k].x + B[k].y + S[k].x + S[k].y + __uint_as_float((c0[k] ^ c1[k] ^ c2[k] ^ c3[k]) & 0x3fffffffu);
     out[blockIdx.x * blockDim.x + threadIdx.x] = r + fi.x;
+}
+
+// Scan-loop variants at the real kernel's shape (1 packed pair per thread, 2-D incremental):
+//   V=13 samples from shared memory, duplicated layout (x,x,y,y): LDS.128, plain pair operands
+//   V=14 samples from shared memory, 16 B layout: LDS.64 + scalar-broadcast operand form (production)
+//   V=15 no shared memory: loop-invariant operand (pure pipe rate of the 6-op mix)
+template <int V>
+__global__ void __launch_bounds__(256) k_peak_scan2d(float* out, int iters, float s0, float a0)
+{
+    __shared__ float4 tile[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) tile[i] = make_float4(a0 + i, a0 + i, a0 - i, a0 - i);
+    __syncthreads();
+    f2_t PX = pk2(threadIdx.x * 0.5f, threadIdx.x * 0.25f), PY = pk2(threadIdx.x * 1.5f, -1.f * threadIdx.x);
+    const f2_t SX = pk2(s0, s0 + 1.f), SY = pk2(s0 - 1.f, s0 + 2.f);
+    const f2_t cinv = pk2(a0, a0);
+    float mn0 = 3.0e38f, mn1 = 3.0e38f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 4
+        for (int k = 0; k < 512; ++k) {
+            f2_t cx, cy;
+            if (V == 13) {
+                const float4 c = tile[k];
+                cx = pk2(c.x, c.y); cy = pk2(c.z, c.w);
+            } else if (V == 14) {
+                const float2 c = *reinterpret_cast<const float2*>(&tile[k]);
+                cx = pk2(c.x, c.x); cy = pk2(c.y, c.y);
+            } else {
+                cx = cinv; cy = cinv;
+            }
+            const f2_t dx = fadd2(PX, cx);
+            const f2_t dy = fadd2(PY, cy);
+            const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
+            mn0 = fminf(mn0, d2.x);
+            mn1 = fminf(mn1, d2.y);
+            PX = fadd2(PX, SX); PY = fadd2(PY, SY);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = mn0 + mn1;
 }
 
 // Clears a run's output arena: words [0, first_off) = 0 (counters, stats, counts),
