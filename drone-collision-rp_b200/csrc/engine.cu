@@ -125,6 +125,10 @@ struct dcrp_engine {
     size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;
     DevBuf d_records, d_cands, d_replay;
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
+    // launch configuration caches (per engine = per device: function attributes are per device)
+    size_t screen_smem[2] = {0, 0};
+    int screen_occ[2] = {0, 0};
+    int ap_occ = 0;
     bool allpairs_run = false;
     uint64_t ap_rays = 0;
     DevBuf d_ap_hist, d_ap_rank, d_ap_rayA, d_ap_rayB, d_ap_meta, d_ap_l2;
@@ -413,14 +417,12 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 struct ScreenCfg {
     int rounds, block, minb;
     const void* kern[2];          // [REPLAY]
-    size_t configured_smem[2];
-    int occ[2];
 };
 template <int R, int BLOCK, int MINB>
 static ScreenCfg make_cfg()
 {
     ScreenCfg c{R, BLOCK, MINB, {(const void*)k_screen2<R, BLOCK, false, MINB>,
-                                 (const void*)k_screen2<R, BLOCK, true, MINB>}, {0, 0}, {0, 0}};
+                                 (const void*)k_screen2<R, BLOCK, true, MINB>}};
     return c;
 }
 // [0] is the production configuration; the others exist for the tuning sweep
@@ -443,16 +445,16 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2));
-    if (c.configured_smem[v] != smem) {
+    if (e->screen_smem[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(c.kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.occ[v], c.kern[v], c.block, smem);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], c.kern[v], c.block, smem);
         if (ce != cudaSuccess) return ce;
-        if (c.occ[v] < 1) c.occ[v] = 1;
-        c.configured_smem[v] = smem;
+        if (e->screen_occ[v] < 1) e->screen_occ[v] = 1;
+        e->screen_smem[v] = smem;
     }
     static const int cta_cap = std::getenv("DCRP_MAX_CTAS") ? std::atoi(std::getenv("DCRP_MAX_CTAS")) : 0;
-    const int occ = (cta_cap > 0 && cta_cap < c.occ[v]) ? cta_cap : c.occ[v];
+    const int occ = (cta_cap > 0 && cta_cap < e->screen_occ[v]) ? cta_cap : e->screen_occ[v];
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ);
     static const uint32_t stagger_ns =
         std::getenv("DCRP_STAGGER_NS") ? (uint32_t)std::atoi(std::getenv("DCRP_STAGGER_NS")) : 0u;
@@ -790,7 +792,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
 
         const size_t smem = (size_t)AP_STAGES * AP_TILE * 8 + 2 * AP_STAGES * sizeof(uint64_t);
         const void* kern = ap_np == 1 ? (const void*)k_ap_scan_tracks<1> : (const void*)k_ap_scan_tracks<2>;
-        static int occ = 0;
+        int& occ = e->ap_occ;
         if (occ == 0) {
             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AP_BLOCK, smem));
