@@ -14,6 +14,7 @@ OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RUNWAY, ERR_STATE, ERR_IO = -1, -2, -3, -4, -5, -6
 FP64, MIXED, FP32 = 0, 1, 2
 FLAG_PER_TRIAL = 1
+FLAG_SUBSTEP = 2
 INT32_MAX = 2**31 - 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -36,8 +37,8 @@ class Draw(C.Structure):
 DRAW_DTYPE = np.dtype([("t1st", "<i4"), ("reserved", "<i4"), ("tx", "<f8"), ("ty", "<f8"), ("tz", "<f8")])
 RECORD_DTYPE = np.dtype([("track", "<u4"), ("drone", "<u4"), ("trial", "<u8"), ("t1st", "<i4"),
                          ("first_hit", "<i4"), ("tx", "<f8"), ("ty", "<f8"), ("tz", "<f8"),
-                         ("min_dist", "<f8")])
-assert DRAW_DTYPE.itemsize == 32 and RECORD_DTYPE.itemsize == 56
+                         ("min_dist", "<f8"), ("first_time", "<f8")])
+assert DRAW_DTYPE.itemsize == 32 and RECORD_DTYPE.itemsize == 64
 
 
 class Model(C.Structure):

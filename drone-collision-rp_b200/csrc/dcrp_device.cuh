@@ -35,6 +35,8 @@ struct TrackDev {
     double   wx32, wy32; // (box[1]-box[0]) * 2^-32, (box[3]-box[2]) * 2^-32
     float    wz32;       // (box[5]-box[4]) * 2^-32
     float    z0rel;      // box[4] - start_alt
+    float    thr2_l1_sub;// sub-step mode, level-1 threshold: (R + margin + (max |dA_xy| + v_straight)/2)^2
+    float    pad2;
 };
 
 struct ScenarioDev {
@@ -49,6 +51,9 @@ struct ScenarioDev {
     double*         p1y;
     int32_t*        s1_first_hit;
     double*         s1_prefmin;
+    double*         s1sub_prefmin;   // [n_pairs*t_max] sub-step: min d2 over stage-1 SEGMENTS with index < L
+    int32_t*        s1sub_first_seg; // [n_pairs] first stage-1 segment in conflict (INT32_MAX if none)
+    double*         s1sub_first_time;// [n_pairs] its conflict time (segment index + t)
     double2*        kink;            // [n_pairs*t_max] (box.xmin - p1x[L], box.ymin - p1y[L]): fast screen set-up
     float2*         p1f;             // [n_drones*t_max] stage-1 path relative to the origin, rounded once to fp32
     int32_t n_tracks, n_drones, t_max, n_steps_max;
@@ -57,18 +62,20 @@ struct ScenarioDev {
     double start_alt, v_straight, v_ascend;
     double radius;                   // R_drone + R_aircraft, summed in fp64 (Drone.cpp:260)
     double thr_d2;                   // sqrt_rn(d2) < radius  <=>  d2 < thr_d2   (exact, host-searched)
+    double radius2;                  // radius * radius: the sub-step mode's threshold on |D(t)|^2
     float  thr2_screen;              // (radius + margin)^2 : fp32 screen, conservative
     float  thr2_fp32;                // radius^2 in fp32    : DCRP_PRECISION_FP32 decisions
     float  v_straight_f, coef_f;     // 19, 2*(19-8)/pi
     int32_t bucket_shift;            // t1st bucket = (t1st-1) >> bucket_shift   (<= 64 buckets)
 };
 
-struct Record {          // == dcrp_record (56 bytes)
+struct Record {          // == dcrp_record (64 bytes)
     uint32_t track, drone;
     uint64_t trial;
     int32_t  t1st, first_hit;
     double   tx, ty, tz;
     double   min_dist;
+    double   first_time;
 };
 
 struct Candidate {       // a trial the fp32 screen could not rule out
@@ -122,6 +129,7 @@ struct RunDev {
     int32_t*  trial_first;
     double*   trial_min;
     int32_t   decide_fp32;               // screen kernel: 1 = DCRP_PRECISION_FP32
+    int32_t   substep;                   // 1 = DCRP_FLAG_SUBSTEP: interpolated separation between samples
 };
 
 }  // namespace dcrp

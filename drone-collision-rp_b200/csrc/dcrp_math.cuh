@@ -159,6 +159,43 @@ DCRP_HD double sep2(double x, double y, double z, double ax, double ay, double a
     return DADD(DADD(DMUL(dx, dx), DMUL(dy, dy)), DMUL(dz, dz));
 }
 
+// ---------------------------------------------------------------- sub-step (interpolated) separation
+// EXTENSION, no counterpart in the reference (which compares sample i with sample i only,
+// Drone.cpp:254-259): drone and aircraft move linearly between consecutive samples; the relative
+// position on segment [i, i+1] is D(t) = D0 + t*(D1 - D0), t in [0, 1].
+struct SegOut {
+    double d2;    // min over t of |D(t)|^2
+    double tc;    // first t in [0, 1] with |D(t)|^2 < r2, or -1 when the segment stays outside
+};
+
+DCRP_HD SegOut seg_closest(double x0, double y0, double z0, double x1, double y1, double z1, double r2)
+{
+    const double ex = DSUB(x1, x0), ey = DSUB(y1, y0), ez = DSUB(z1, z0);
+    const double a = DADD(DADD(DMUL(ex, ex), DMUL(ey, ey)), DMUL(ez, ez));
+    const double b = DADD(DADD(DMUL(x0, ex), DMUL(y0, ey)), DMUL(z0, ez));
+    const double c = DADD(DADD(DMUL(x0, x0), DMUL(y0, y0)), DMUL(z0, z0));
+    double t = 0.0;
+    if (a > 0.0) {
+        t = DDIV(-b, a);
+        if (t < 0.0) t = 0.0;
+        if (t > 1.0) t = 1.0;
+    }
+    SegOut o;
+    o.d2 = DADD(c, DMUL(t, DADD(DMUL(2.0, b), DMUL(t, a))));
+    if (o.d2 < 0.0) o.d2 = 0.0;
+    o.tc = -1.0;
+    if (c < r2) {
+        o.tc = 0.0;
+    } else if (o.d2 < r2) {              // enters the sphere inside the segment: smaller root of |D(t)|^2 = r2
+        const double disc = DSUB(DMUL(b, b), DMUL(a, DSUB(c, r2)));
+        double tc = DDIV(DSUB(-b, DSQRT(disc > 0.0 ? disc : 0.0)), a);
+        if (tc < 0.0) tc = 0.0;
+        if (tc > 1.0) tc = 1.0;
+        o.tc = tc;
+    }
+    return o;
+}
+
 // ---------------------------------------------------------------- fp32 screen set-up
 struct Ray32 {           // second-stage ray relative to the scenario origin, fp32:
     float bx, by, bz;    // position(i) = b + i * s  for absolute index i >= t1st

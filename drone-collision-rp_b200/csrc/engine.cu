@@ -22,7 +22,7 @@
 using namespace dcrp;
 
 static_assert(sizeof(dcrp_draw) == sizeof(Draw) && sizeof(Draw) == 32, "draw layout");
-static_assert(sizeof(dcrp_record) == sizeof(Record) && sizeof(Record) == 56, "record layout");
+static_assert(sizeof(dcrp_record) == sizeof(Record) && sizeof(Record) == 64, "record layout");
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -107,7 +107,7 @@ struct dcrp_engine {
     //   [tracks | ax | ay | az | trk32 | drones], each segment 256-B aligned
     DevBuf d_scn;
     PinnedBuf h_scn;
-    DevBuf d_p1x, d_p1y, d_s1fh, d_s1pm, d_kink, d_p1f;
+    DevBuf d_p1x, d_p1y, d_s1fh, d_s1pm, d_kink, d_p1f, d_s1sub_pm, d_s1sub_fs, d_s1sub_ft;
     bool prepare_timed = false;
 
     // run
@@ -194,7 +194,8 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     if (!e) return DCRP_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_out, &e->d_records,
+    DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_s1sub_pm, &e->d_s1sub_fs,
+                      &e->d_s1sub_ft, &e->d_out, &e->d_records,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
                       &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
                       &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2};
@@ -319,6 +320,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         while (std::sqrt(c) < s.radius) c = std::nextafter(c, INFINITY);
         s.thr_d2 = c;
     }
+    s.radius2 = s.radius * s.radius;
     // fp32 screen error budget per coordinate (DESIGN.md "screen margin"): the scan accumulates
     // P += S for at most tile_steps indices between exact re-bases (<= tile_steps/2 ulp), plus one
     // rounding each for the re-based start, the recentred track sample and the difference, plus the
@@ -329,6 +331,16 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     const double margin = 0.02 + 1.7321 * (0.5 * screen_tile + 4.0) * ulp +
                           (double)vl_max * model->v_straight * std::ldexp(1.0, -22);
     s.thr2_screen = std::nextafterf((float)((s.radius + margin) * (s.radius + margin)), INFINITY);
+    for (int a = 0; a < n_tracks; ++a) {          // sub-step mode: per-track level-1 radius
+        const dcrp_track& t = tracks[a];
+        double amax = 0.0;
+        for (int i = 0; i + 1 < t.n_steps; ++i)
+            amax = std::max(amax, std::hypot(t.x[i + 1] - t.x[i], t.y[i + 1] - t.y[i]));
+        const double rr = s.radius + margin + 0.5 * (amax + model->v_straight) * (1.0 + 1e-6);
+        TrackDev& d = e->h_tracks[(size_t)a];
+        d.thr2_l1_sub = std::nextafterf((float)(rr * rr), INFINITY);
+        d.pad2 = 0.f;
+    }
     s.thr2_fp32 = (float)(s.radius * s.radius);
     s.v_straight_f = (float)model->v_straight;
     s.coef_f = (float)(2.0 * (model->v_straight - model->v_ascend) / DCRP_PI);
@@ -381,6 +393,9 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     CU(e->d_s1fh.need(sizeof(int32_t) * n_pairs));
     CU(e->d_s1pm.need(sizeof(double) * n_pairs * (size_t)t_max));
     CU(e->d_kink.need(sizeof(double2) * n_pairs * (size_t)t_max));
+    CU(e->d_s1sub_pm.need(sizeof(double) * n_pairs * (size_t)t_max));
+    CU(e->d_s1sub_fs.need(sizeof(int32_t) * n_pairs));
+    CU(e->d_s1sub_ft.need(sizeof(double) * n_pairs));
     CU(e->d_p1f.need(sizeof(float2) * (size_t)n_drones * (size_t)t_max));
     CU(cudaEventRecord(e->ev_a, st));
     CU(cudaMemcpyAsync(e->d_scn.p, hb, scn_bytes, cudaMemcpyHostToDevice, st));
@@ -399,6 +414,9 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.s1_prefmin = e->d_s1pm.as<double>();
     s.kink = e->d_kink.as<double2>();
     s.p1f = e->d_p1f.as<float2>();
+    s.s1sub_prefmin = e->d_s1sub_pm.as<double>();
+    s.s1sub_first_seg = e->d_s1sub_fs.as<int32_t>();
+    s.s1sub_first_time = e->d_s1sub_ft.as<double>();
 
     k_stage1<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(s);
     ++e->launches;
@@ -475,6 +493,10 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         return fail(DCRP_ERR_INVALID, "unknown precision %d", run->precision);
     if ((run->flags & DCRP_FLAG_PER_TRIAL) && run->precision != DCRP_PRECISION_FP64)
         return fail(DCRP_ERR_INVALID, "DCRP_FLAG_PER_TRIAL needs DCRP_PRECISION_FP64");
+    if ((run->flags & DCRP_FLAG_SUBSTEP) && run->precision == DCRP_PRECISION_FP32)
+        return fail(DCRP_ERR_INVALID, "DCRP_FLAG_SUBSTEP needs DCRP_PRECISION_FP64 or DCRP_PRECISION_MIXED");
+    if ((run->flags & DCRP_FLAG_SUBSTEP) && e->sd.n_steps_max < 2)
+        return fail(DCRP_ERR_INVALID, "DCRP_FLAG_SUBSTEP needs tracks of at least 2 samples");
     if (run->trial_begin + run->trial_count < run->trial_begin)
         return fail(DCRP_ERR_INVALID, "trial range overflows 64 bits");
     CU(cudaSetDevice(e->device));
@@ -522,6 +544,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     r.cand_cap = CAND_CAP;
     r.stats = small_stats(e);
     r.decide_fp32 = (run->precision == DCRP_PRECISION_FP32) ? 1 : 0;
+    r.substep = (run->flags & DCRP_FLAG_SUBSTEP) ? 1 : 0;
     if (run->flags & DCRP_FLAG_PER_TRIAL) {
         const size_t n = n_pairs * (size_t)run->trial_count;
         CU(e->d_trial_hit.need(n ? n : 1));

@@ -219,8 +219,22 @@ __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
     double x = d.x, y = d.y;
     double mn = INFINITY;
     int first = INT_MAX;
+    // sub-step extension: the same walk over the stage-1 SEGMENTS i-1 -> i
+    double px = 0, py = 0, pz = 0, smn = INFINITY, stime = -1.0;
+    int sfirst = INT_MAX;
     for (int i = 0; i < s.t_max; ++i) {
         if (i > 0) { x = DADD(x, d.z); y = DADD(y, d.w); }
+        s.s1sub_prefmin[(size_t)pair * s.t_max + i] = smn;          // segments with index < i
+        if (i < t.n_steps) {
+            const double cx = DSUB(x, s.ax[t.off + i]), cy = DSUB(y, s.ay[t.off + i]),
+                         cz = DSUB(s.start_alt, s.az[t.off + i]);
+            if (i > 0) {
+                const SegOut sg = seg_closest(px, py, pz, cx, cy, cz, s.radius2);
+                if (sg.d2 < smn) smn = sg.d2;
+                if (sg.tc >= 0.0 && sfirst == INT_MAX) { sfirst = i - 1; stime = DADD((double)(i - 1), sg.tc); }
+            }
+            px = cx; py = cy; pz = cz;
+        }
         if (a == 0) {
             s.p1x[(size_t)j * s.t_max + i] = x; s.p1y[(size_t)j * s.t_max + i] = y;
             s.p1f[(size_t)j * s.t_max + i] = make_float2((float)DSUB(x, s.ox), (float)DSUB(y, s.oy));
@@ -234,14 +248,17 @@ __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
         s.s1_prefmin[(size_t)pair * s.t_max + i] = mn;
     }
     s.s1_first_hit[pair] = first;
+    s.s1sub_first_seg[pair] = sfirst;
+    s.s1sub_first_time[pair] = stime;
 }
 
 // =========================================================================
 // the exact trial (fp64, reference order of operations)
 // =========================================================================
 struct TrialOut {
-    int32_t first;     // first index in collision, -1 if none
-    double  min_d2;    // min squared separation over all indices
+    int32_t first;     // first index (sub-step mode: first segment) in collision, -1 if none
+    double  min_d2;    // min squared separation over all indices (sub-step: over all segments)
+    double  first_time;// first-conflict time in index units (= first unless sub-step mode)
 };
 
 // ax/ay/az point at sample 0 of the track (global or shared).
@@ -265,7 +282,45 @@ __device__ __forceinline__ TrialOut exact_trial(const ScenarioDev& s, int pair, 
         if (d2 < o.min_d2) o.min_d2 = d2;
         if (d2 < s.thr_d2 && o.first < 0) o.first = i;      // Drone.cpp:260 (sqrt folded into thr_d2)
     }
+    o.first_time = (double)o.first;
     return o;
+}
+
+// The same trial with the separation interpolated between samples (extension; see seg_closest).
+// Segments 0..t1st-2 lie in stage 1 and come from the per-pair tables; segment t1st-1 starts at the kink.
+__device__ __forceinline__ TrialOut exact_trial_sub(const ScenarioDev& s, int pair, int j, int n_steps,
+                                                    const double* __restrict__ ax,
+                                                    const double* __restrict__ ay,
+                                                    const double* __restrict__ az, const Draw& d)
+{
+    const int last = d.t1st - 1;
+    const double xl = s.p1x[(size_t)j * s.t_max + last];
+    const double yl = s.p1y[(size_t)j * s.t_max + last];
+    const Ray64 r = stage2_ray(xl, yl, s.start_alt, d.tx, d.ty, d.tz, s.v_straight, s.v_ascend);
+    TrialOut o;
+    const int s1 = s.s1sub_first_seg[pair];
+    o.first = (s1 < last) ? s1 : -1;
+    o.first_time = (s1 < last) ? s.s1sub_first_time[pair] : -1.0;
+    o.min_d2 = s.s1sub_prefmin[(size_t)pair * s.t_max + last];
+    double x = r.x, y = r.y, z = r.z;
+    double px = DSUB(x, ax[last]), py = DSUB(y, ay[last]), pz = DSUB(z, az[last]);
+    for (int i = d.t1st; i < n_steps; ++i) {
+        x = DADD(x, r.sx); y = DADD(y, r.sy); z = DADD(z, r.sz);
+        const double cx = DSUB(x, ax[i]), cy = DSUB(y, ay[i]), cz = DSUB(z, az[i]);
+        const SegOut sg = seg_closest(px, py, pz, cx, cy, cz, s.radius2);
+        if (sg.d2 < o.min_d2) o.min_d2 = sg.d2;
+        if (sg.tc >= 0.0 && o.first < 0) { o.first = i - 1; o.first_time = DADD((double)(i - 1), sg.tc); }
+        px = cx; py = cy; pz = cz;
+    }
+    return o;
+}
+
+__device__ __forceinline__ TrialOut exact_any(const ScenarioDev& s, const RunDev& r, int pair, int j, int n_steps,
+                                              const double* __restrict__ ax, const double* __restrict__ ay,
+                                              const double* __restrict__ az, const Draw& d)
+{
+    return r.substep ? exact_trial_sub(s, pair, j, n_steps, ax, ay, az, d)
+                     : exact_trial(s, pair, j, n_steps, ax, ay, az, d);
 }
 
 __device__ __forceinline__ Draw fetch_draw(const ScenarioDev& s, const RunDev& r, const TrackDev& t,
@@ -288,6 +343,7 @@ __device__ __forceinline__ void publish_hit(const ScenarioDev& s, const RunDev& 
         rec.t1st = d.t1st; rec.first_hit = o.first;
         rec.tx = d.tx; rec.ty = d.ty; rec.tz = d.tz;
         rec.min_dist = DSQRT(o.min_d2);
+        rec.first_time = o.first_time;
         r.records[slot] = rec;
     }
 }
@@ -340,7 +396,7 @@ __global__ void __launch_bounds__(EXB) k_exact(const ScenarioDev s, const RunDev
         const uint64_t local = r.slice_first + in_slice;       // index within the run
         if (in_slice < r.slice_count) {
             const Draw d = fetch_draw(s, r, t, pair, a, j, local);
-            const TrialOut o = exact_trial(s, pair, j, t.n_steps, ax, ay, az, d);
+            const TrialOut o = exact_any(s, r, pair, j, t.n_steps, ax, ay, az, d);
             ev += (unsigned long long)(t.n_steps - d.t1st);
             sh += (unsigned long long)d.t1st;
             st += (unsigned long long)(t.n_steps - 1);
@@ -372,7 +428,7 @@ __global__ void __launch_bounds__(128) k_confirm_all(const ScenarioDev s, const 
         const TrackDev t = s.tracks[a];
         const uint64_t local = cd.trial - r.trial_begin;
         const Draw d = fetch_draw(s, r, t, pair, a, j, local);
-        const TrialOut o = exact_trial(s, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
+        const TrialOut o = exact_any(s, r, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
         if (o.first >= 0) {
             ++hits;
             publish_hit(s, r, pair, a, j, cd.trial, d, o);
@@ -443,7 +499,7 @@ __device__ __forceinline__ void rescan_fp32(const ScenarioDev& s, const RunDev& 
     }
     if (first >= 0) {
         Draw d; d.t1st = u.t1st; d.reserved = 0; d.tx = u.tx; d.ty = u.ty; d.tz = u.tz;
-        TrialOut o; o.first = first; o.min_d2 = (double)mn;
+        TrialOut o; o.first = first; o.min_d2 = (double)mn; o.first_time = (double)first;
         atomicAdd(&r.stats[ST_HITS], 1ull);
         publish_hit(s, r, pair, a, j, trial, d, o);
     }
@@ -461,6 +517,33 @@ __device__ __forceinline__ float min3d_fp32(const ScenarioDev& s, const TrackDev
         const float dy = fmaf(p.w, u.ray.sy, u.ray.by) + p.y;
         const float dz = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
         mn = fminf(mn, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+    return mn;
+}
+
+// Level 2 in sub-step mode: min over the per-trial SEGMENTS [i, i+1], i >= t1st-1, of the fp32 closest
+// approach of the interpolated relative position.
+__device__ __forceinline__ float min3d_seg_fp32(const ScenarioDev& s, const TrackDev& t, const Setup32& u)
+{
+    const float4* __restrict__ g = s.trk32 + (size_t)t.off;
+    float mn = 3.0e38f;
+    const int last = u.t1st - 1;
+    float4 p = __ldg(&g[last]);
+    float x0 = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x, y0 = fmaf(p.w, u.ray.sy, u.ray.by) + p.y,
+          z0 = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
+    for (int i = u.t1st; i < t.n_steps; ++i) {
+        p = __ldg(&g[i]);
+        const float x1 = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x, y1 = fmaf(p.w, u.ray.sy, u.ray.by) + p.y,
+                    z1 = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
+        const float ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
+        const float a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+        const float b = fmaf(z0, ez, fmaf(y0, ey, x0 * ex));
+        const float c = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
+        const float tt = a > 0.f ? fminf(fmaxf(__fdividef(-b, a), 0.f), 1.f) : 0.f;
+        // the interior minimum c - b^2/a cancels: bound its fp32 error by comparing against both ends too
+        const float dmin = fmaf(tt, fmaf(tt, a, 2.f * b), c);
+        mn = fminf(mn, fminf(dmin, c));
+        x0 = x1; y0 = y1; z0 = z1;
     }
     return mn;
 }
@@ -566,7 +649,13 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         const int n_tiles = (VL + tile_steps - 1) / tile_steps;
         const uint64_t chunk_first64 = r.slice_first + (uint64_t)c * CH;
         const uint32_t n_valid = (uint32_t)min((uint64_t)CH, r.slice_count - (uint64_t)c * CH);
-        const int s1_first = __ldg(&s.s1_first_hit[pair]);
+        // first stage-1 conflict, as "every trial whose kink index is >= this must be confirmed":
+        // a sample index in sample mode, (segment index + 1) in sub-step mode
+        int s1_first = __ldg(&s.s1_first_hit[pair]);
+        if (r.substep) {
+            const int sg = __ldg(&s.s1sub_first_seg[pair]);
+            s1_first = sg == INT_MAX ? INT_MAX : sg + 1;
+        }
         const float2* __restrict__ gtrk = s.trkxy + (size_t)__ldg(&tk->off_xy);
 
         if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {        // rare: keep the 32-bit partial sums exact
@@ -654,7 +743,9 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         if (single && need_load) { mbar_wait(&bars[0], phase0); phase0 ^= 1u; }
         loaded_track = single ? a : -1;
 
-        const float thr = r.decide_fp32 ? s.thr2_fp32 : s.thr2_screen;
+        // sub-step mode: a segment can only come within R of the aircraft if one of its end SAMPLES is
+        // within R + half the largest relative step, so level 1 keeps testing samples against a wider radius
+        const float thr = r.decide_fp32 ? s.thr2_fp32 : (r.substep ? __ldg(&tk->thr2_l1_sub) : s.thr2_screen);
 
         // ---------------- R rounds: set up one packed pair, scan it
 #pragma unroll 1
@@ -695,7 +786,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             }
             const f2_t BX = pk2(bxs[0], bxs[1]), BY = pk2(bys[0], bys[1]);
             const f2_t SX[1] = {pk2(sxs[0], sxs[1])}, SY[1] = {pk2(sys[0], sys[1])};
-            const int imin = __reduce_min_sync(0xffffffffu, tmin);
+            // sub-step mode also needs the kink sample (index t1st-1), the first end of the first segment
+            const int imin = __reduce_min_sync(0xffffffffu, tmin) - (r.substep ? 1 : 0);
             if (imin < VL) acc_is += (uint32_t)(VL - imin) * 2u;
 
             float mn[2] = {3.0e38f, 3.0e38f};       // running min of the horizontal d2 of trial 0 / 1
@@ -744,7 +836,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
                     if (r.decide_fp32) {
                         rescan_fp32(s, r, *tk, pair, a, j, s1_first, trial, u);
-                    } else if (u.force || min3d_fp32(s, *tk, u) < s.thr2_screen) {
+                    } else if (u.force ||
+                               (r.substep ? min3d_seg_fp32(s, *tk, u) : min3d_fp32(s, *tk, u)) < s.thr2_screen) {
                         ++ncand;
                         const uint32_t slot = warp_claim_slot(r.cand_count);
                         if (slot < r.cand_cap) {

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DCRP_ABI_VERSION 1
+#define DCRP_ABI_VERSION 2
 
 /* status codes */
 #define DCRP_OK               0
@@ -45,6 +45,12 @@ extern "C" {
 
 /* flags */
 #define DCRP_FLAG_PER_TRIAL   1u  /* fill per-trial outputs (FP64 mode only; test aid)              */
+#define DCRP_FLAG_SUBSTEP     2u  /* EXTENSION (not in the reference, which compares sample i with
+                                     sample i only, Drone.cpp:254-259): drone and aircraft are
+                                     interpolated linearly between samples and a collision is
+                                     min over t of the separation on a segment < R.  first_hit is then
+                                     the first SEGMENT in conflict, first_time the conflict time in
+                                     index units, min_dist the continuous minimum.  FP64 / MIXED only. */
 
 typedef struct dcrp_engine dcrp_engine;
 
@@ -113,6 +119,8 @@ typedef struct dcrp_record {
     int32_t  first_hit;        /* first index with distance < R     */
     double   tx, ty, tz;       /* stage-2 target                    */
     double   min_dist;         /* min separation over the track (m) */
+    double   first_time;       /* first-conflict time in index units: == first_hit in sample mode,
+                                  segment + t in [0,1) with DCRP_FLAG_SUBSTEP                         */
 } dcrp_record;
 
 typedef struct dcrp_stats {

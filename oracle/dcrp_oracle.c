@@ -221,6 +221,68 @@ int64_t orc_run_philox(const double* ax, const double* ay, const double* az, int
     return hits;
 }
 
+/* ------------------------------------------------------- sub-step extension */
+static void seg_closest(double x0, double y0, double z0, double x1, double y1, double z1, double r2,
+                        double* d2_out, double* tc_out)
+{
+    double ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
+    double a = (ex * ex + ey * ey) + ez * ez;
+    double b = (x0 * ex + y0 * ey) + z0 * ez;
+    double c = (x0 * x0 + y0 * y0) + z0 * z0;
+    double t = 0.0;
+    if (a > 0.0) {
+        t = -b / a;
+        if (t < 0.0) t = 0.0;
+        if (t > 1.0) t = 1.0;
+    }
+    double d2 = c + t * (2.0 * b + t * a);
+    if (d2 < 0.0) d2 = 0.0;
+    double tc = -1.0;
+    if (c < r2) {
+        tc = 0.0;
+    } else if (d2 < r2) {
+        double disc = b * b - a * (c - r2);
+        tc = (-b - sqrt(disc > 0.0 ? disc : 0.0)) / a;
+        if (tc < 0.0) tc = 0.0;
+        if (tc > 1.0) tc = 1.0;
+    }
+    *d2_out = d2;
+    *tc_out = tc;
+}
+
+int64_t orc_run_trials_substep(const double* ax, const double* ay, const double* az, int32_t n_steps,
+                               double x0, double y0, double heading0,
+                               const orc_draw* draws, int64_t n, const orc_model* model,
+                               uint8_t* hit, int32_t* first_seg, double* first_time, double* min_dist)
+{
+    int64_t hits = 0;
+    const double R = model->drone_radius + model->aircraft_radius;
+    const double r2 = R * R;
+    double* X = (double*)malloc(sizeof(double) * (size_t)n_steps * 3);
+    double* Y = X + n_steps;
+    double* Z = X + 2 * (size_t)n_steps;
+    for (int64_t r = 0; r < n; ++r) {
+        orc_trial_result res;
+        orc_trial(ax, ay, az, n_steps, x0, y0, heading0, &draws[r], model, X, Y, Z, &res);
+        int first = -1;
+        double ftime = -1.0, mn = INFINITY;
+        for (int i = 0; i + 1 < n_steps; ++i) {
+            double d2, tc;
+            seg_closest(X[i] - ax[i], Y[i] - ay[i], Z[i] - az[i],
+                        X[i + 1] - ax[i + 1], Y[i + 1] - ay[i + 1], Z[i + 1] - az[i + 1], r2, &d2, &tc);
+            if (d2 < mn) mn = d2;
+            if (tc >= 0.0 && first < 0) { first = i; ftime = (double)i + tc; }
+        }
+        if (first >= 0) ++hits;
+        if (hit) hit[r] = first >= 0;
+        if (first_seg) first_seg[r] = first;
+        if (first_time) first_time[r] = ftime;
+        if (min_dist) min_dist[r] = sqrt(mn);
+    }
+    free(X);
+    return hits;
+}
+
 int64_t orc_format_block(const double* x, const double* y, const double* z, int32_t n_steps,
                          int32_t run_no, char* buf, int64_t cap)
 {

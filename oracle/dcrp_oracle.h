@@ -92,6 +92,18 @@ int64_t orc_run_philox(const double* ax, const double* ay, const double* az, int
                        uint64_t trial_begin, int64_t n, const orc_model* model,
                        uint64_t* hit_ids, int64_t cap, int64_t* n_ids);
 
+/* EXTENSION -- NOT in the reference (it compares sample i with sample i only,
+ * Drone.cpp:254-259), parity UNPINNED for this function: it is the build's own
+ * definition of the interpolated ("sub-step") separation and only checks that
+ * the GPU implements the same definition.  Drone and aircraft move linearly
+ * between consecutive samples; on segment i the relative position is
+ * D(t) = D_i + t (D_{i+1} - D_i); a conflict is min_t |D(t)|^2 < R^2.
+ * n trials of one (track, drone); trajectories come from orc_trial. */
+int64_t orc_run_trials_substep(const double* ax, const double* ay, const double* az, int32_t n_steps,
+                               double x0, double y0, double heading0,
+                               const orc_draw* draws, int64_t n, const orc_model* model,
+                               uint8_t* hit, int32_t* first_seg, double* first_time, double* min_dist);
+
 /* Drone::Output row format, Drone.cpp:237-241: ostream precision(10), default
  * floatfield == printf "%.10g".  Writes n_steps lines "x,y,z,run\n" plus one
  * blank line into buf (capacity cap); returns bytes written or -1. */

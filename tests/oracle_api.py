@@ -58,6 +58,10 @@ class Oracle:
         L.orc_run_philox.argtypes = [dp, dp, dp, C.c_int32, C.c_int32, dp, C.c_double, C.c_double, C.c_double,
                                      C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int64, C.POINTER(Model),
                                      C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.orc_run_trials_substep.restype = C.c_int64
+        L.orc_run_trials_substep.argtypes = [dp, dp, dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p,
+                                             C.c_int64, C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
         L.orc_trial.argtypes = [dp, dp, dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p,
                                 C.POINTER(Model), dp, dp, dp, C.c_void_p]
         L.orc_format_block.restype = C.c_int64
@@ -95,6 +99,19 @@ class Oracle:
         self.L.orc_run_trials(_d(x), _d(y), _d(z), len(x), float(drone[0]), float(drone[1]), float(drone[2]),
                               draws.ctypes.data, n, C.byref(m), hit.ctypes.data, first.ctypes.data, mind.ctypes.data)
         return hit, first, mind
+
+    def run_trials_substep(self, trk, drone, draws, model=None):
+        """EXTENSION (no reference counterpart): interpolated separation, see dcrp_oracle.h."""
+        n = len(draws)
+        x, y, z = (np.ascontiguousarray(trk[k], dtype=np.float64) for k in "xyz")
+        draws = np.ascontiguousarray(draws, dtype=DRAW_DTYPE)
+        hit, first = np.zeros(n, np.uint8), np.zeros(n, np.int32)
+        ftime, mind = np.zeros(n, np.float64), np.zeros(n, np.float64)
+        m = model or self.model
+        self.L.orc_run_trials_substep(_d(x), _d(y), _d(z), len(x), float(drone[0]), float(drone[1]), float(drone[2]),
+                                      draws.ctypes.data, n, C.byref(m), hit.ctypes.data, first.ctypes.data,
+                                      ftime.ctypes.data, mind.ctypes.data)
+        return hit, first, ftime, mind
 
     def run_philox(self, trk, box, drone, seed, drone_id, track_id, trial_begin, n, cap=4096, model=None):
         x, y, z = (np.ascontiguousarray(trk[k], dtype=np.float64) for k in "xyz")
