@@ -95,7 +95,8 @@ DCRP_SYMBOLS = [
     "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_launch_count", "dcrp_device_info",
 ]
 DCRP_HOST_SYMBOLS = [
-    "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_aircraft_load",
+    "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_ring_write",
+    "dcrph_aircraft_load",
     "dcrph_ring_row", "dcrph_monte_carlo", "dcrph_monte_carlo_batch", "dcrph_write_block",
 ]
 
@@ -145,6 +146,7 @@ def host():
         H.dcrph_last_error.restype = C.c_char_p
         H.dcrph_reference_aircraft_csv.restype = C.c_char_p
         H.dcrph_synth_day_write.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_int]
+        H.dcrph_ring_write.argtypes = [C.c_char_p, C.c_double, C.c_int]
         H.dcrph_aircraft_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), c_double_p, c_double_p, c_double_p, c_double_p,
                                           C.c_int]

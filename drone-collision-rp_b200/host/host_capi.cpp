@@ -24,6 +24,16 @@ extern "C" int dcrph_synth_day_write(const char* path, int n_flights, uint64_t s
     return 0;
 }
 
+extern "C" int dcrph_ring_write(const char* path, double radius_m, int n_rows)
+{
+    if (!path) { g_host_err = "path is NULL"; return -1; }
+    if (dcrp_host::write_ring_csv(path, radius_m, n_rows) != 0) {
+        g_host_err = std::string("cannot write ring ") + path;
+        return -6;
+    }
+    return 0;
+}
+
 extern "C" int dcrph_aircraft_load(const char* path, int n_cols, int index, int* vector_length, int* takeoff_t,
                                    int* index_size, double* x, double* y, double* z, double* gs, int cap)
 {

@@ -1,6 +1,7 @@
 // synth_day.cpp -- see synth_day.h.
 #include "synth_day.h"
 
+#include <cmath>
 #include <cstdio>
 
 namespace dcrp_host {
@@ -64,6 +65,26 @@ int write_synthetic_day(const std::string& path, int n_flights, uint64_t seed, b
             if (v > vmax) v = vmax;
             easting -= v;
         }
+    }
+    std::fclose(f);
+    return 0;
+}
+
+int write_ring_csv(const std::string& path, double radius_m, int n_rows)
+{
+    if (n_rows < 2 || !(radius_m > 0)) return -1;
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return -1;
+    const double pi = 3.14159265358979323846;
+    const double cx = 676346.3657, cy = 5705295.6395;      // centre of both shipped rings
+    // calibrated on the shipped rings: grid convergence, and slightly different north / east scales
+    const double convergence = 0.0347, scale_n = 1.000535, scale_e = 1.003159;
+    std::fprintf(f, ",longitude,latitude,heading\r\n");
+    for (int k = 0; k < n_rows; ++k) {
+        const double bearing = 2.0 * pi * (double)(k % (n_rows - 1)) / (double)(n_rows - 1);
+        const double grid = bearing - convergence;
+        std::fprintf(f, "%d,%.10f,%.10f,%.15f\r\n", k, cx + scale_e * radius_m * std::sin(grid),
+                     cy + scale_n * radius_m * std::cos(grid), std::fmod(bearing + pi, 2.0 * pi));
     }
     std::fclose(f);
     return 0;

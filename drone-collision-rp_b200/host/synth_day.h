@@ -24,6 +24,15 @@ extern const char* const kReferenceAircraftCsv;
 // Returns 0, or -1 if the file cannot be written.
 int write_synthetic_day(const std::string& path, int n_flights, uint64_t seed, bool trailing_dummy);
 
+// Drone start ring in the format of drone_inital_positions_{1km,5km}.csv (header
+// ",longitude,latitude,heading", rows "k,easting,northing,heading", CRLF): n_rows points on a circle of
+// `radius_m` metres about the Heathrow reference point, row k at true bearing 2*pi*k/(n_rows-1) from it
+// (row n_rows-1 repeats row 0, as in the shipped files), heading = bearing + pi (towards the centre).
+// (mod 2*pi).  Calibrated on the two shipped rings: grid convergence 0.0347 rad and
+// north / east scales 1.000535 / 1.003159 reproduce them to < 0.1 % of the radius; headings to 1e-12.
+// Returns 0, or -1 on I/O failure.
+int write_ring_csv(const std::string& path, double radius_m, int n_rows);
+
 }  // namespace dcrp_host
 
 #endif

@@ -24,6 +24,9 @@ const char* dcrph_reference_aircraft_csv(void);      /* Monte_Carlo.cpp:11 file 
 /* Seeded synthetic ADS-B day in the reference's 22-column schema (synth_day.h). */
 int dcrph_synth_day_write(const char* path, int n_flights, uint64_t seed, int trailing_dummy);
 
+/* Drone start ring of any radius in the format of drone_inital_positions_{1km,5km}.csv (synth_day.h). */
+int dcrph_ring_write(const char* path, double radius_m, int n_rows);
+
 /* Aircraft::Set_Parameters_and_Data + Vector_Allocation(index) + Deallocation.
  * Writes Vector_length, takeoff_t, Aircraft_Index_size and up to `cap` samples
  * of the four column arrays; index < 0 only reports Aircraft_Index_size.

@@ -82,6 +82,23 @@ def test_ring_rows_as_the_reference_binds_them():
         scenario.load_ring(os.path.join(pk.DATA_DIR, "nope.csv"), n=1)
 
 
+def test_ring_generator_reproduces_the_shipped_rings(tmp_path):
+    """rings of other radii.  Calibration check: 1 km and 5 km rings against the shipped files."""
+    for radius, shipped in ((1000.0, pk.RING_1KM), (5000.0, pk.RING_5KM)):
+        path = str(tmp_path / ("ring_%d.csv" % radius))
+        capi._hcheck(capi.host().dcrph_ring_write(path.encode(), radius, 100))
+        got = scenario.load_ring(path, n=100)
+        want = scenario.load_ring(shipped, n=100)
+        assert np.abs(got[:, 2] - want[:, 2]).max() < 1e-12                   # headings: pi + 2 pi k / 99
+        assert np.hypot(got[:, 0] - want[:, 0], got[:, 1] - want[:, 1]).max() < 1e-3 * radius
+        assert open(path, "rb").read().count(b"\r\n") == 101
+    path = str(tmp_path / "ring_2500.csv")
+    capi._hcheck(capi.host().dcrph_ring_write(path.encode(), 2500.0, 100))
+    r = scenario.load_ring(path, n=99)
+    d = np.hypot(r[:, 0] - 676346.3657, r[:, 1] - 5705295.6395)
+    assert (d > 2500.0).all() and (d < 2510.0).all()
+
+
 def test_synthetic_day_schema_and_determinism(tmp_path):
     a = scenario.write_synthetic_day(str(tmp_path / "a.csv"), 5, 77, True)
     b = scenario.write_synthetic_day(str(tmp_path / "b.csv"), 5, 77, True)
