@@ -83,8 +83,9 @@ struct PinnedBuf {         // grow-only pinned host buffer (async copies need pa
 
 static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
-// screen kernel configuration: 256 threads, 2 rounds x 2 trials per thread per item,
-// 4 CTAs per SM (63 registers, no spills): best of the sweep in profiles/r01_screen_cfg_sweep.txt
+// screen kernel configuration: 512 threads, 4 rounds x 2 trials per thread per item
+// (4096-trial chunks), 2 CTAs per SM, 64 registers, no spills: best of the sweeps in
+// profiles/r01_screen_cfg_sweep.txt
 constexpr uint32_t DEFAULT_RECORD_CAP = 1u << 16;
 constexpr uint32_t CAND_CAP = 1u << 22;
 constexpr uint64_t MAX_ITEMS_PER_LAUNCH = 1ull << 30;
@@ -445,8 +446,8 @@ static ScreenCfg make_cfg()
 }
 // [0] is the production configuration; the others exist for the tuning sweep
 // (tools/profile_target.py with DCRP_SCREEN_CFG=n) and cost nothing unless selected.
-static ScreenCfg g_cfgs[] = {make_cfg<2, 256, 4>(), make_cfg<2, 256, 5>(), make_cfg<2, 512, 2>(),
-                             make_cfg<2, 128, 10>()};
+static ScreenCfg g_cfgs[] = {make_cfg<4, 512, 2>(), make_cfg<2, 256, 4>(), make_cfg<4, 256, 4>(),
+                             make_cfg<2, 512, 2>(), make_cfg<4, 128, 8>()};
 static ScreenCfg& screen_cfg()
 {
     static const int sel = std::getenv("DCRP_SCREEN_CFG") ? std::atoi(std::getenv("DCRP_SCREEN_CFG")) : 0;
@@ -462,7 +463,8 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     const int v = r.replay ? 1 : 0;
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
-                        (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2));
+                        (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2)) +
+                        (c.rounds > 2 ? (size_t)screen_chunk() * 2 : 0);          // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(c.kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;

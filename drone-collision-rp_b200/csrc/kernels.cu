@@ -620,6 +620,10 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     uint64_t* bars  = reinterpret_cast<uint64_t*>(hist + 80);
     double2*  tabk  = reinterpret_cast<double2*>(bars + 2);            // this pair's kink tables
     float2*   tabp  = reinterpret_cast<float2*>(tabk + SCREEN_TAB);
+    // K > 4: the draws stay where phase A wrote them (stage[local]) and only a 2-byte permutation is
+    // sorted (order[sorted slot] = local), so phase A never holds more than one trial's words in registers
+    constexpr bool IND = (K > 4);
+    uint16_t* order = reinterpret_cast<uint16_t*>(tabp + SCREEN_TAB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -689,13 +693,14 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         }
 
         {
-            uint32_t w1[K], w2[K], w3[K], meta[K], rank[K];
+            uint32_t w1[IND ? 1 : K], w2[IND ? 1 : K], w3[IND ? 1 : K], meta[IND ? 1 : K], rank[K];
 #pragma unroll
             for (int m = 0; m < K; ++m) {
+                const int mm = IND ? 0 : m;
                 const uint32_t local = (uint32_t)(m * BLOCK + tid);
                 uint32_t bucket = 64u;
-                meta[m] = local;
-                w1[m] = w2[m] = w3[m] = 0u;
+                meta[mm] = local;
+                w1[mm] = w2[mm] = w3[mm] = 0u;
                 if (local < n_valid) {
                     int32_t t1st;
                     if (REPLAY) {
@@ -703,16 +708,17 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     } else if (dbg & 4u) {      // profiling aid: no Philox (results meaningless)
                         const uint32_t h = (uint32_t)(chunk_first64 + local) * 2654435761u;
                         t1st = draw_t1st(h, takeoff_t);
-                        w1[m] = h ^ 0x9e3779b9u; w2[m] = h * 40503u; w3[m] = h + 0x7f4a7c15u;
+                        w1[mm] = h ^ 0x9e3779b9u; w2[mm] = h * 40503u; w3[mm] = h + 0x7f4a7c15u;
                     } else {
                         const U4 w = trial_words(r.seed, r.trial_begin + chunk_first64 + local,
                                                  r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a);
                         t1st = draw_t1st(w.x, takeoff_t);
-                        w1[m] = w.y; w2[m] = w.z; w3[m] = w.w;
+                        w1[mm] = w.y; w2[mm] = w.z; w3[mm] = w.w;
                     }
                     bucket = (uint32_t)(t1st - 1) >> s.bucket_shift;
-                    meta[m] = local | ((uint32_t)t1st << 12);
+                    meta[mm] = local | ((uint32_t)t1st << 12);
                 }
+                if (IND) stage[local] = make_uint4(w1[0], w2[0], w3[0], meta[0]);
                 rank[m] = atomicAdd(&hist[bucket], 1u) | (bucket << 16);
             }
             __syncthreads();
@@ -735,7 +741,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 #pragma unroll
             for (int m = 0; m < K; ++m) {
                 const uint32_t slot = hist[rank[m] >> 16] + (rank[m] & 0xffffu);
-                stage[slot] = make_uint4(w1[m], w2[m], w3[m], meta[m]);
+                if (IND) order[slot] = (uint16_t)(m * BLOCK + tid);
+                else     stage[slot] = make_uint4(w1[IND ? 0 : m], w2[IND ? 0 : m], w3[IND ? 0 : m], meta[IND ? 0 : m]);
             }
         }
         __syncthreads();
@@ -757,9 +764,11 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             float bxs[2], bys[2], sxs[2], sys[2];  // level 1 needs the horizontal ray only
             int tmin = INT_MAX;
             uint32_t fmask = 0;                   // bit m: trial m must go to level 2 regardless of the scan
+            uint32_t sidx[2];                     // where this lane's two trials sit in stage[]
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                const uint4 q = stage[slot0 + m * 32];
+                sidx[m] = IND ? (uint32_t)order[slot0 + m * 32] : slot0 + m * 32;
+                const uint4 q = stage[sidx[m]];
                 float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
                 if ((q.w >> 12) != 0u) {
                     int32_t t1;
@@ -829,7 +838,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 #pragma unroll 1
                 for (int m = 0; m < 2; ++m) {
                     if (!((fmask >> m) & 1u)) continue;
-                    const uint4 q = stage[slot0 + m * 32];
+                    const uint4 q = stage[m ? sidx[1] : sidx[0]];
                     if ((q.w >> 12) == 0u) continue;
                     ++npass;
                     const uint64_t trial = r.trial_begin + chunk_first64 + (q.w & 4095u);
