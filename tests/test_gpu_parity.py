@@ -144,6 +144,29 @@ def test_whole_day_batch_fp32_vs_fp64(engine, oracle, ring1, ring5, tmp_path):
     assert np.array_equal(a5.counts, b5.counts) and np.array_equal(a5.first_conflict, b5.first_conflict)
 
 
+def test_config3_scale_1e10_trials(engine, tracks, ring1, ring5):
+    """BASELINE config 3 at full size on one GPU: 1.0e10 trials against one track, 1 km and 5 km
+    rings.  Size-independent properties: the count over the whole range equals the sum over two
+    disjoint halves (what two ranks would compute), every record is reproduced, ids are unique."""
+    n = 101_010_102                      # x 99 drones = 1.0000000098e10 trials
+    for ring in (ring1, ring5):
+        full = engine.simulate(tracks[:1], ring, seed=SEED, trial_count=n, precision=capi.MIXED,
+                               record_capacity=1 << 18)
+        lo = engine.simulate(tracks[:1], ring, seed=SEED, trial_begin=0, trial_count=n // 2, precision=capi.MIXED,
+                             record_capacity=1 << 18)
+        hi = engine.simulate(tracks[:1], ring, seed=SEED, trial_begin=n // 2, trial_count=n - n // 2,
+                             precision=capi.MIXED, record_capacity=1 << 18)
+        assert full.stats["trials"] == 99 * n >= 10**10
+        assert np.array_equal(full.counts, lo.counts + hi.counts)
+        assert not full.overflow and len(full.records) == full.hits
+        ids = lambda r: set(zip(r.records["drone"].tolist(), r.records["trial"].tolist()))
+        assert ids(full) == ids(lo) | ids(hi) and len(ids(full)) == full.hits
+        assert full.stats["tests_evaluated"] == lo.stats["tests_evaluated"] + hi.stats["tests_evaluated"]
+        print("ring %s: %d hits in %.3e trials, p = %.3e, screen %.1f ms" % (
+            "1km" if ring is ring1 else "5km", full.hits, 99 * n, full.hits / (99 * n), full.stats["ms_trials"]))
+    assert full.hits >= 0
+
+
 def test_fp32_mode_is_close(engine, tracks, ring1):
     n = 200000
     a = engine.simulate(tracks[:1], ring1, seed=SEED, trial_count=n, precision=capi.FP64)
