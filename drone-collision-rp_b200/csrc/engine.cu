@@ -446,8 +446,7 @@ static ScreenCfg make_cfg()
 }
 // [0] is the production configuration; the others exist for the tuning sweep
 // (tools/profile_target.py with DCRP_SCREEN_CFG=n) and cost nothing unless selected.
-static ScreenCfg g_cfgs[] = {make_cfg<4, 512, 2>(), make_cfg<2, 256, 4>(), make_cfg<4, 256, 4>(),
-                             make_cfg<2, 512, 2>(), make_cfg<4, 128, 8>()};
+static ScreenCfg g_cfgs[] = {make_cfg<4, 512, 2>(), make_cfg<2, 256, 4>()};
 static ScreenCfg& screen_cfg()
 {
     static const int sel = std::getenv("DCRP_SCREEN_CFG") ? std::atoi(std::getenv("DCRP_SCREEN_CFG")) : 0;
@@ -461,14 +460,15 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
 {
     ScreenCfg& c = screen_cfg();
     const int v = r.replay ? 1 : 0;
+    const void* kern = c.kern[v];
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2)) +
                         (c.rounds > 2 ? (size_t)screen_chunk() * 2 : 0);          // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
-        cudaError_t ce = cudaFuncSetAttribute(c.kern[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], c.kern[v], c.block, smem);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], kern, c.block, smem);
         if (ce != cudaSuccess) return ce;
         if (e->screen_occ[v] < 1) e->screen_occ[v] = 1;
         e->screen_smem[v] = smem;
@@ -482,7 +482,7 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     ScenarioDev sd = e->sd;
     RunDev rr = r;
     void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &tile_steps, (void*)&stagger_ns, (void*)&dbg};
-    cudaError_t ce = cudaLaunchKernel(c.kern[v], dim3(grid), dim3((unsigned)c.block), args, smem, st);
+    cudaError_t ce = cudaLaunchKernel(kern, dim3(grid), dim3((unsigned)c.block), args, smem, st);
     ++e->launches; ++e->launches_this_run;
     return ce != cudaSuccess ? ce : cudaGetLastError();
 }
@@ -917,7 +917,7 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
 extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms_out)
 {
     if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
-    if (which < 0 || which > 15) return fail(DCRP_ERR_INVALID, "which must be 0..15");
+    if (which < 0 || which > 16) return fail(DCRP_ERR_INVALID, "which must be 0..16");
     CU(cudaSetDevice(e->device));
     const int threads = 256;
     int blocks = e->prop.multiProcessorCount * 8;
@@ -947,7 +947,8 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
             case 12: k_peak_variant2<12><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 13: k_peak_scan2d<13><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 14: k_peak_scan2d<14><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            default: k_peak_scan2d<15><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 15: k_peak_scan2d<15><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            default: k_peak_scan2d<16><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
         }
         ++e->launches;
         CU(cudaGetLastError());

@@ -1394,10 +1394,14 @@ __global__ void __launch_bounds__(256) k_peak_variant2(float* out, int iters, fl
     out[blockIdx.x * blockDim.x + threadIdx.x] = r + fi.x;
 }
 
+__constant__ float2 c_peak_xy[512];
+
 // Scan-loop variants at the real kernel's shape (1 packed pair per thread, 2-D incremental):
 //   V=13 samples from shared memory, duplicated layout (x,x,y,y): LDS.128, plain pair operands
 //   V=14 samples from shared memory, 16 B layout: LDS.64 + scalar-broadcast operand form (production)
 //   V=15 no shared memory: loop-invariant operand (pure pipe rate of the 6-op mix)
+//   V=16 samples from __constant__ memory through the uniform datapath (LDCU + UR broadcast operand);
+//        needs CTA-uniform loop bounds, which the per-warp sorted bins of k_screen2 cannot offer
 template <int V>
 __global__ void __launch_bounds__(256) k_peak_scan2d(float* out, int iters, float s0, float a0)
 {
@@ -1417,6 +1421,9 @@ __global__ void __launch_bounds__(256) k_peak_scan2d(float* out, int iters, floa
                 cx = pk2(c.x, c.y); cy = pk2(c.z, c.w);
             } else if (V == 14) {
                 const float2 c = *reinterpret_cast<const float2*>(&tile[k]);
+                cx = pk2(c.x, c.x); cy = pk2(c.y, c.y);
+            } else if (V == 16) {
+                const float2 c = c_peak_xy[k];
                 cx = pk2(c.x, c.x); cy = pk2(c.y, c.y);
             } else {
                 cx = cinv; cy = cinv;
