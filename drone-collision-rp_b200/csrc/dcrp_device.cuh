@@ -130,6 +130,7 @@ struct RunDev {
     double*   trial_min;
     int32_t   decide_fp32;               // screen kernel: 1 = DCRP_PRECISION_FP32
     int32_t   substep;                   // 1 = DCRP_FLAG_SUBSTEP: interpolated separation between samples
+    uint32_t  rk[20];                    // Philox round keys of `seed` (philox_round_keys)
 };
 
 }  // namespace dcrp

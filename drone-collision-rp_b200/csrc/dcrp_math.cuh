@@ -75,6 +75,32 @@ DCRP_HD U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     return o;
 }
 
+// Same function with the ten round keys (k0 + r*W0, k1 + r*W1) precomputed by the caller: in a kernel
+// they sit in the parameter constant bank and feed the XORs directly, so the per-round key bump
+// (two integer adds per round per trial) disappears.  rk[2r] = k0_r, rk[2r+1] = k1_r.
+DCRP_HD U4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+        uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    U4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+inline void philox_round_keys(uint64_t seed, uint32_t (&rk)[20])
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
 // counter = (trial_lo, trial_hi, drone, track), key = seed
 DCRP_HD U4 trial_words(uint64_t seed, uint64_t trial, uint32_t drone, uint32_t track)
 {

@@ -434,26 +434,26 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 // One instantiation of the screen kernel: R rounds x 2 trials per thread per item, BLOCK threads,
 // at least MINB CTAs per SM.
 struct ScreenCfg {
-    int rounds, block, minb;
+    int rounds, block, minb, np;
     const void* kern[2];          // [REPLAY]
 };
-template <int R, int BLOCK, int MINB>
+template <int R, int BLOCK, int MINB, int NP>
 static ScreenCfg make_cfg()
 {
-    ScreenCfg c{R, BLOCK, MINB, {(const void*)k_screen2<R, BLOCK, false, MINB>,
-                                 (const void*)k_screen2<R, BLOCK, true, MINB>}};
+    ScreenCfg c{R, BLOCK, MINB, NP, {(const void*)k_screen2<R, BLOCK, false, MINB, NP>,
+                                     (const void*)k_screen2<R, BLOCK, true, MINB, NP>}};
     return c;
 }
 // [0] is the production configuration; the others exist for the tuning sweep
 // (tools/profile_target.py with DCRP_SCREEN_CFG=n) and cost nothing unless selected.
-static ScreenCfg g_cfgs[] = {make_cfg<4, 512, 2>(), make_cfg<2, 256, 4>()};
+static ScreenCfg g_cfgs[] = {make_cfg<2, 384, 2, 2>(), make_cfg<4, 512, 2, 1>(), make_cfg<2, 512, 2, 2>(), make_cfg<2, 256, 3, 2>()};
 static ScreenCfg& screen_cfg()
 {
     static const int sel = std::getenv("DCRP_SCREEN_CFG") ? std::atoi(std::getenv("DCRP_SCREEN_CFG")) : 0;
     const int n = (int)(sizeof g_cfgs / sizeof g_cfgs[0]);
     return g_cfgs[(sel >= 0 && sel < n) ? sel : 0];
 }
-static uint64_t screen_chunk() { const ScreenCfg& c = screen_cfg(); return (uint64_t)2 * c.rounds * c.block; }
+static uint64_t screen_chunk() { const ScreenCfg& c = screen_cfg(); return (uint64_t)2 * c.np * c.rounds * c.block; }
 
 static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                                   cudaStream_t st)
@@ -464,7 +464,7 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2)) +
-                        (c.rounds > 2 ? (size_t)screen_chunk() * 2 : 0);          // order[] of the K > 4 variants
+                        (2 * c.np * c.rounds > 4 ? (size_t)screen_chunk() * 2 : 0);   // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ce != cudaSuccess) return ce;
@@ -547,6 +547,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     r.stats = small_stats(e);
     r.decide_fp32 = (run->precision == DCRP_PRECISION_FP32) ? 1 : 0;
     r.substep = (run->flags & DCRP_FLAG_SUBSTEP) ? 1 : 0;
+    philox_round_keys(run->seed, r.rk);
     if (run->flags & DCRP_FLAG_PER_TRIAL) {
         const size_t n = n_pairs * (size_t)run->trial_count;
         CU(e->d_trial_hit.need(n ? n : 1));
@@ -917,7 +918,7 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
 extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms_out)
 {
     if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
-    if (which < 0 || which > 16) return fail(DCRP_ERR_INVALID, "which must be 0..16");
+    if (which < 0 || which > 24) return fail(DCRP_ERR_INVALID, "which must be 0..24");
     CU(cudaSetDevice(e->device));
     const int threads = 256;
     int blocks = e->prop.multiProcessorCount * 8;
@@ -948,7 +949,17 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
             case 13: k_peak_scan2d<13><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 14: k_peak_scan2d<14><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
             case 15: k_peak_scan2d<15><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            default: k_peak_scan2d<16><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+            case 16: k_peak_scan2d<16><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
+#define DCRP_L1(F, S, N) k_peak_level1<F, S, N><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f, 1e-3f)
+            case 17: DCRP_L1(0, 1, 1); break;
+            case 18: DCRP_L1(0, 1, 2); break;
+            case 19: DCRP_L1(0, 1, 4); break;
+            case 20: DCRP_L1(1, 0, 1); break;
+            case 21: DCRP_L1(1, 1, 1); break;
+            case 22: DCRP_L1(1, 1, 2); break;
+            case 23: DCRP_L1(1, 1, 4); break;
+            default: DCRP_L1(1, 0, 2); break;
+#undef DCRP_L1
         }
         ++e->launches;
         CU(cudaGetLastError());
@@ -967,6 +978,10 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
     else if (which == 8) flops = lanes * iters * 8.0 * 16.0;                            // FMNMX3 count, not flops
     else if (which == 10) flops = lanes * iters * 8.0 * 4.0 / 10.0;                     // Philox4x32-10 calls
     else if (which == 12) flops = lanes * iters * 8.0 * 2.0 * 2.0 * 2.0 * 11.0;         // 2 steps x 2 pairs x 2 tests
+    else if (which >= 17) {
+        static const int np_of[] = {1, 2, 4, 1, 1, 2, 4, 2};
+        flops = lanes * iters * 512.0 * 2.0 * np_of[which - 17] * 11.0;                  // 512 steps x 2 NP tests
+    }
     else if (which >= 13) flops = lanes * iters * 512.0 * 2.0 * 11.0;                   // 512 steps x 2 tests
     else                 flops = lanes * iters * 8.0 * 4.0 * 2.0 * 11.0;   // 2 tests per packed pair, 11 flop each
     *tflops = flops / ((double)best * 1e-3) * 1e-12;

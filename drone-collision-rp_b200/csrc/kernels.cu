@@ -602,12 +602,13 @@ __device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const Track
 
 constexpr int SCREEN_TAB = 128;     // kink-table entries kept in shared memory per CTA
 
-template <int R, int BLOCK, bool REPLAY, int MINB>
+template <int R, int BLOCK, bool REPLAY, int MINB, int NP>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int tile_steps,
           uint32_t stagger_ns, uint32_t dbg)
 {
-    constexpr int K = 2 * R;                 // trials per thread per item
+    constexpr int TR = 2 * NP;               // trials per thread per round (NP packed pairs)
+    constexpr int K = TR * R;                // trials per thread per item
     constexpr int CH = K * BLOCK;
     constexpr int NW = BLOCK / 32;
     static_assert(R % 2 == 0, "rounds come in complementary (long, short) pairs");
@@ -710,8 +711,9 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                         t1st = draw_t1st(h, takeoff_t);
                         w1[mm] = h ^ 0x9e3779b9u; w2[mm] = h * 40503u; w3[mm] = h + 0x7f4a7c15u;
                     } else {
-                        const U4 w = trial_words(r.seed, r.trial_begin + chunk_first64 + local,
-                                                 r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a);
+                        const uint64_t trial = r.trial_begin + chunk_first64 + local;
+                        const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32),
+                                                      r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a, r.rk);
                         t1st = draw_t1st(w.x, takeoff_t);
                         w1[mm] = w.y; w2[mm] = w.z; w3[mm] = w.w;
                     }
@@ -757,16 +759,16 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         // ---------------- R rounds: set up one packed pair, scan it
 #pragma unroll 1
         for (int rd = 0; rd < R; ++rd) {
-            // 64-trial bins in ascending t1st order; rounds (2q, 2q+1) take bins b and its mirror
+            // bins of 32*TR trials in ascending t1st order; rounds (2q, 2q+1) take bin b and its mirror
             const int q2 = rd >> 1;
             const int bin = (rd & 1) ? (q2 * 2 * NW + 2 * NW - 1 - warp) : (q2 * 2 * NW + warp);
-            const uint32_t slot0 = (uint32_t)(bin * 64 + lane);
-            float bxs[2], bys[2], sxs[2], sys[2];  // level 1 needs the horizontal ray only
+            const uint32_t slot0 = (uint32_t)(bin * (32 * TR) + lane);
+            float bxs[TR], bys[TR], sxs[TR], sys[TR];  // level 1 needs the horizontal ray only
             int tmin = INT_MAX;
             uint32_t fmask = 0;                   // bit m: trial m must go to level 2 regardless of the scan
-            uint32_t sidx[2];                     // where this lane's two trials sit in stage[]
+            uint32_t sidx[TR];                    // where this lane's trials sit in stage[]
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < TR; ++m) {
                 sidx[m] = IND ? (uint32_t)order[slot0 + m * 32] : slot0 + m * 32;
                 const uint4 q = stage[sidx[m]];
                 float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
@@ -793,13 +795,19 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 }
                 bxs[m] = bx; bys[m] = by; sxs[m] = sx; sys[m] = sy;
             }
-            const f2_t BX = pk2(bxs[0], bxs[1]), BY = pk2(bys[0], bys[1]);
-            const f2_t SX[1] = {pk2(sxs[0], sxs[1])}, SY[1] = {pk2(sys[0], sys[1])};
+            f2_t BX[NP], BY[NP], SX[NP], SY[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                BX[p] = pk2(bxs[2 * p], bxs[2 * p + 1]); BY[p] = pk2(bys[2 * p], bys[2 * p + 1]);
+                SX[p] = pk2(sxs[2 * p], sxs[2 * p + 1]); SY[p] = pk2(sys[2 * p], sys[2 * p + 1]);
+            }
             // sub-step mode also needs the kink sample (index t1st-1), the first end of the first segment
             const int imin = __reduce_min_sync(0xffffffffu, tmin) - (r.substep ? 1 : 0);
-            if (imin < VL) acc_is += (uint32_t)(VL - imin) * 2u;
+            if (imin < VL) acc_is += (uint32_t)(VL - imin) * (uint32_t)TR;
 
-            float mn[2] = {3.0e38f, 3.0e38f};       // running min of the horizontal d2 of trial 0 / 1
+            float mn[TR];                           // running min of the horizontal d2 of each trial
+#pragma unroll
+            for (int m = 0; m < TR; ++m) mn[m] = 3.0e38f;
             for (int tl = 0; tl < n_tiles; ++tl) {
                 const int buf = single ? 0 : (tl & 1);
                 if (!single) {
@@ -825,20 +833,25 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 if (lo < hi) {
                     const float lof = (float)lo;
                     const f2_t lo2 = pk2(lof, lof);
-                    f2_t PX[1] = {ffma2(lo2, SX[0], BX)}, PY[1] = {ffma2(lo2, SY[0], BY)};
-                    scan_tile_xy<1>(tiles + (size_t)buf * tile_steps, t0, lo, hi, PX, PY, SX, SY, mn);
+                    f2_t PX[NP], PY[NP];
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) { PX[p] = ffma2(lo2, SX[p], BX[p]); PY[p] = ffma2(lo2, SY[p], BY[p]); }
+                    scan_tile_xy<NP>(tiles + (size_t)buf * tile_steps, t0, lo, hi, PX, PY, SX, SY, mn);
                 }
             }
 
             // ---------------- rare path (~1e-3 of trials): LEVEL 2, the full 3-D fp32 distance of the
             // flagged trial alone; what survives goes to the fp64 confirm (LEVEL 3)
-            if (mn[0] < thr) fmask |= 1u;
-            if (mn[1] < thr) fmask |= 2u;
+#pragma unroll
+            for (int m = 0; m < TR; ++m) if (mn[m] < thr) fmask |= 1u << m;
             if (fmask) {
 #pragma unroll 1
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < TR; ++m) {
                     if (!((fmask >> m) & 1u)) continue;
-                    const uint4 q = stage[m ? sidx[1] : sidx[0]];
+                    uint32_t si = sidx[0];
+#pragma unroll
+                    for (int mm = 1; mm < TR; ++mm) si = (m == mm) ? sidx[mm] : si;
+                    const uint4 q = stage[si];
                     if ((q.w >> 12) == 0u) continue;
                     ++npass;
                     const uint64_t trial = r.trial_begin + chunk_first64 + (q.w & 4095u);
@@ -1437,6 +1450,57 @@ __global__ void __launch_bounds__(256) k_peak_scan2d(float* out, int iters, floa
         }
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = mn0 + mn1;
+}
+
+// Level-1 loop shapes, parameterised: FORM 0 = Euclidean (FMUL2 + FFMA2 + min), 1 = Chebyshev (FMNMX of
+// |dx|, |dy| + predicate); SRC 0 = loop-invariant operand (registers only), 1 = one broadcast LDS.128 per
+// two indices (the production tile layout); NP packed pairs per thread.  512 indices per outer iteration.
+template <int FORM, int SRC, int NP>
+__global__ void __launch_bounds__(256) k_peak_level1(float* out, int iters, float s0, float a0, float thr1)
+{
+    __shared__ float4 tile[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tile[i] = make_float4(a0 + i, a0 - i, a0 + i + 0.5f, a0 - i - 0.5f);
+    __syncthreads();
+    f2_t PX[NP], PY[NP], SX[NP], SY[NP];
+    float mn[2 * NP];
+    bool near[2 * NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        PX[p] = pk2(threadIdx.x * 0.5f + p, threadIdx.x * 0.25f - p); PY[p] = pk2(threadIdx.x * 1.5f, -1.f * threadIdx.x + p);
+        SX[p] = pk2(s0 + p, s0 + 1.f); SY[p] = pk2(s0 - 1.f, s0 + 2.f + p);
+        mn[2 * p] = mn[2 * p + 1] = 3.0e38f; near[2 * p] = near[2 * p + 1] = false;
+    }
+    const float4 cinv = make_float4(a0, a0 + 1.f, a0 + 2.f, a0 + 3.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 2
+        for (int k = 0; k < 256; ++k) {
+            const float4 c = SRC ? tile[k] : cinv;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float vx = h ? c.z : c.x, vy = h ? c.w : c.y;
+                const f2_t cx = pk2(vx, vx), cy = pk2(vy, vy);
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    if (FORM == 0) {
+                        const f2_t dx = fadd2(PX[p], cx), dy = fadd2(PY[p], cy);
+                        const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
+                        mn[2 * p] = fminf(mn[2 * p], d2.x); mn[2 * p + 1] = fminf(mn[2 * p + 1], d2.y);
+                    } else {
+                        const float2 dx = up2(fadd2(PX[p], cx)), dy = up2(fadd2(PY[p], cy));
+                        near[2 * p] |= fmaxf(fabsf(dx.x), fabsf(dy.x)) < thr1;
+                        near[2 * p + 1] |= fmaxf(fabsf(dx.y), fabsf(dy.y)) < thr1;
+                    }
+                    PX[p] = fadd2(PX[p], SX[p]); PY[p] = fadd2(PY[p], SY[p]);
+                }
+            }
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int p = 0; p < 2 * NP; ++p) r += FORM == 0 ? mn[p] : (near[p] ? 1.f : 0.f);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { const float2 a = up2(PX[p]), b = up2(PY[p]); r += a.x + a.y + b.x + b.y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 // Clears a run's output arena: words [0, first_off) = 0 (counters, stats, counts),
