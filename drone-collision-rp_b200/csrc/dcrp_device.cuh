@@ -56,6 +56,11 @@ struct ScenarioDev {
     double*         s1sub_first_time;// [n_pairs] its conflict time (segment index + t)
     double2*        kink;            // [n_pairs*t_max] (box.xmin - p1x[L], box.ymin - p1y[L]): fast screen set-up
     float2*         p1f;             // [n_drones*t_max] stage-1 path relative to the origin, rounded once to fp32
+    // reachability (DCRP_FLAG_REACH_CULL): feasible stage-2 index range [lo, hi) per (pair, t1st), the pairs
+    // with any feasible index (or a stage-1 conflict), and the guaranteed tests of the others
+    int2*           reach;           // [n_pairs*t_max] entry t1st-1; empty = (INT32_MAX, 0)
+    uint32_t*       alive;           // [n_pairs] pair ids, n_alive of them valid (unordered)
+    unsigned long long* reach_tot;   // [0] n_alive  [1] sum over dead pairs of (n_steps - takeoff_t)
     int32_t n_tracks, n_drones, t_max, n_steps_max;
     int32_t n_sm;                    // SMs of the device (CTA stagger)
     double ox, oy, oz;               // fp32 origin
@@ -109,7 +114,8 @@ struct AllPairsDev {
     uint32_t  tracks_per_chunk, n_tchunks;
 };
 
-enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_LEVEL2, ST_COUNT };
+enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_LEVEL2,
+                ST_CULLED_TRIALS, ST_CULLED_TESTS, ST_DEAD_TESTS, ST_PROCESSED_TESTS, ST_COUNT };
 
 struct RunDev {
     uint64_t seed, trial_begin, trial_count;   // the whole run: trials [begin, begin+count) per pair
@@ -131,6 +137,7 @@ struct RunDev {
     int32_t   decide_fp32;               // screen kernel: 1 = DCRP_PRECISION_FP32
     int32_t   substep;                   // 1 = DCRP_FLAG_SUBSTEP: interpolated separation between samples
     uint32_t  rk[20];                    // Philox round keys of `seed` (philox_round_keys)
+    int32_t   cull;                      // 1 = DCRP_FLAG_REACH_CULL
 };
 
 }  // namespace dcrp

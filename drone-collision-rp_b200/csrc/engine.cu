@@ -109,6 +109,7 @@ struct dcrp_engine {
     DevBuf d_scn;
     PinnedBuf h_scn;
     DevBuf d_p1x, d_p1y, d_s1fh, d_s1pm, d_kink, d_p1f, d_s1sub_pm, d_s1sub_fs, d_s1sub_ft;
+    DevBuf d_reach, d_alive, d_reach_tot;
     bool prepare_timed = false;
 
     // run
@@ -131,6 +132,7 @@ struct dcrp_engine {
     int screen_occ[2] = {0, 0};
     int ap_occ = 0;
     bool allpairs_run = false;
+    bool run_cull = false;         // the last run used DCRP_FLAG_REACH_CULL
     uint64_t ap_rays = 0;
     DevBuf d_ap_hist, d_ap_rank, d_ap_rayA, d_ap_rayB, d_ap_meta, d_ap_l2;
     DevBuf d_scratch;    // peak kernels / draws / trajectories
@@ -199,7 +201,7 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
                       &e->d_s1sub_ft, &e->d_out, &e->d_records,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
                       &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
-                      &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2};
+                      &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2, &e->d_reach, &e->d_alive, &e->d_reach_tot};
     for (DevBuf* b : bufs) b->release();
     e->h_scn.release();
     e->h_out.release();
@@ -398,6 +400,9 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     CU(e->d_s1sub_fs.need(sizeof(int32_t) * n_pairs));
     CU(e->d_s1sub_ft.need(sizeof(double) * n_pairs));
     CU(e->d_p1f.need(sizeof(float2) * (size_t)n_drones * (size_t)t_max));
+    CU(e->d_reach.need(sizeof(int2) * n_pairs * (size_t)t_max));
+    CU(e->d_alive.need(sizeof(uint32_t) * n_pairs));
+    CU(e->d_reach_tot.need(sizeof(unsigned long long) * 2));
     CU(cudaEventRecord(e->ev_a, st));
     CU(cudaMemcpyAsync(e->d_scn.p, hb, scn_bytes, cudaMemcpyHostToDevice, st));
     e->h2d_scenario = scn_bytes;
@@ -419,7 +424,15 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.s1sub_first_seg = e->d_s1sub_fs.as<int32_t>();
     s.s1sub_first_time = e->d_s1sub_ft.as<double>();
 
+    s.reach = e->d_reach.as<int2>();
+    s.alive = e->d_alive.as<uint32_t>();
+    s.reach_tot = e->d_reach_tot.as<unsigned long long>();
+
     k_stage1<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(s);
+    ++e->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(e->d_reach_tot.p, 0, sizeof(unsigned long long) * 2, st));
+    k_reach<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s);      // one warp per pair
     ++e->launches;
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev_b, st));   // no host sync here: runs queue behind it on the same stream
@@ -463,7 +476,7 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     const void* kern = c.kern[v];
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
-                        (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2)) +
+                        (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2) + sizeof(int2)) +
                         (2 * c.np * c.rounds > 4 ? (size_t)screen_chunk() * 2 : 0);   // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
         cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -548,6 +561,10 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     r.decide_fp32 = (run->precision == DCRP_PRECISION_FP32) ? 1 : 0;
     r.substep = (run->flags & DCRP_FLAG_SUBSTEP) ? 1 : 0;
     philox_round_keys(run->seed, r.rk);
+    // exact reach culling: screen kernel only, sample mode only, no per-trial outputs
+    r.cull = ((run->flags & DCRP_FLAG_REACH_CULL) && run->precision == DCRP_PRECISION_MIXED && !r.substep &&
+              !(run->flags & DCRP_FLAG_PER_TRIAL) && !run->replay) ? 1 : 0;
+    e->run_cull = r.cull != 0;
     if (run->flags & DCRP_FLAG_PER_TRIAL) {
         const size_t n = n_pairs * (size_t)run->trial_count;
         CU(e->d_trial_hit.need(n ? n : 1));
@@ -686,6 +703,13 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     if (e->allpairs_run) {            // every ray against every track: the scan kernel counted them
         o.tests_evaluated = stats[ST_EVALUATED];
         o.tests_shared = 0;
+        o.drone_steps = 0;
+    }
+    if (!e->allpairs_run && e->run_cull) {
+        // processed pairs: every test decided (computed or culled); cleared pairs: the guaranteed minimum
+        o.trials_culled = stats[ST_CULLED_TRIALS];
+        o.tests_culled = stats[ST_CULLED_TESTS] + stats[ST_DEAD_TESTS];
+        o.tests_evaluated = stats[ST_PROCESSED_TESTS] - stats[ST_SHARED] + stats[ST_DEAD_TESTS];
         o.drone_steps = 0;
     }
     o.candidates = stats[ST_CANDIDATES];

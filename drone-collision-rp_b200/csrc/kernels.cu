@@ -252,6 +252,54 @@ __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
     s.s1sub_first_time[pair] = stime;
 }
 
+// Reachability table (DCRP_FLAG_REACH_CULL), once per scenario, one warp per (track, drone), one lane
+// per kink index.  After the kink the drone's step is (sin b * vf, cos b * vf, sin p * vf) with
+// vf = v_straight - coef * pitch and pitch in [0, pi/2] (Drone.cpp:218-227), so vf lies between
+// v_straight and v_ascend whatever the target: at index i > L the drone is horizontally within
+// (i - L) * vmax of the kink and between start_alt and start_alt + (i - L) * vmax in altitude,
+// vmax = max(|v_straight|, |v_ascend|).  Sample i can only be a conflict if the aircraft sample i is
+// inside that set grown by R (+ a 1 cm margin that dwarfs the fp64 rounding of the accumulated path).
+// [lo, hi) is the hull of the feasible indices of (pair, t1st); pairs with a stage-1 conflict keep
+// the full range (their trials must be drawn to know which of them kink after the conflict).
+__global__ void __launch_bounds__(128) k_reach(const ScenarioDev s)
+{
+    const int pair = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= s.n_tracks * s.n_drones) return;
+    const int a = pair / s.n_drones, j = pair - a * s.n_drones;
+    const TrackDev t = s.tracks[a];
+    const bool keep_all = s.s1_first_hit[pair] != INT_MAX;
+    const double vmax = fmax(fabs(s.v_straight), fabs(s.v_ascend)) * (1.0 + 1e-9);
+    const double rm = s.radius + 0.01;
+    bool any = false;
+    for (int t1 = lane + 1; t1 <= s.t_max; t1 += 32) {
+        int lo = INT_MAX, hi = 0;
+        if (t1 <= t.takeoff_t) {
+            if (keep_all) {
+                lo = t1; hi = t.n_steps;
+            } else {
+                const int last = t1 - 1;
+                const double kx = s.p1x[(size_t)j * s.t_max + last], ky = s.p1y[(size_t)j * s.t_max + last];
+                for (int i = t1; i < t.n_steps; ++i) {
+                    const double dx = s.ax[t.off + i] - kx, dy = s.ay[t.off + i] - ky;
+                    const double az = s.az[t.off + i];
+                    const double reach = (double)(i - last) * vmax + rm;
+                    const bool feas = (dx * dx + dy * dy < reach * reach) && (az > s.start_alt - rm) &&
+                                      (az < s.start_alt + reach);
+                    if (feas) { lo = min(lo, i); hi = i + 1; }
+                }
+            }
+            if (hi > lo) any = true;
+        }
+        s.reach[(size_t)pair * s.t_max + (t1 - 1)] = make_int2(lo, hi);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) {
+        if (any) s.alive[atomicAdd(&s.reach_tot[0], 1ull)] = (uint32_t)pair;
+        else     atomicAdd(&s.reach_tot[1], (unsigned long long)(t.n_steps - t.takeoff_t));
+    }
+}
+
 // =========================================================================
 // the exact trial (fp64, reference order of operations)
 // =========================================================================
@@ -621,10 +669,11 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     uint64_t* bars  = reinterpret_cast<uint64_t*>(hist + 80);
     double2*  tabk  = reinterpret_cast<double2*>(bars + 2);            // this pair's kink tables
     float2*   tabp  = reinterpret_cast<float2*>(tabk + SCREEN_TAB);
+    int2*     tabr  = reinterpret_cast<int2*>(tabp + SCREEN_TAB);          // this pair's reach ranges
     // K > 4: the draws stay where phase A wrote them (stage[local]) and only a 2-byte permutation is
     // sorted (order[sorted slot] = local), so phase A never holds more than one trial's words in registers
     constexpr bool IND = (K > 4);
-    uint16_t* order = reinterpret_cast<uint16_t*>(tabp + SCREEN_TAB);
+    uint16_t* order = reinterpret_cast<uint16_t*>(tabr + SCREEN_TAB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -633,16 +682,29 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 
     uint32_t phase0 = 0, phase1 = 0;
     int loaded_track = -1;
-    uint32_t acc_t1 = 0, acc_is = 0, ncand = 0, npass = 0;   // partial sums (flushed before overflow)
+    uint32_t acc_t1 = 0, acc_is = 0, acc_cull = 0, ncand = 0, npass = 0;   // partial sums (flushed before overflow)
 
     // CTAs co-resident on an SM all start at once and, doing identical work per item, would stay in
     // phase (all in the integer/set-up phases together, then all fighting for the FMA pipe).  Offset
     // the k-th CTA of an SM by k/occupancy of an item so that scans overlap the other phases.
     if (stagger_ns) __nanosleep(stagger_ns * (blockIdx.x / s.n_sm));
 
+    // Reach culling: only the pairs of the scenario's alive list get items; the others are accounted
+    // for here, once per launch, with the tests every one of their trials is guaranteed to hold.
+    if (r.cull) {
+        const unsigned long long n_alive = s.reach_tot[0];
+        n_items = (uint32_t)(n_alive * chunks_per_pair);
+        if (blockIdx.x == 0 && tid == 0) {
+            const unsigned long long dead = (unsigned long long)(s.n_tracks * s.n_drones) - n_alive;
+            atomicAdd(&r.stats[ST_CULLED_TRIALS], dead * r.slice_count);
+            atomicAdd(&r.stats[ST_DEAD_TESTS], s.reach_tot[1] * r.slice_count);
+        }
+    }
+
     // (pair, chunk) of the item, carried along the grid-stride loop: divisions only when a pair ends
-    int pair = (int)(blockIdx.x / chunks_per_pair);
-    uint32_t c = blockIdx.x - (uint32_t)pair * chunks_per_pair;
+    int po = (int)(blockIdx.x / chunks_per_pair);          // ordinal in the list of pairs that get work
+    uint32_t c = blockIdx.x - (uint32_t)po * chunks_per_pair;
+    int pair = (r.cull && blockIdx.x < n_items) ? (int)s.alive[po] : po;
     int a = pair / s.n_drones, j = pair - a * s.n_drones;
     int tab_pair = -1;
     const bool tab_smem = s.t_max <= SCREEN_TAB;
@@ -663,11 +725,13 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         }
         const float2* __restrict__ gtrk = s.trkxy + (size_t)__ldg(&tk->off_xy);
 
-        if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {        // rare: keep the 32-bit partial sums exact
+        if (acc_t1 > 0x40000000u || acc_is > 0x40000000u || acc_cull > 0x40000000u) {   // rare: keep the 32-bit partial sums exact
             atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
             atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
-            acc_t1 = acc_is = 0;
+            atomicAdd(&r.stats[ST_CULLED_TESTS], (unsigned long long)acc_cull);
+            acc_t1 = acc_is = acc_cull = 0;
         }
+        if (r.cull && tid == 0) atomicAdd(&r.stats[ST_PROCESSED_TESTS], (unsigned long long)n_valid * (unsigned long long)VL);
 
         // ---------------- phase A: draws + histogram over t1st buckets
         for (int h = tid; h < 80; h += BLOCK) hist[h] = 0;
@@ -677,6 +741,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             if (tid < takeoff_t) {
                 tabk[tid] = __ldg(&s.kink[(size_t)pair * s.t_max + tid]);
                 tabp[tid] = __ldg(&s.p1f[(size_t)j * s.t_max + tid]);
+                if (r.cull) tabr[tid] = __ldg(&s.reach[(size_t)pair * s.t_max + tid]);
             }
             tab_pair = pair;
         }
@@ -767,6 +832,31 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             int tmin = INT_MAX;
             uint32_t fmask = 0;                   // bit m: trial m must go to level 2 regardless of the scan
             uint32_t sidx[TR];                    // where this lane's trials sit in stage[]
+            // Reach culling: the union [clo, chi) of the feasible index ranges of this warp's trials (the
+            // bins are sorted by t1st, so it is tight); an empty union means none of them can collide
+            // whatever their targets, and the round needs neither ray set-up nor scan.
+            int clo = 0, chi = INT_MAX;
+            if (r.cull) {
+                int lo_l = INT_MAX, hi_l = 0;
+                uint32_t t1s = 0, nv = 0;
+#pragma unroll
+                for (int m = 0; m < TR; ++m) {
+                    const uint32_t si = IND ? (uint32_t)order[slot0 + m * 32] : slot0 + m * 32;
+                    const uint32_t t1 = stage[si].w >> 12;
+                    if (t1 != 0u) {
+                        const int2 rg = tab_smem ? tabr[t1 - 1] : __ldg(&s.reach[(size_t)pair * s.t_max + (t1 - 1)]);
+                        lo_l = min(lo_l, rg.x); hi_l = max(hi_l, rg.y);
+                        t1s += t1; ++nv;
+                    }
+                }
+                clo = __reduce_min_sync(0xffffffffu, lo_l);
+                chi = __reduce_max_sync(0xffffffffu, hi_l);
+                if (chi <= clo) {
+                    acc_t1 += t1s;
+                    acc_cull += nv * (uint32_t)VL - t1s;
+                    continue;
+                }
+            }
 #pragma unroll
             for (int m = 0; m < TR; ++m) {
                 sidx[m] = IND ? (uint32_t)order[slot0 + m * 32] : slot0 + m * 32;
@@ -792,6 +882,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     }
                     tmin = min(tmin, t1);
                     acc_t1 += (uint32_t)t1;
+                    if (r.cull) acc_cull += (uint32_t)((VL - t1) - max(0, min(VL, chi) - max(clo, t1)));
                 }
                 bxs[m] = bx; bys[m] = by; sxs[m] = sx; sys[m] = sy;
             }
@@ -802,8 +893,9 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 SX[p] = pk2(sxs[2 * p], sxs[2 * p + 1]); SY[p] = pk2(sys[2 * p], sys[2 * p + 1]);
             }
             // sub-step mode also needs the kink sample (index t1st-1), the first end of the first segment
-            const int imin = __reduce_min_sync(0xffffffffu, tmin) - (r.substep ? 1 : 0);
-            if (imin < VL) acc_is += (uint32_t)(VL - imin) * (uint32_t)TR;
+            const int imin = max(__reduce_min_sync(0xffffffffu, tmin) - (r.substep ? 1 : 0), clo);
+            const int iend = min(VL, chi);
+            if (imin < iend) acc_is += (uint32_t)(iend - imin) * (uint32_t)TR;
 
             float mn[TR];                           // running min of the horizontal d2 of each trial
 #pragma unroll
@@ -824,7 +916,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     else          { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
                 }
                 const int t0 = tl * tile_steps;
-                const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(VL, t0 + tile_steps);   // dbg 1: no scan
+                const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(iend, t0 + tile_steps);   // dbg 1: no scan
                 // LEVEL 1, horizontal screen: d2xy(i) = |Pxy(i) - Axy(i)|^2 <= d2(i), so a trial whose
                 // horizontal separation never drops below R + margin cannot collide at any index, whatever
                 // the altitudes.  6 packed ops per pair-step instead of 9.  P(lo) = B + lo*S is re-based
@@ -875,13 +967,15 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         if (c >= chunks_per_pair) {
             const uint32_t adv = c / chunks_per_pair;
             c -= adv * chunks_per_pair;
-            pair += (int)adv;
+            po += (int)adv;
+            pair = (r.cull && (uint32_t)po * chunks_per_pair + c < n_items) ? (int)s.alive[po] : po;
             a = pair / s.n_drones;
             j = pair - a * s.n_drones;
         }
     }
     flush_stats(r, 0, acc_t1, acc_is, 0, 0);
-    const unsigned long long nc = warp_sum_u64(ncand), np = warp_sum_u64(npass);
+    const unsigned long long nc = warp_sum_u64(ncand), np = warp_sum_u64(npass), ncl = warp_sum_u64(acc_cull);
+    if (lane == 0 && ncl) atomicAdd(&r.stats[ST_CULLED_TESTS], ncl);
     if (lane == 0 && nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
     if (lane == 0 && np) atomicAdd(&r.stats[ST_LEVEL2], np);
 }

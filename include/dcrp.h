@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DCRP_ABI_VERSION 2
+#define DCRP_ABI_VERSION 3
 
 /* status codes */
 #define DCRP_OK               0
@@ -51,6 +51,18 @@ extern "C" {
                                      min over t of the separation on a segment < R.  first_hit is then
                                      the first SEGMENT in conflict, first_time the conflict time in
                                      index units, min_dist the continuous minimum.  FP64 / MIXED only. */
+#define DCRP_FLAG_REACH_CULL  4u  /* OPT-IN, MIXED mode, sample mode only.  Exact culling by reachability:
+                                     after the kink the drone moves at most max(v_straight, v_ascend) per
+                                     index horizontally and only upwards, so sample i of a trial with kink
+                                     index L can only be a conflict if the aircraft sample i lies within
+                                     (i - L) * vmax + R of the kink and in the altitude band the drone can
+                                     have reached.  Indices outside the feasible range [lo, hi) of a
+                                     (track, drone, t1st), computed once per scenario, are decided by that
+                                     bound and not scanned; a (track, drone) pair with no feasible index
+                                     for any t1st and no stage-1 conflict gets no trial work at all (its
+                                     count is 0 by the bound, no draws are made).  Counts, colliding trial
+                                     ids and records are identical to the un-culled run; stats report what
+                                     was computed (tests_issued) and what the bound decided (tests_culled). */
 
 typedef struct dcrp_engine dcrp_engine;
 
@@ -143,6 +155,11 @@ typedef struct dcrp_stats {
     float    ms_device_total;  /* first to last kernel, CUDA events on the engine stream              */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    /* DCRP_FLAG_REACH_CULL only (0 otherwise) */
+    uint64_t trials_culled;    /* trials of (track, drone) pairs the reach bound cleared as a whole: no
+                                  draws made; tests_evaluated counts their GUARANTEED minimum of
+                                  n_steps - takeoff_t stage-2 tests each, tests_shared nothing            */
+    uint64_t tests_culled;     /* stage-2 tests decided by the reach bound instead of being computed     */
 } dcrp_stats;
 
 /* Result buffers (host, caller-owned).  counts is required; the rest optional. */

@@ -11,13 +11,14 @@ import drone_collision_rp_b200 as pk
 from drone_collision_rp_b200 import capi, scenario
 
 prec = capi.FP64 if "--fp64" in sys.argv else capi.MIXED
+flags = capi.FLAG_REACH_CULL if "--cull" in sys.argv else 0
 eng = capi.Engine(0)
 tracks, _ = scenario.synthetic_tracks(tempfile.mkdtemp(), 1)
 ring = scenario.load_ring(pk.RING_5KM)
 eng.upload(tracks, ring)
 sizes = [101011] * 5 + ([] if "--short" in sys.argv else [10_000_000])
 for i, n in enumerate(sizes):
-    run = eng.run_async(seed=20170630, trial_begin=i * 101011, trial_count=n, precision=prec)
+    run = eng.run_async(seed=20170630, trial_begin=i * 101011, trial_count=n, precision=prec, flags=flags)
     r = eng.fetch(run)
     print(i, "trials %.3e ms_trials %.4f  tests/s %.4e  TFLOP11 %.2f  issued/eval %.4f hits %d cand %d level2 %d" % (
         r.stats["trials"], r.stats["ms_trials"], r.stats["tests_evaluated"] / (r.stats["ms_trials"] * 1e-3),
