@@ -99,7 +99,7 @@ DCRP_SYMBOLS = [
 DCRP_HOST_SYMBOLS = [
     "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_ring_write",
     "dcrph_aircraft_load",
-    "dcrph_ring_row", "dcrph_monte_carlo", "dcrph_monte_carlo_batch", "dcrph_write_block",
+    "dcrph_ring_row", "dcrph_monte_carlo", "dcrph_monte_carlo_batch", "dcrph_set_run_flags", "dcrph_write_block",
 ]
 
 
@@ -159,6 +159,8 @@ def host():
         H.dcrph_monte_carlo_batch.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_int,
                                               C.c_uint64, C.c_double, C.c_double, C.c_uint64, C.c_int, C.c_char_p,
                                               C.POINTER(C.c_uint64)]
+        H.dcrph_set_run_flags.argtypes = [C.c_uint32]
+        H.dcrph_set_run_flags.restype = None
         H.dcrph_write_block.argtypes = [C.c_char_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_long]
         _host = H
     return _host

@@ -133,6 +133,7 @@ struct dcrp_engine {
     int ap_occ = 0;
     bool allpairs_run = false;
     bool run_cull = false;         // the last run used DCRP_FLAG_REACH_CULL
+    bool reach_ready = false;      // k_reach has run for the current scenario
     uint64_t ap_rays = 0;
     DevBuf d_ap_hist, d_ap_rank, d_ap_rayA, d_ap_rayB, d_ap_meta, d_ap_l2;
     DevBuf d_scratch;    // peak kernels / draws / trajectories
@@ -428,13 +429,10 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.alive = e->d_alive.as<uint32_t>();
     s.reach_tot = e->d_reach_tot.as<unsigned long long>();
 
-    k_stage1<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(s);
+    k_stage1<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s);            // one warp per pair
     ++e->launches;
     CU(cudaGetLastError());
-    CU(cudaMemsetAsync(e->d_reach_tot.p, 0, sizeof(unsigned long long) * 2, st));
-    k_reach<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s);      // one warp per pair
-    ++e->launches;
-    CU(cudaGetLastError());
+    e->reach_ready = false;        // the reach table is built by the first run that asks for it
     CU(cudaEventRecord(e->ev_b, st));   // no host sync here: runs queue behind it on the same stream
     e->prepare_timed = false;
     e->sd = s;
@@ -565,6 +563,13 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     r.cull = ((run->flags & DCRP_FLAG_REACH_CULL) && run->precision == DCRP_PRECISION_MIXED && !r.substep &&
               !(run->flags & DCRP_FLAG_PER_TRIAL) && !run->replay) ? 1 : 0;
     e->run_cull = r.cull != 0;
+    if (r.cull && !e->reach_ready) {
+        CU(cudaMemsetAsync(e->d_reach_tot.p, 0, sizeof(unsigned long long) * 2, st));
+        k_reach<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s);      // one warp per pair, once per scenario
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+        e->reach_ready = true;
+    }
     if (run->flags & DCRP_FLAG_PER_TRIAL) {
         const size_t n = n_pairs * (size_t)run->trial_count;
         CU(e->d_trial_hit.need(n ? n : 1));

@@ -205,51 +205,89 @@ __device__ __forceinline__ void scan_tile_xy(const float2* __restrict__ txy, int
 // =========================================================================
 // stage 1: once per scenario
 // =========================================================================
-// One thread per (track, drone).  Walks the stage-1 indices 0..t_max-1 of the
-// drone (Drone.cpp:120-126: constant step (sin h0 * v, cos h0 * v), z = start
-// altitude), tests each against the track sample of the same index
-// (Drone.cpp:253-262) and keeps the first hit and the running minimum.
+// One WARP per (track, drone), one lane per stage-1 index (32 indices per pass).  The drone's stage-1
+// path is the reference's running sum (Drone.cpp:120-126: x[i] = x[i-1] + sin(h0)*v, two roundings per
+// step, z = start altitude), so lane l re-runs the l additions from the pass's first position -- the same
+// additions in the same order, hence the same bits -- instead of waiting for its neighbour.  Each index
+// is tested against the track sample of the same index (Drone.cpp:253-262); first hit and running
+// minimum come from a ballot and a warp prefix-min (min is order-independent).
+__device__ __forceinline__ double warp_prefix_min(double v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v = fmin(v, u);
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
 {
-    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (pair >= s.n_tracks * s.n_drones) return;
     const int a = pair / s.n_drones, j = pair - a * s.n_drones;
     const TrackDev t = s.tracks[a];
     const double4 d = s.drones[j];
-    double x = d.x, y = d.y;
-    double mn = INFINITY;
-    int first = INT_MAX;
-    // sub-step extension: the same walk over the stage-1 SEGMENTS i-1 -> i
-    double px = 0, py = 0, pz = 0, smn = INFINITY, stime = -1.0;
-    int sfirst = INT_MAX;
-    for (int i = 0; i < s.t_max; ++i) {
-        if (i > 0) { x = DADD(x, d.z); y = DADD(y, d.w); }
-        s.s1sub_prefmin[(size_t)pair * s.t_max + i] = smn;          // segments with index < i
-        if (i < t.n_steps) {
-            const double cx = DSUB(x, s.ax[t.off + i]), cy = DSUB(y, s.ay[t.off + i]),
-                         cz = DSUB(s.start_alt, s.az[t.off + i]);
-            if (i > 0) {
-                const SegOut sg = seg_closest(px, py, pz, cx, cy, cz, s.radius2);
-                if (sg.d2 < smn) smn = sg.d2;
-                if (sg.tc >= 0.0 && sfirst == INT_MAX) { sfirst = i - 1; stime = DADD((double)(i - 1), sg.tc); }
+    double bx = d.x, by = d.y;                   // position at the first index of the pass
+    double mn_carry = INFINITY, smn_carry = INFINITY;
+    int first = INT_MAX, sfirst = INT_MAX;
+    double stime = -1.0;
+    double qx = 0, qy = 0, qz = 0;               // relative position at the sample before the pass
+    for (int c0 = 0; c0 < s.t_max; c0 += 32) {
+        const int i = c0 + lane;
+        double x = bx, y = by;
+        for (int k = 0; k < lane; ++k) { x = DADD(x, d.z); y = DADD(y, d.w); }
+        bx = __shfl_sync(0xffffffffu, DADD(x, d.z), 31);
+        by = __shfl_sync(0xffffffffu, DADD(y, d.w), 31);
+        const bool in_t = i < s.t_max;
+        const bool on = in_t && i < t.n_steps;   // all i < t_max: all-pairs rays may kink later than this track's takeoff_t
+        double cx = 0, cy = 0, cz = 0, d2 = INFINITY;
+        if (on) {
+            const double ax = s.ax[t.off + i], ay = s.ay[t.off + i], az = s.az[t.off + i];
+            cx = DSUB(x, ax); cy = DSUB(y, ay); cz = DSUB(s.start_alt, az);
+            d2 = sep2(x, y, s.start_alt, ax, ay, az);
+        }
+        const uint32_t hm = __ballot_sync(0xffffffffu, on && d2 < s.thr_d2);
+        if (first == INT_MAX && hm) first = c0 + __ffs((int)hm) - 1;
+        const double pm = fmin(warp_prefix_min(d2, lane), mn_carry);
+        mn_carry = __shfl_sync(0xffffffffu, pm, 31);
+
+        // sub-step extension: segment i-1 -> i belongs to lane i; s1sub_prefmin[i] covers every segment
+        // that ends at a sample <= i, i.e. all the segments a trial kinking at sample i flies in stage 1
+        double px = __shfl_up_sync(0xffffffffu, cx, 1), py = __shfl_up_sync(0xffffffffu, cy, 1),
+               pz = __shfl_up_sync(0xffffffffu, cz, 1);
+        if (lane == 0) { px = qx; py = qy; pz = qz; }
+        double sd2 = INFINITY, tc = -1.0;
+        if (on && i > 0) {
+            const SegOut sg = seg_closest(px, py, pz, cx, cy, cz, s.radius2);
+            sd2 = sg.d2; tc = sg.tc;
+        }
+        const uint32_t sm = __ballot_sync(0xffffffffu, tc >= 0.0);
+        if (sfirst == INT_MAX && sm) {
+            const int src = __ffs((int)sm) - 1;
+            sfirst = c0 + src - 1;
+            stime = DADD((double)sfirst, __shfl_sync(0xffffffffu, tc, src));
+        }
+        const double spm = fmin(warp_prefix_min(sd2, lane), smn_carry);
+        smn_carry = __shfl_sync(0xffffffffu, spm, 31);
+        qx = __shfl_sync(0xffffffffu, cx, 31); qy = __shfl_sync(0xffffffffu, cy, 31); qz = __shfl_sync(0xffffffffu, cz, 31);
+
+        if (in_t) {
+            if (a == 0) {
+                s.p1x[(size_t)j * s.t_max + i] = x; s.p1y[(size_t)j * s.t_max + i] = y;
+                s.p1f[(size_t)j * s.t_max + i] = make_float2((float)DSUB(x, s.ox), (float)DSUB(y, s.oy));
             }
-            px = cx; py = cy; pz = cz;
+            s.kink[(size_t)pair * s.t_max + i] = make_double2(DSUB(t.box[0], x), DSUB(t.box[2], y));
+            s.s1_prefmin[(size_t)pair * s.t_max + i] = pm;
+            s.s1sub_prefmin[(size_t)pair * s.t_max + i] = spm;
         }
-        if (a == 0) {
-            s.p1x[(size_t)j * s.t_max + i] = x; s.p1y[(size_t)j * s.t_max + i] = y;
-            s.p1f[(size_t)j * s.t_max + i] = make_float2((float)DSUB(x, s.ox), (float)DSUB(y, s.oy));
-        }
-        s.kink[(size_t)pair * s.t_max + i] = make_double2(DSUB(t.box[0], x), DSUB(t.box[2], y));
-        if (i < t.n_steps) {      // all i < t_max: all-pairs rays may kink later than this track's takeoff_t
-            const double d2 = sep2(x, y, s.start_alt, s.ax[t.off + i], s.ay[t.off + i], s.az[t.off + i]);
-            if (d2 < mn) mn = d2;
-            if (d2 < s.thr_d2 && first == INT_MAX) first = i;
-        }
-        s.s1_prefmin[(size_t)pair * s.t_max + i] = mn;
     }
-    s.s1_first_hit[pair] = first;
-    s.s1sub_first_seg[pair] = sfirst;
-    s.s1sub_first_time[pair] = stime;
+    if (lane == 0) {
+        s.s1_first_hit[pair] = first;
+        s.s1sub_first_seg[pair] = sfirst;
+        s.s1sub_first_time[pair] = stime;
+    }
 }
 
 // Reachability table (DCRP_FLAG_REACH_CULL), once per scenario, one warp per (track, drone), one lane

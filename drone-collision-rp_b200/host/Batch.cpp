@@ -13,7 +13,7 @@ namespace dcrp_host {
 BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols, int aircraft_begin,
                               int aircraft_end, const std::string& drone_csv, int drone_cols, int drone_total,
                               uint64_t number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
-                              int precision, const std::string& out_dir)
+                              int precision, const std::string& out_dir, uint32_t run_flags)
 {
     BatchResult out;
     auto fail = [&](int status, const std::string& what) { out.status = status; out.error = what; return out; };
@@ -61,6 +61,7 @@ BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols
     model.drone_radius = drone_radius;
     dcrp_run run{};
     run.seed = seed; run.trial_begin = 0; run.trial_count = number_runs; run.precision = precision;
+    run.flags = run_flags;
     run.record_capacity = 1u << 20;
     run.track_id_base = (uint32_t)aircraft_begin;       // same Philox ids as Drone::Simulation(i, j)
     std::vector<uint64_t> counts((size_t)n_tracks * drone_total, 0);

@@ -50,6 +50,7 @@ class Drone {
     // ---- extensions (not in the reference)
     void SetSeed(uint64_t seed) { seed_ = seed; }
     void SetPrecision(int precision) { precision_ = precision; }     // DCRP_PRECISION_*
+    void SetRunFlags(uint32_t flags) { run_flags_ = flags; }         // DCRP_FLAG_* (e.g. DCRP_FLAG_REACH_CULL)
     void SetOutputDirectory(const std::string& dir) { out_dir_ = dir; }
     void Simulation64(uint64_t number_runs, double* total_collisions);   // number_runs is int in Drone.h:74
     uint64_t ExactCollisions() const { return exact_total_; }        // the double counter loses integers past 2^53
@@ -73,6 +74,7 @@ class Drone {
 
     uint64_t seed_ = 20170630ull;
     int precision_ = DCRP_PRECISION_MIXED;
+    uint32_t run_flags_ = 0;
     std::string out_dir_ = "Drone_Collisions";
     std::map<std::pair<int, int>, uint64_t> next_trial_;   // trials already consumed per (aircraft, drone)
     uint64_t exact_total_ = 0;

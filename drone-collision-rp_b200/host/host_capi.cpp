@@ -74,6 +74,11 @@ extern "C" int dcrph_ring_row(const char* path, int total_cols, int drone_index,
     return 0;
 }
 
+// Process-wide DCRP_FLAG_* applied by dcrph_monte_carlo / dcrph_monte_carlo_batch (their signatures mirror
+// the reference's main() and carry no flag word).
+static uint32_t g_host_run_flags = 0;
+extern "C" void dcrph_set_run_flags(uint32_t flags) { g_host_run_flags = flags; }
+
 extern "C" int dcrph_monte_carlo(const char* aircraft_csv, int aircraft_cols, int aircraft_begin,
                                  int aircraft_end, const char* drone_csv, int drone_cols, int drone_total,
                                  int number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
@@ -85,6 +90,7 @@ extern "C" int dcrph_monte_carlo(const char* aircraft_csv, int aircraft_cols, in
     Drone drone;
     drone.SetSeed(seed);
     drone.SetPrecision(precision);
+    drone.SetRunFlags(g_host_run_flags);
     if (out_dir && *out_dir) drone.SetOutputDirectory(out_dir);
     aircraft.Set_Parameters_and_Data(aircraft_csv, aircraft_cols);            // Monte_Carlo.cpp:26
     if (!aircraft.ok()) { g_host_err = aircraft.last_error(); return -6; }
@@ -118,7 +124,8 @@ extern "C" int dcrph_monte_carlo_batch(const char* aircraft_csv, int aircraft_co
     if (!aircraft_csv || !drone_csv || !total_collisions) { g_host_err = "NULL argument"; return -1; }
     const dcrp_host::BatchResult r = dcrp_host::monte_carlo_batch(
         aircraft_csv, aircraft_cols, aircraft_begin, aircraft_end, drone_csv, drone_cols, drone_total, number_runs,
-        aircraft_radius, drone_radius, seed, precision, (out_dir && *out_dir) ? out_dir : "Drone_Collisions");
+        aircraft_radius, drone_radius, seed, precision, (out_dir && *out_dir) ? out_dir : "Drone_Collisions",
+        g_host_run_flags);
     if (r.status != 0) { g_host_err = r.error; return r.status; }
     *total_collisions = r.collisions;
     return 0;

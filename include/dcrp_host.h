@@ -54,6 +54,10 @@ int dcrph_monte_carlo_batch(const char* aircraft_csv, int aircraft_cols, int air
                             double aircraft_radius, double drone_radius, uint64_t seed, int precision,
                             const char* out_dir, uint64_t* total_collisions);
 
+/* DCRP_FLAG_* (dcrp.h) applied to every later dcrph_monte_carlo / dcrph_monte_carlo_batch call of the
+ * process, e.g. DCRP_FLAG_REACH_CULL.  Extension: the reference's main() has no such knob. */
+void dcrph_set_run_flags(uint32_t flags);
+
 /* Drone::Output's row format (Drone.cpp:237-241) applied to one trajectory;
  * appends to `path`. */
 int dcrph_write_block(const char* path, const double* x, const double* y, const double* z, int n,

@@ -82,6 +82,21 @@ def test_batch_driver_equals_per_pair_loop(day, tmp_path):
     for a in (1, 2, 3):
         name = "Drone_coords_%d.csv" % a
         assert open(loop_dir / name).read() == open(batch_dir / name).read()
+    # the same two drivers with DCRP_FLAG_REACH_CULL: same count, byte-identical files
+    cull_dir = tmp_path / "cull"
+    cull_dir.mkdir()
+    capi.host().dcrph_set_run_flags(capi.FLAG_REACH_CULL)
+    try:
+        ctotal = C.c_uint64(0)
+        capi._hcheck(capi.host().dcrph_monte_carlo_batch(csv.encode(), 22, 1, 4, pk.RING_1KM.encode(), 4, 99, 8000,
+                                                         3.5, 0.19, SEED, capi.MIXED, str(cull_dir).encode(),
+                                                         C.byref(ctotal)))
+    finally:
+        capi.host().dcrph_set_run_flags(0)
+    assert ctotal.value == exact.value
+    for a in (1, 2, 3):
+        name = "Drone_coords_%d.csv" % a
+        assert open(loop_dir / name).read() == open(cull_dir / name).read()
 
 
 def test_monte_carlo_binary_as_the_reference_is_run(engine, tracks, ring1, tmp_path):
@@ -105,6 +120,9 @@ def test_monte_carlo_binary_as_the_reference_is_run(engine, tracks, ring1, tmp_p
     r3 = subprocess.run([pk.MONTE_CARLO, "--synthetic", "6", "--batch"], cwd=tmp_path, capture_output=True, text=True,
                         timeout=300)
     assert r3.returncode == 0 and int(re.search(r"Number of collisions: (\d+)", r3.stdout).group(1)) == batch.hits
+    r4 = subprocess.run([pk.MONTE_CARLO, "--synthetic", "6", "--cull"], cwd=tmp_path, capture_output=True, text=True,
+                        timeout=300)
+    assert r4.returncode == 0 and int(re.search(r"Number of collisions: (\d+)", r4.stdout).group(1)) == batch.hits
 
 
 def test_out_of_band_runway_is_an_error_not_stale_values(engine, tracks, ring1, tmp_path):

@@ -88,3 +88,27 @@ def test_substep_flag_errors(engine, tracks, ring1):
     with pytest.raises(capi.DcrpError) as e:
         engine.simulate(tracks[:1], ring1, trial_count=10, precision=capi.FP32, flags=capi.FLAG_SUBSTEP)
     assert e.value.status == capi.ERR_INVALID
+
+
+def test_substep_minimum_on_the_last_stage1_segment(engine, oracle, tracks, ring1):
+    """The closest approach falls INSIDE a first-stage segment (aircraft parked 10 m beside the middle of
+    segment 5 -> 6 of the drone's straight run): every kink index, in particular the kink at sample 6
+    whose last stage-1 segment that is, must report the same interpolated minimum as the oracle."""
+    t = tracks[0]
+    j = 23
+    x0, y0, h0 = ring1[j]
+    n = len(t["x"])
+    box = capi.target_box(t["y"][0], 0.0)
+    ux, uy = np.sin(h0), np.cos(h0)
+    px = x0 + ux * 19.0 * 5.5 + uy * 10.0          # abeam of the middle of segment 5 -> 6
+    py = y0 + uy * 19.0 * 5.5 - ux * 10.0
+    trk = {"x": np.full(n, px), "y": np.full(n, py), "z": np.full(n, 100.0), "takeoff_t": t["takeoff_t"], "box": box}
+    runs = 4000
+    res = engine.simulate([trk], ring1[j:j + 1], seed=11, trial_count=runs, precision=capi.FP64,
+                          flags=capi.FLAG_PER_TRIAL | capi.FLAG_SUBSTEP, drone_id_base=j)
+    draws = engine.dump_draws(0, 0, 11, 0, runs, drone_id_base=j)
+    hit, first, ftime, mind = oracle.run_trials_substep(trk, ring1[j], draws)
+    assert np.array_equal(res.per_trial["hit"][0], hit)
+    assert np.abs(res.per_trial["min_dist"][0] - mind).max() < 1e-9
+    late = draws["t1st"] >= 7
+    assert late.any() and np.abs(mind[late] - 10.0).max() < 1e-6

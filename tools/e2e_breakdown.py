@@ -1,0 +1,29 @@
+"""Fixed cost of one dcrp_simulate call (host buffers in/out): wall time vs the device-side event times."""
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import drone_collision_rp_b200 as pk
+from drone_collision_rp_b200 import capi, scenario
+
+eng = capi.Engine(0)
+tracks, _ = scenario.synthetic_tracks(tempfile.mkdtemp(), 1)
+ring = scenario.load_ring(pk.RING_5KM)
+scn = capi.Scenario(tracks, ring)
+for flags, name in ((0, "plain"), (capi.FLAG_REACH_CULL, "cull")):
+    for n in (1, 101011):
+        walls, st = [], None
+        for k in range(30):
+            t0 = time.perf_counter()
+            r = eng.simulate(scn, seed=1, trial_begin=k * n, trial_count=n, precision=capi.MIXED, record_capacity=4096,
+                             flags=flags)
+            walls.append(time.perf_counter() - t0)
+            st = r.stats
+        walls = sorted(walls[5:])
+        print("%-5s n=%-7d wall median %.1f us  min %.1f us | prepare %.1f trials %.1f confirm %.1f device_total %.1f us" % (
+            name, n, 1e6 * walls[len(walls) // 2], 1e6 * walls[0], 1e3 * st["ms_prepare"], 1e3 * st["ms_trials"],
+            1e3 * st["ms_confirm"], 1e3 * st["ms_device_total"]))
+eng.close()
