@@ -501,21 +501,87 @@ __global__ void __launch_bounds__(EXB) k_exact(const ScenarioDev s, const RunDev
     flush_stats(r, ev, sh, ev, st, hits);
 }
 
-// fp64 confirmation of the screen's candidates.  The list length lives on the
-// device (no host round trip between screen and confirm): grid-stride over it.
+// The exact trial, one WARP per trial: lane l takes the stage-2 indices c0 + l of every 32-index pass.
+// The positions are the reference's running sums (Drone.cpp:224-230), so each lane re-runs the l + 1
+// additions from the pass's base position -- the same additions in the same order as exact_trial, hence
+// the same bits -- while the 32 track samples of the pass arrive in one coalesced load instead of 32
+// dependent ones.  First conflict = lowest index (ballot), minimum = warp min: both order-independent.
+__device__ __forceinline__ TrialOut exact_any_warp(const ScenarioDev& s, const RunDev& r, int pair, int j,
+                                                   int n_steps, const double* __restrict__ ax,
+                                                   const double* __restrict__ ay, const double* __restrict__ az,
+                                                   const Draw& d, int lane)
+{
+    const int last = d.t1st - 1;
+    const double xl = s.p1x[(size_t)j * s.t_max + last];
+    const double yl = s.p1y[(size_t)j * s.t_max + last];
+    const Ray64 ray = stage2_ray(xl, yl, s.start_alt, d.tx, d.ty, d.tz, s.v_straight, s.v_ascend);
+    int first = -1;
+    double ftime = -1.0, mn;
+    if (r.substep) {
+        const int s1 = s.s1sub_first_seg[pair];
+        if (s1 < last) { first = s1; ftime = s.s1sub_first_time[pair]; }
+        mn = s.s1sub_prefmin[(size_t)pair * s.t_max + last];
+    } else {
+        const int s1 = s.s1_first_hit[pair];
+        if (s1 <= last) { first = s1; ftime = (double)s1; }
+        mn = s.s1_prefmin[(size_t)pair * s.t_max + last];
+    }
+    double bx = ray.x, by = ray.y, bz = ray.z;                         // position at index c0 - 1
+    double qx = DSUB(bx, ax[last]), qy = DSUB(by, ay[last]), qz = DSUB(bz, az[last]);   // sub-step: previous sample
+    for (int c0 = d.t1st; c0 < n_steps; c0 += 32) {
+        const int i = c0 + lane;
+        double x = bx, y = by, z = bz;
+        for (int k = 0; k <= lane; ++k) { x = DADD(x, ray.sx); y = DADD(y, ray.sy); z = DADD(z, ray.sz); }
+        bx = __shfl_sync(0xffffffffu, x, 31); by = __shfl_sync(0xffffffffu, y, 31); bz = __shfl_sync(0xffffffffu, z, 31);
+        const bool on = i < n_steps;
+        double cx = 0, cy = 0, cz = 0, d2 = INFINITY, tc = -1.0;
+        if (on) { cx = DSUB(x, ax[i]); cy = DSUB(y, ay[i]); cz = DSUB(z, az[i]); }
+        if (r.substep) {
+            double px = __shfl_up_sync(0xffffffffu, cx, 1), py = __shfl_up_sync(0xffffffffu, cy, 1),
+                   pz = __shfl_up_sync(0xffffffffu, cz, 1);
+            if (lane == 0) { px = qx; py = qy; pz = qz; }
+            if (on) {
+                const SegOut sg = seg_closest(px, py, pz, cx, cy, cz, s.radius2);
+                d2 = sg.d2; tc = sg.tc;
+            }
+            qx = __shfl_sync(0xffffffffu, cx, 31); qy = __shfl_sync(0xffffffffu, cy, 31); qz = __shfl_sync(0xffffffffu, cz, 31);
+            const uint32_t hm = __ballot_sync(0xffffffffu, tc >= 0.0);
+            if (first < 0 && hm) {
+                const int src = __ffs((int)hm) - 1;
+                first = c0 + src - 1;                                           // the segment's first sample
+                ftime = DADD((double)first, __shfl_sync(0xffffffffu, tc, src));
+            }
+        } else {
+            if (on) d2 = sep2(x, y, z, ax[i], ay[i], az[i]);
+            const uint32_t hm = __ballot_sync(0xffffffffu, d2 < s.thr_d2);     // Drone.cpp:260, sqrt folded into thr_d2
+            if (first < 0 && hm) { first = c0 + __ffs((int)hm) - 1; ftime = (double)first; }
+        }
+        mn = fmin(mn, d2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    TrialOut out;
+    out.first = first; out.min_d2 = mn; out.first_time = r.substep ? ftime : (double)first;
+    return out;
+}
+
+// fp64 confirmation of the screen's candidates, one warp per candidate.  The list length lives on the
+// device (no host round trip between screen and confirm): warp-stride over it.
 __global__ void __launch_bounds__(128) k_confirm_all(const ScenarioDev s, const RunDev r)
 {
     const uint32_t n_cand = min(*r.cand_count, r.cand_cap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     unsigned long long hits = 0;
-    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_cand; idx += gridDim.x * blockDim.x) {
+    for (uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n_cand; idx += n_warps) {
         const Candidate cd = r.cands[idx];
         const int pair = (int)cd.pair;
         const int a = pair / s.n_drones, j = pair - a * s.n_drones;
         const TrackDev t = s.tracks[a];
         const uint64_t local = cd.trial - r.trial_begin;
         const Draw d = fetch_draw(s, r, t, pair, a, j, local);
-        const TrialOut o = exact_any(s, r, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
-        if (o.first >= 0) {
+        const TrialOut o = exact_any_warp(s, r, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d, lane);
+        if (o.first >= 0 && lane == 0) {
             ++hits;
             publish_hit(s, r, pair, a, j, cd.trial, d, o);
         }
