@@ -188,7 +188,7 @@ __device__ __forceinline__ void scan_tile_xy(const float2* __restrict__ txy, int
     }
     const int npair = (hi - i) >> 1;
     const float4* __restrict__ q4 = reinterpret_cast<const float4*>(txy + (i - t0));
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < npair; ++k) {
         const float4 c = q4[k];
         DCRP_STEP(c.x, c.y)
