@@ -940,6 +940,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             // bins are sorted by t1st, so it is tight); an empty union means none of them can collide
             // whatever their targets, and the round needs neither ray set-up nor scan.
             int clo = 0, chi = INT_MAX;
+            bool skip_round = false;
             if (r.cull) {
                 int lo_l = INT_MAX, hi_l = 0;
                 uint32_t t1s = 0, nv = 0;
@@ -958,7 +959,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 if (chi <= clo) {
                     acc_t1 += t1s;
                     acc_cull += nv * (uint32_t)VL - t1s;
-                    continue;
+                    if (single) continue;
+                    skip_round = true;      // multi-tile tracks: the tile hand-over below is CTA-wide, walk it idle
                 }
             }
 #pragma unroll
@@ -966,7 +968,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                 sidx[m] = IND ? (uint32_t)order[slot0 + m * 32] : slot0 + m * 32;
                 const uint4 q = stage[sidx[m]];
                 float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
-                if ((q.w >> 12) != 0u) {
+                if ((q.w >> 12) != 0u && !skip_round) {
                     int32_t t1;
                     if (REPLAY) {
                         const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);

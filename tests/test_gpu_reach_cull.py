@@ -114,3 +114,46 @@ def test_cull_flag_is_ignored_where_it_does_not_apply(engine, tracks, ring1):
         assert np.array_equal(a.counts, b.counts)
         assert b.stats["trials_culled"] == 0 and b.stats["tests_culled"] == 0
         assert b.stats["tests_evaluated"] == a.stats["tests_evaluated"]
+
+
+def test_cull_long_tracks_and_large_takeoff(engine, oracle, tracks, ring1):
+    """Multi-tile tracks (700 and 1300 samples: the culled range is clamped tile by tile) and a takeoff
+    time of 200 (> the 128-entry shared-memory tables: the reach ranges then come from global memory),
+    with a shadowing aircraft whose conflicts sit deep in the second tile."""
+    from test_gpu_allpairs import _extend
+
+    n, t_ref = 1300, 200
+    drones = ring1[40:60]
+    box0 = capi.target_box(tracks[0]["y"][0], 0.0)
+    dummy = {"x": np.zeros(n), "y": np.zeros(n), "z": np.zeros(n), "takeoff_t": t_ref}
+    star = oracle.draws(21, 5, 1, 10, 2, t_ref, box0)[0]
+    sx, sy, sz = oracle.trajectory(dummy, drones[10], star)
+    i = np.arange(n)
+    loiter = {"x": sx + 0.5 * np.maximum(0, 900 - i), "y": sy.copy(), "z": sz.copy(), "takeoff_t": t_ref,
+              "box": box0, "n_steps": n}
+    cases = [_extend(tracks[0], 129), _extend(tracks[1], 700, wobble=30.0), loiter]
+    runs = 3000
+    ref = engine.simulate(cases, drones, seed=21, trial_count=runs, precision=capi.FP64)
+    plain = engine.simulate(cases, drones, seed=21, trial_count=runs, precision=capi.MIXED)
+    cull = engine.simulate(cases, drones, seed=21, trial_count=runs, precision=capi.MIXED, flags=capi.FLAG_REACH_CULL)
+    _same(plain, cull)
+    assert np.array_equal(ref.counts, cull.counts)
+    assert cull.hits > 0 and cull.records["first_hit"].max() > 512
+    assert cull.stats["tests_issued"] < plain.stats["tests_issued"]
+    got = cull.counts.reshape(len(cases), len(drones))
+    h, _ = oracle.run_philox(loiter, box0, drones[10], 21, 10, 2, 0, runs)
+    assert h == int(got[2, 10]) > 0
+
+
+def test_cull_sliced_and_repeated_runs(engine, tracks, ring5):
+    """The reach table is built once per scenario and reused by later runs; trial ranges compose."""
+    eng = engine
+    eng.upload(tracks[:2], ring5)
+    tot = None
+    for k in range(3):
+        run = eng.run_async(seed=SEED, trial_begin=k * 50000, trial_count=50000, precision=capi.MIXED,
+                            flags=capi.FLAG_REACH_CULL)
+        r = eng.fetch(run)
+        tot = r.counts.copy() if tot is None else tot + r.counts
+    whole = eng.simulate(tracks[:2], ring5, seed=SEED, trial_count=150000, precision=capi.MIXED)
+    assert np.array_equal(tot, whole.counts)
