@@ -168,8 +168,11 @@ def cpu_port_run(track, ring, runs_per_drone, nproc):
 
     t0 = time.time()
     jobs = [(track, ring, list(range(w, 99, nproc)), runs_per_drone) for w in range(nproc)]
-    with mp.get_context("fork").Pool(nproc) as pool:
-        hits = sum(pool.map(_port_worker, jobs))
+    if nproc == 1:                      # in-process: no fork from a process that holds a CUDA context
+        hits = _port_worker(jobs[0])
+    else:
+        with mp.get_context("fork").Pool(nproc) as pool:
+            hits = sum(pool.map(_port_worker, jobs))
     secs = time.time() - t0
     trials = 99 * runs_per_drone
     return {"trials": trials, "tests": trials * track["n_steps"], "seconds": secs, "hits": hits, "kind": "port"}
@@ -404,13 +407,14 @@ def engine_arm(args):
 
     # ---- the same workload with the OPT-IN exact reach culling (DCRP_FLAG_REACH_CULL): identical counts,
     # ids and records (tests/test_gpu_reach_cull.py); reported beside the headline, never as it
-    rc_ms, rc_tests, rc_issued, rc_culled_trials, rc_trials, rc_hits = 0.0, 0, 0, 0, 0, 0
+    rc_ms, rc_tests, rc_issued, rc_culled_trials, rc_trials, rc_hits, rc_eval = 0.0, 0, 0, 0, 0, 0, 0
     for s in range(args.warmup + args.steps):
         run = eng.run_async(seed=SEED, trial_begin=(s * world + rank) * n, trial_count=n, precision=capi.MIXED,
                             flags=capi.FLAG_REACH_CULL, stream=sh)
         r = eng.fetch(run)
         if s >= args.warmup:
-            rc_ms += r.stats["ms_device_total"]; rc_tests += r.stats["tests_evaluated"]
+            rc_ms += r.stats["ms_device_total"]; rc_tests += r.stats["tests_evaluated"] + r.stats["tests_culled"]
+            rc_eval += r.stats["tests_evaluated"]
             rc_issued += r.stats["tests_issued"]; rc_culled_trials += r.stats["trials_culled"]
             rc_trials += r.stats["trials"]; rc_hits += r.stats["hits"]
         eng.flush_l2(sh)
@@ -424,21 +428,22 @@ def engine_arm(args):
         dt = time.perf_counter() - t0
         if s >= args.warmup:
             rc_e2e_secs += dt
-            rc_e2e_tests += r.stats["tests_evaluated"]
+            rc_e2e_tests += r.stats["tests_evaluated"] + r.stats["tests_culled"]
     if world > 1:
         mx = torch.tensor([rc_ms, rc_e2e_secs], dtype=torch.float64, device=dev)
         sm2 = torch.tensor([float(rc_tests), float(rc_issued), float(rc_culled_trials), float(rc_trials),
-                            float(rc_e2e_tests)], dtype=torch.float64, device=dev)
+                            float(rc_e2e_tests), float(rc_eval)], dtype=torch.float64, device=dev)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm2, op=dist.ReduceOp.SUM)
         rc_ms, rc_e2e_secs = mx[0].item(), mx[1].item()
-        rc_tests, rc_issued, rc_culled_trials, rc_trials, rc_e2e_tests = (sm2[i].item() for i in range(5))
+        rc_tests, rc_issued, rc_culled_trials, rc_trials, rc_e2e_tests, rc_eval = (sm2[i].item() for i in range(6))
     reach_cull = {
         "flag": "DCRP_FLAG_REACH_CULL (opt-in; results identical to the headline path)",
         "value": rc_tests / (rc_ms * 1e-3), "unit": "tests decided/s (computed or proven impossible by the reach bound; "
                                                     "pairs cleared as a whole count their guaranteed minimum)",
         "ms_per_step": rc_ms / args.steps, "trials_per_s": rc_trials / (rc_ms * 1e-3),
-        "tests_computed_fraction": rc_issued / max(1.0, rc_tests),
+        "tests_evaluated_per_s": rc_eval / (rc_ms * 1e-3),
+        "tests_evaluated_fraction": rc_eval / max(1.0, rc_tests),
         "trials_in_cleared_pairs_fraction": rc_culled_trials / max(1.0, rc_trials),
         "e2e": {"value": rc_e2e_tests / rc_e2e_secs, "ms_per_step": 1e3 * rc_e2e_secs / args.steps},
     }
@@ -487,6 +492,22 @@ def engine_arm(args):
     cpu = {"value": base["tests"] / base["seconds"], "unit": UNIT, "cores": base["cores"], "kind": base["kind"],
            "sample": "99 drones x 20000 trials (%.1f s); %s" % (base["seconds"], base["what"]),
            "trials_per_s": base["trials"] / base["seconds"]}
+    # also one core as shipped, and one core without std::random_device (the C restatement
+    # on Philox draws: what the reference's arithmetic costs once its RNG is out of the way)
+    try:
+        import oracle_api as oa
+        if os.path.exists(oa.REF_ASSHIPPED):
+            one = cpu_reference_run(csv, pk.RING_5KM, 1500, 1, os.path.join(tmp, "asshipped1"))
+            cpu["one_core_as_shipped"] = {"tests_per_s": one["tests"] / one["seconds"],
+                                          "trials_per_s": one["trials"] / one["seconds"],
+                                          "sample": "99 drones x 1500 trials, 1 process (%.1f s)" % one["seconds"]}
+        port = cpu_port_run(tracks[0], ring, 20000, 1)
+        cpu["one_core_port_philox"] = {"tests_per_s": port["tests"] / port["seconds"],
+                                       "trials_per_s": port["trials"] / port["seconds"],
+                                       "sample": "oracle/dcrp_oracle.c, 99 drones x 20000 trials, 1 process (%.1f s)"
+                                                 % port["seconds"]}
+    except Exception as exc:          # reported baseline only: never fail the bench line over it
+        cpu["one_core_note"] = "unavailable: %s" % exc
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -711,10 +711,11 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
         o.drone_steps = 0;
     }
     if (!e->allpairs_run && e->run_cull) {
-        // processed pairs: every test decided (computed or culled); cleared pairs: the guaranteed minimum
+        // evaluated and culled tests are reported separately.  Processed pairs: every stage-2
+        // test is either evaluated or culled; cleared pairs: the guaranteed minimum, all culled.
         o.trials_culled = stats[ST_CULLED_TRIALS];
         o.tests_culled = stats[ST_CULLED_TESTS] + stats[ST_DEAD_TESTS];
-        o.tests_evaluated = stats[ST_PROCESSED_TESTS] - stats[ST_SHARED] + stats[ST_DEAD_TESTS];
+        o.tests_evaluated = stats[ST_PROCESSED_TESTS] - stats[ST_SHARED] - stats[ST_CULLED_TESTS];
         o.drone_steps = 0;
     }
     o.candidates = stats[ST_CANDIDATES];

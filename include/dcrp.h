@@ -157,9 +157,11 @@ typedef struct dcrp_stats {
     uint64_t d2h_bytes;
     /* DCRP_FLAG_REACH_CULL only (0 otherwise) */
     uint64_t trials_culled;    /* trials of (track, drone) pairs the reach bound cleared as a whole: no
-                                  draws made; tests_evaluated counts their GUARANTEED minimum of
-                                  n_steps - takeoff_t stage-2 tests each, tests_shared nothing            */
-    uint64_t tests_culled;     /* stage-2 tests decided by the reach bound instead of being computed     */
+                                  draws made, nothing in tests_shared                                     */
+    uint64_t tests_culled;     /* stage-2 tests decided by the reach bound instead of being evaluated:
+                                  exact for the pairs that ran (there tests_evaluated + tests_culled =
+                                  sum of n_steps - t1st), the GUARANTEED minimum n_steps - takeoff_t per
+                                  trial for the cleared pairs; never part of tests_evaluated             */
 } dcrp_stats;
 
 /* Result buffers (host, caller-owned).  counts is required; the rest optional. */
