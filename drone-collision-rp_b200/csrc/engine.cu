@@ -8,6 +8,7 @@
 #include "dcrp_device.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -741,13 +742,24 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
                              const dcrp_run* run, dcrp_result* result)
 {
     if (!result || !result->counts) return fail(DCRP_ERR_INVALID, "dcrp_simulate: result->counts is required");
+    static const bool timing = std::getenv("DCRP_HOST_TIMING") != nullptr;     // profiling aid (tools/e2e_breakdown.py)
+    using clk = std::chrono::steady_clock;
+    const clk::time_point t0 = clk::now();
     int rc = dcrp_scenario_upload(e, tracks, n_tracks, drones, n_drones, model);
     if (rc != DCRP_OK) return rc;
+    const clk::time_point t1 = clk::now();
     rc = dcrp_run_async(e, run, nullptr, nullptr);
     if (rc != DCRP_OK) return rc;
+    const clk::time_point t2 = clk::now();
     rc = dcrp_fetch(e, result);
     if (rc != DCRP_OK) return rc;
     result->stats.h2d_bytes += e->h2d_scenario;
+    if (timing) {
+        const clk::time_point t3 = clk::now();
+        auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        std::fprintf(stderr, "dcrp_simulate host us: upload %.1f  run_async %.1f  fetch %.1f  total %.1f\n", us(t0, t1), us(t1, t2),
+                     us(t2, t3), us(t0, t3));
+    }
     return DCRP_OK;
 }
 
