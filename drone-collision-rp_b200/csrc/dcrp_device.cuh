@@ -36,7 +36,7 @@ struct TrackDev {
     float    wz32;       // (box[5]-box[4]) * 2^-32
     float    z0rel;      // box[4] - start_alt
     float    thr2_l1_sub;// sub-step mode, level-1 threshold: (R + margin + (max |dA_xy| + v_straight)/2)^2
-    float    pad2;
+    float    thr2_l2_sub;// sub-step mode, level-2 threshold: (R + margin)^2 + the fp32 error of the segment closest approach
 };
 
 struct ScenarioDev {

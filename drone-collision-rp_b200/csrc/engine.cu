@@ -333,18 +333,30 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     // is that bound times sqrt(3) for the 3-D distance, plus a 0.02 m floor.
     const int screen_tile = vl_max <= 128 ? 128 : 512;
     const double ulp = (double)ulp32_of(extent);
+    // after the kink the speed factor lies between v_straight and v_ascend (Drone.cpp:220, pitch in [0, pi/2])
+    const double vmax = std::max(std::fabs(model->v_straight), std::fabs(model->v_ascend));
     const double margin = 0.02 + 1.7321 * (0.5 * screen_tile + 4.0) * ulp +
-                          (double)vl_max * model->v_straight * std::ldexp(1.0, -22);
+                          (double)vl_max * vmax * std::ldexp(1.0, -22);
     s.thr2_screen = std::nextafterf((float)((s.radius + margin) * (s.radius + margin)), INFINITY);
     for (int a = 0; a < n_tracks; ++a) {          // sub-step mode: per-track level-1 radius
         const dcrp_track& t = tracks[a];
-        double amax = 0.0;
-        for (int i = 0; i + 1 < t.n_steps; ++i)
-            amax = std::max(amax, std::hypot(t.x[i + 1] - t.x[i], t.y[i + 1] - t.y[i]));
-        const double rr = s.radius + margin + 0.5 * (amax + model->v_straight) * (1.0 + 1e-6);
+        double amax = 0.0, amax3 = 0.0;
+        for (int i = 0; i + 1 < t.n_steps; ++i) {
+            const double h = std::hypot(t.x[i + 1] - t.x[i], t.y[i + 1] - t.y[i]);
+            amax = std::max(amax, h);
+            amax3 = std::max(amax3, std::hypot(h, t.z[i + 1] - t.z[i]));
+        }
+        // level 1 tests SAMPLES: a segment whose interpolated horizontal separation drops below R has an end
+        // within R + half the horizontal relative step (<= aircraft step + vmax)
+        const double rr = s.radius + margin + 0.5 * (amax + vmax) * (1.0 + 1e-6);
         TrackDev& d = e->h_tracks[(size_t)a];
         d.thr2_l1_sub = std::nextafterf((float)(rr * rr), INFINITY);
-        d.pad2 = 0.f;
+        // level 2 evaluates c + t(2b + ta) in fp32 with |c|, |b|, |a| up to (R + E)^2, E the 3-D relative step
+        // (<= aircraft step + sqrt(2) vmax): ~10 roundings of 2^-24 each, bounded by 4e-6 (R + E)^2.  Nothing for
+        // real tracks (E ~ 100 m: 0.05 m^2), decisive for sparse or teleporting ones.
+        const double E = amax3 + 1.4143 * vmax;
+        d.thr2_l2_sub = std::nextafterf((float)((s.radius + margin) * (s.radius + margin) +
+                                                4e-6 * (s.radius + E) * (s.radius + E)), INFINITY);
     }
     s.thr2_fp32 = (float)(s.radius * s.radius);
     s.v_straight_f = (float)model->v_straight;

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(128) k_reach(const ScenarioDev s)
         int lo = INT_MAX, hi = 0;
         if (t1 <= t.takeoff_t) {
             if (keep_all) {
-                lo = t1; hi = t.n_steps;
+                lo = 0; hi = INT_MAX;        // never empty: a trial with t1st == n_steps has no stage-2 index at all
             } else {
                 const int last = t1 - 1;
                 const double kx = s.p1x[(size_t)j * s.t_max + last], ky = s.p1y[(size_t)j * s.t_max + last];
@@ -1057,7 +1057,8 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     if (r.decide_fp32) {
                         rescan_fp32(s, r, *tk, pair, a, j, s1_first, trial, u);
                     } else if (u.force ||
-                               (r.substep ? min3d_seg_fp32(s, *tk, u) : min3d_fp32(s, *tk, u)) < s.thr2_screen) {
+                               (r.substep ? min3d_seg_fp32(s, *tk, u) < __ldg(&tk->thr2_l2_sub)
+                                          : min3d_fp32(s, *tk, u) < s.thr2_screen)) {
                         ++ncand;
                         const uint32_t slot = warp_claim_slot(r.cand_count);
                         if (slot < r.cand_cap) {

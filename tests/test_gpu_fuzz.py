@@ -1,0 +1,93 @@
+"""GPU tier: randomised scenario shapes.  For every shape the fp64 kernel (the parity kernel, checked
+against the oracle and the unmodified reference in test_gpu_parity.py) is the yardstick; the mixed
+screen, the reach-culled screen and the sub-step pair must reproduce it exactly: counts, first-conflict
+indices and the colliding (track, drone, trial, first_hit) records.  Shapes cover what the fixed tests
+do not combine: 1-sample and 2-sample tracks, takeoff_t = 1 and = n_steps, tracks just around the
+128 / 512 sample tile limits, takeoff_t beyond the 128-entry shared tables, aircraft that shadow a
+drone (many hits), huge and tiny radii, trial counts around the item size."""
+import os
+
+import numpy as np
+import pytest
+
+from drone_collision_rp_b200 import capi
+
+pytestmark = pytest.mark.gpu
+KEYS = ["track", "drone", "trial", "first_hit"]
+
+
+def _random_track(rng, base, n_steps, takeoff_t, ring, shadow, v_straight=19.0, start_alt=100.0):
+    """A smooth random walk through the neighbourhood of the ring, sample 0 kept in the 27L band."""
+    t = np.arange(n_steps, dtype=np.float64)
+    x0 = np.mean([r[0] for r in ring]) + rng.uniform(-1500, 1500)
+    y0 = float(base["y"][0])
+    heading = rng.uniform(0, 2 * np.pi)
+    speed = rng.uniform(0.0, 90.0)
+    x = x0 + np.sin(heading) * speed * t + 40.0 * np.sin(t * rng.uniform(0.01, 0.3))
+    y = y0 + np.cos(heading) * speed * t * rng.uniform(0.0, 1.0)
+    z = np.clip(rng.uniform(2.0, 12.0) * (t - rng.uniform(0, takeoff_t)), 0.0, 600.0)
+    if shadow is not None:
+        # sit on a drone's straight first-stage line for a while, at its altitude: stage-1 and early stage-2 hits
+        xs, ys, hs = shadow
+        k = min(n_steps, rng.integers(1, 12))
+        lo = rng.integers(0, max(1, n_steps - k))
+        idx = np.arange(lo, lo + k)
+        x[idx] = xs + np.sin(hs) * v_straight * idx + rng.uniform(-3, 3)
+        y[idx] = ys + np.cos(hs) * v_straight * idx + rng.uniform(-3, 3)
+        z[idx] = start_alt + rng.uniform(-2, 2)
+    y[0] = y0
+    return {"x": x, "y": y, "z": z, "takeoff_t": int(takeoff_t), "n_steps": int(n_steps),
+            "box": capi.target_box(float(base["y"][0]), 0.0)}
+
+
+def _same(a, b, what):
+    assert np.array_equal(a.counts, b.counts), what
+    assert np.array_equal(a.first_conflict, b.first_conflict), what
+    assert np.array_equal(a.records[KEYS], b.records[KEYS]), what
+    assert np.array_equal(a.records["min_dist"], b.records["min_dist"]), what
+
+
+# DCRP_FUZZ_CASES=n widens the sweep for a one-off soak run (2000 cases were run on B200 in round 1)
+@pytest.mark.parametrize("case", range(int(os.environ.get("DCRP_FUZZ_CASES", "64"))))
+def test_random_shapes_mixed_and_cull_equal_fp64(engine, tracks, ring1, ring5, case):
+    rng = np.random.default_rng(1000 + case)
+    ring = ring1 if case % 3 else ring5
+    n_drones = int(rng.integers(1, 9))
+    j0 = int(rng.integers(0, 99 - n_drones))
+    drones = ring[j0:j0 + n_drones]
+    model = capi.default_model()
+    model.aircraft_radius = float(rng.choice([3.5, 0.5, 40.0]))
+    if case >= 24:       # other kinematic constants: the reach bound must follow them (incl. v_ascend > v_straight)
+        model.v_straight = float(rng.choice([19.0, 10.0, 30.0]))
+        model.v_ascend = float(rng.choice([8.0, 25.0, 0.5]))
+        model.start_alt = float(rng.choice([100.0, 30.0]))
+    lengths = [1, 2, 3, 31, 127, 128, 129, 200, 511, 512, 513, 700, 1100]
+    n_tracks = int(rng.integers(1, 4))
+    trks = []
+    for _ in range(n_tracks):
+        n_steps = int(rng.choice(lengths))
+        takeoff_t = int(rng.choice([1, n_steps, max(1, n_steps // 2), min(n_steps, 30), min(n_steps, 150)]))
+        shadow = drones[int(rng.integers(0, n_drones))] if rng.random() < 0.6 else None
+        trks.append(_random_track(rng, tracks[0], n_steps, takeoff_t, drones, shadow, model.v_straight, model.start_alt))
+    n = int(rng.choice([1, 63, 3071, 3072, 3073, 5000, 12289]))
+    kw = dict(seed=77 + case, trial_begin=int(rng.integers(0, 2**40)), trial_count=n, model=model,
+              record_capacity=1 << 18)
+    ref = engine.simulate(trks, drones, precision=capi.FP64, **kw)
+    if ref.overflow:
+        pytest.skip("more hits than the record buffer: counts-only case")
+    mixed = engine.simulate(trks, drones, precision=capi.MIXED, **kw)
+    cull = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_REACH_CULL, **kw)
+    _same(ref, mixed, "mixed")
+    _same(ref, cull, "cull")
+    assert cull.stats["tests_issued"] <= mixed.stats["tests_issued"]
+    if max(t["n_steps"] for t in trks) < 2:
+        with pytest.raises(capi.DcrpError):           # a segment needs two samples
+            engine.simulate(trks, drones, precision=capi.FP64, flags=capi.FLAG_SUBSTEP, **kw)
+        return
+    sref = engine.simulate(trks, drones, precision=capi.FP64, flags=capi.FLAG_SUBSTEP, **kw)
+    smix = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_SUBSTEP, **kw)
+    if not sref.overflow:
+        _same(sref, smix, "substep")
+        assert np.array_equal(sref.records["first_time"], smix.records["first_time"])
+    if min(t["n_steps"] for t in trks) >= 2:         # a 1-sample track has no segment to interpolate on
+        assert sref.hits >= ref.hits
