@@ -79,7 +79,9 @@ def test_random_shapes_mixed_and_cull_equal_fp64(engine, tracks, ring1, ring5, c
     cull = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_REACH_CULL, **kw)
     _same(ref, mixed, "mixed")
     _same(ref, cull, "cull")
-    assert cull.stats["tests_issued"] <= mixed.stats["tests_issued"]
+    # (with takeoff_t > 64 a t1st bucket holds several values and its internal order comes from atomics:
+    # the issued lane-steps then vary by a few warp-steps from run to run)
+    assert cull.stats["tests_issued"] <= mixed.stats["tests_issued"] * 1.01 + 4096
     if max(t["n_steps"] for t in trks) < 2:
         with pytest.raises(capi.DcrpError):           # a segment needs two samples
             engine.simulate(trks, drones, precision=capi.FP64, flags=capi.FLAG_SUBSTEP, **kw)
@@ -91,3 +93,49 @@ def test_random_shapes_mixed_and_cull_equal_fp64(engine, tracks, ring1, ring5, c
         assert np.array_equal(sref.records["first_time"], smix.records["first_time"])
     if min(t["n_steps"] for t in trks) >= 2:         # a 1-sample track has no segment to interpolate on
         assert sref.hits >= ref.hits
+
+
+@pytest.mark.parametrize("case", range(int(os.environ.get("DCRP_FUZZ_AP_CASES", "12"))))
+def test_random_shapes_allpairs_equals_oracle(engine, oracle, tracks, ring1, case):
+    """The all-pairs path (every ray against every track) on random shapes: tracks around the 512-sample
+    tile limit, 1- and 2-sample tracks, shadowing aircraft, ray counts around the 1024-ray block, reference
+    takeoff times of 1 and beyond the shared-memory table: counts and (track, drone, ray, first_hit) ids
+    equal the oracle's."""
+    rng = np.random.default_rng(5000 + case)
+    n_drones = int(rng.integers(1, 5))
+    j0 = int(rng.integers(0, 99 - n_drones))
+    drones = ring1[j0:j0 + n_drones]
+    trks = []
+    for _ in range(int(rng.integers(1, 4))):
+        n_steps = int(rng.choice([1, 2, 40, 511, 512, 513, 1030]))
+        takeoff_t = int(rng.choice([1, max(1, n_steps // 3), min(n_steps, 30), min(n_steps, 140)]))
+        shadow = drones[int(rng.integers(0, n_drones))] if rng.random() < 0.7 else None
+        trks.append(_random_track(rng, tracks[0], n_steps, takeoff_t, drones, shadow))
+    t_ref = max(t["takeoff_t"] for t in trks)
+    box = capi.target_box(tracks[0]["y"][0], 0.0)
+    n = int(rng.choice([1, 100, 1023, 1024, 1025, 2100]))
+    begin = int(rng.integers(0, 2**33))
+    model = capi.default_model()
+    model.aircraft_radius = float(rng.choice([3.5, 25.0]))
+    engine.upload(trks, drones, model=model)
+    res = engine.allpairs(9 + case, begin, n, t_ref, box, record_capacity=1 << 18)
+    if res.overflow:
+        pytest.skip("more hits than the record buffer")
+    import oracle_api as oa
+
+    om = oa.Model()
+    om.aircraft_radius, om.drone_radius = model.aircraft_radius, model.drone_radius
+    om.start_alt, om.v_straight, om.v_ascend = model.start_alt, model.v_straight, model.v_ascend
+    want_counts = np.zeros((len(trks), len(drones)), dtype=np.int64)
+    want_ids = []
+    for j in range(len(drones)):
+        draws = oracle.draws(9 + case, begin, n, j, 0xFFFFFFFF, t_ref, box)      # all-pairs rays: track id 2^32 - 1
+        for a, t in enumerate(trks):
+            hit, first, _ = oracle.run_trials(t, drones[j], draws, model=om)
+            want_counts[a, j] = int(hit.sum())
+            want_ids += [(a, j, begin + int(k), int(first[k])) for k in np.nonzero(hit)[0]]
+    want_ids.sort()
+    got = res.counts.reshape(len(trks), len(drones)).astype(np.int64)
+    assert np.array_equal(got, want_counts)
+    got_ids = sorted((int(r["track"]), int(r["drone"]), int(r["trial"]), int(r["first_hit"])) for r in res.records)
+    assert got_ids == want_ids
