@@ -603,7 +603,10 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     // slices keep the item count of one launch below 2^30
     const bool exact = (run->precision == DCRP_PRECISION_FP64);
     const uint64_t per_item = exact ? (uint64_t)EXB : screen_chunk();
-    const uint64_t max_chunks = std::max<uint64_t>(1, MAX_ITEMS_PER_LAUNCH / n_pairs);
+    // DCRP_MAX_ITEMS: test aid, forces the slicing below at small sizes (tests/test_gpu_parity.py)
+    static const uint64_t max_items = std::getenv("DCRP_MAX_ITEMS")
+        ? std::max<uint64_t>(1, std::strtoull(std::getenv("DCRP_MAX_ITEMS"), nullptr, 10)) : MAX_ITEMS_PER_LAUNCH;
+    const uint64_t max_chunks = std::max<uint64_t>(1, max_items / n_pairs);
     const uint64_t slice_max = max_chunks * per_item;
     for (uint64_t first = 0; first < run->trial_count; first += slice_max) {
         r.slice_first = first;

@@ -302,3 +302,47 @@ def test_free_running_probability_vs_reference_as_shipped(engine, tracks, ring1)
         print("aircraft %d: p_gpu %.3e (%d hits)  p_ref %.3e (%d hits)  z %.2f" % (
             a, p_gpu, res.hits, p_ref, entry["hits"], z))
         assert abs(z) < 3.0
+
+
+def test_sliced_launches_equal_one_launch(tracks, ring1):
+    """Runs whose item count would exceed 2^30 are cut into slices of consecutive trials, one launch each.
+    DCRP_MAX_ITEMS (a test aid read once per process) forces that at a small size, in a child process:
+    fp64, mixed and culled runs of 40 000 trials in slices of <= 3 items per pair must equal the un-sliced ones."""
+    import json
+    import subprocess
+    import sys
+
+    code = r'''
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+import drone_collision_rp_b200 as pk
+from drone_collision_rp_b200 import capi, scenario
+import tempfile
+eng = capi.Engine(0)
+tracks, _ = scenario.synthetic_tracks(tempfile.mkdtemp(), 2)
+ring = scenario.load_ring(pk.RING_1KM)[:30]
+out = {}
+for name, prec, flags in (("fp64", capi.FP64, 0), ("mixed", capi.MIXED, 0), ("cull", capi.MIXED, capi.FLAG_REACH_CULL)):
+    r = eng.simulate(tracks, ring, seed=31, trial_count=40000, precision=prec, flags=flags)
+    out[name] = {"counts": r.counts.tolist(), "launches": r.stats["kernel_launches"], "trials": r.stats["trials"],
+                 "ids": [[int(x["track"]), int(x["drone"]), int(x["trial"]), int(x["first_hit"])] for x in r.records]}
+print(json.dumps(out))
+''' % pk.REPO_ROOT
+    import os
+
+    def run(env_extra):
+        env = dict(os.environ, **env_extra)
+        p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        assert p.returncode == 0, p.stderr[-2000:]
+        return json.loads(p.stdout.strip().split("\n")[-1])
+
+    whole = run({})
+    sliced = run({"DCRP_MAX_ITEMS": "180"})          # 60 pairs -> 3 items per pair per launch
+    for name in ("fp64", "mixed", "cull"):
+        assert sliced[name]["counts"] == whole[name]["counts"], name
+        assert sliced[name]["ids"] == whole[name]["ids"], name
+        assert sliced[name]["trials"] == whole[name]["trials"] == 60 * 40000
+        assert sliced[name]["launches"] > whole[name]["launches"] + 2, name      # several screen launches
+    assert whole["fp64"]["counts"] == whole["mixed"]["counts"] == whole["cull"]["counts"]
+    assert sum(whole["fp64"]["counts"]) > 0
