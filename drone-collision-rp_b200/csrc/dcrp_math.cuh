@@ -229,6 +229,31 @@ struct Ray32 {           // second-stage ray relative to the scenario origin, fp
     bool  degenerate;    // target (numerically) on top of the kink: must be confirmed
 };
 
+// atan(x) for x >= 0 in fp32 (the pitch of the screen's ray, Drone.cpp:218): degree-7 minimax polynomial of
+// atan(sqrt(u))/sqrt(u) on [0, 1] (fit and measured in fp32 by tests/test_hostsim_math.py: |error| <= 2e-7 rad,
+// the same as the 2 ulp of the library atanf at pi/4) and atan(x) = pi/2 - atan(1/x) above 1.  14 instructions
+// instead of the library's 25; the error is inside the screen margin (engine.cu: n_steps * vmax * 2^-21 term).
+DCRP_HD float atan_nonneg(float x)
+{
+    const bool big = x > 1.0f;
+#if defined(__CUDA_ARCH__)
+    const float r = big ? __fdividef(1.0f, x) : x;
+#else
+    const float r = big ? 1.0f / x : x;
+#endif
+    const float u = r * r;
+    float p = -0.004668773151934147f;
+    p = fmaf(p, u, 0.02416618913412094f);
+    p = fmaf(p, u, -0.0593671016395092f);
+    p = fmaf(p, u, 0.09906096756458282f);
+    p = fmaf(p, u, -0.14016585052013397f);
+    p = fmaf(p, u, 0.19969235360622406f);
+    p = fmaf(p, u, -0.33331960439682007f);
+    p = fmaf(p, u, 0.9999998807907104f);
+    p *= r;
+    return big ? 1.57079632679489662f - p : p;
+}
+
 // (dls, dbs, da) = target - kink, formed in fp64 and rounded once to fp32;
 // (xlf, ylf, zlf) = kink - origin rounded once to fp32; lastf = float(t1st-1).
 // Direction without trig: sin(atan(dL/dB)) = dL/m etc.; pitch needs one atanf.
@@ -251,7 +276,7 @@ DCRP_HD Ray32 stage2_ray32(float dls, float dbs, float da,
     float inv_n = 1.0f / sqrtf(n2);
 #endif
     float ada = fabsf(da);
-    float pitch = atanf(ada * inv_m);
+    float pitch = atan_nonneg(ada * inv_m);
     float vf = fmaf(-coef, pitch, v_straight);
     r.sx = dls * inv_m * vf;
     r.sy = dbs * inv_m * vf;

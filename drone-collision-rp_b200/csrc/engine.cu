@@ -129,8 +129,8 @@ struct dcrp_engine {
     DevBuf d_records, d_cands, d_replay;
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
     // launch configuration caches (per engine = per device: function attributes are per device)
-    size_t screen_smem[2] = {0, 0};
-    int screen_occ[2] = {0, 0};
+    size_t screen_smem[4] = {0, 0, 0, 0};
+    int screen_occ[4] = {0, 0, 0, 0};
     int ap_occ = 0;
     bool allpairs_run = false;
     bool run_cull = false;         // the last run used DCRP_FLAG_REACH_CULL
@@ -336,7 +336,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     // after the kink the speed factor lies between v_straight and v_ascend (Drone.cpp:220, pitch in [0, pi/2])
     const double vmax = std::max(std::fabs(model->v_straight), std::fabs(model->v_ascend));
     const double margin = 0.02 + 1.7321 * (0.5 * screen_tile + 4.0) * ulp +
-                          (double)vl_max * vmax * std::ldexp(1.0, -22);
+                          (double)vl_max * vmax * std::ldexp(1.0, -21);
     s.thr2_screen = std::nextafterf((float)((s.radius + margin) * (s.radius + margin)), INFINITY);
     for (int a = 0; a < n_tracks; ++a) {          // sub-step mode: per-track level-1 radius
         const dcrp_track& t = tracks[a];
@@ -459,18 +459,20 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
 // at least MINB CTAs per SM.
 struct ScreenCfg {
     int rounds, block, minb, np;
-    const void* kern[2];          // [REPLAY]
+    const void* kern[4];          // plain, replay table, reach culling, profiling (DCRP_DEBUG phase ablation)
 };
 template <int R, int BLOCK, int MINB, int NP>
 static ScreenCfg make_cfg()
 {
-    ScreenCfg c{R, BLOCK, MINB, NP, {(const void*)k_screen2<R, BLOCK, false, MINB, NP>,
-                                     (const void*)k_screen2<R, BLOCK, true, MINB, NP>}};
+    ScreenCfg c{R, BLOCK, MINB, NP, {(const void*)k_screen2<R, BLOCK, false, MINB, NP, false, false>,
+                                     (const void*)k_screen2<R, BLOCK, true, MINB, NP, false, false>,
+                                     (const void*)k_screen2<R, BLOCK, false, MINB, NP, true, false>,
+                                     (const void*)k_screen2<R, BLOCK, false, MINB, NP, false, true>}};
     return c;
 }
 // [0] is the production configuration; the others exist for the tuning sweep
 // (tools/profile_target.py with DCRP_SCREEN_CFG=n) and cost nothing unless selected.
-static ScreenCfg g_cfgs[] = {make_cfg<2, 384, 2, 2>(), make_cfg<4, 512, 2, 1>(), make_cfg<2, 512, 2, 2>(), make_cfg<2, 256, 3, 2>()};
+static ScreenCfg g_cfgs[] = {make_cfg<2, 384, 2, 2>(), make_cfg<4, 512, 2, 1>()};
 static ScreenCfg& screen_cfg()
 {
     static const int sel = std::getenv("DCRP_SCREEN_CFG") ? std::atoi(std::getenv("DCRP_SCREEN_CFG")) : 0;
@@ -483,7 +485,8 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
                                   cudaStream_t st)
 {
     ScreenCfg& c = screen_cfg();
-    const int v = r.replay ? 1 : 0;
+    static const uint32_t dbg = std::getenv("DCRP_DEBUG") ? (uint32_t)std::atoi(std::getenv("DCRP_DEBUG")) : 0u;
+    const int v = r.replay ? 1 : (r.cull ? 2 : (dbg ? 3 : 0));     // r.cull is never set together with a replay table
     const void* kern = c.kern[v];
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
@@ -502,7 +505,6 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ);
     static const uint32_t stagger_ns =
         std::getenv("DCRP_STAGGER_NS") ? (uint32_t)std::atoi(std::getenv("DCRP_STAGGER_NS")) : 0u;
-    static const uint32_t dbg = std::getenv("DCRP_DEBUG") ? (uint32_t)std::atoi(std::getenv("DCRP_DEBUG")) : 0u;
     ScenarioDev sd = e->sd;
     RunDev rr = r;
     void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &tile_steps, (void*)&stagger_ns, (void*)&dbg};

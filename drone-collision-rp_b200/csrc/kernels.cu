@@ -741,7 +741,7 @@ __device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const Track
     const float ada = fabsf(fmaf((float)q.z, wz32, z0rel));
     const float m2 = fmaf(dls, dls, dbs * dbs);
     const float inv_m = rsqrtf(m2);
-    const float pitch = atanf(ada * inv_m);                     // Drone.cpp:218
+    const float pitch = atan_nonneg(ada * inv_m);               // Drone.cpp:218
     const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
     const float lastf = (float)last;
     o.sx = dls * k;
@@ -754,7 +754,7 @@ __device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const Track
 
 constexpr int SCREEN_TAB = 128;     // kink-table entries kept in shared memory per CTA
 
-template <int R, int BLOCK, bool REPLAY, int MINB, int NP>
+template <int R, int BLOCK, bool REPLAY, int MINB, int NP, bool CULL, bool DBG>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int tile_steps,
           uint32_t stagger_ns, uint32_t dbg)
@@ -780,6 +780,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     uint16_t* order = reinterpret_cast<uint16_t*>(tabr + SCREEN_TAB);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_shift = tile_steps == 128 ? 7 : 9;      // the host passes 128 or 512
 
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -795,7 +796,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 
     // Reach culling: only the pairs of the scenario's alive list get items; the others are accounted
     // for here, once per launch, with the tests every one of their trials is guaranteed to hold.
-    if (r.cull) {
+    if (CULL) {
         const unsigned long long n_alive = s.reach_tot[0];
         n_items = (uint32_t)(n_alive * chunks_per_pair);
         if (blockIdx.x == 0 && tid == 0) {
@@ -808,7 +809,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
     // (pair, chunk) of the item, carried along the grid-stride loop: divisions only when a pair ends
     int po = (int)(blockIdx.x / chunks_per_pair);          // ordinal in the list of pairs that get work
     uint32_t c = blockIdx.x - (uint32_t)po * chunks_per_pair;
-    int pair = (r.cull && blockIdx.x < n_items) ? (int)s.alive[po] : po;
+    int pair = (CULL && blockIdx.x < n_items) ? (int)s.alive[po] : po;
     int a = pair / s.n_drones, j = pair - a * s.n_drones;
     int tab_pair = -1;
     const bool tab_smem = s.t_max <= SCREEN_TAB;
@@ -817,7 +818,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
         const TrackDev* __restrict__ tk = s.tracks + a;
         const int VL = __ldg(&tk->n_steps);
         const int takeoff_t = __ldg(&tk->takeoff_t);
-        const int n_tiles = (VL + tile_steps - 1) / tile_steps;
+        const int n_tiles = (VL + tile_steps - 1) >> tile_shift;
         const uint64_t chunk_first64 = r.slice_first + (uint64_t)c * CH;
         const uint32_t n_valid = (uint32_t)min((uint64_t)CH, r.slice_count - (uint64_t)c * CH);
         // first stage-1 conflict, as "every trial whose kink index is >= this must be confirmed":
@@ -835,7 +836,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             atomicAdd(&r.stats[ST_CULLED_TESTS], (unsigned long long)acc_cull);
             acc_t1 = acc_is = acc_cull = 0;
         }
-        if (r.cull && tid == 0) atomicAdd(&r.stats[ST_PROCESSED_TESTS], (unsigned long long)n_valid * (unsigned long long)VL);
+        if (CULL && tid == 0) atomicAdd(&r.stats[ST_PROCESSED_TESTS], (unsigned long long)n_valid * (unsigned long long)VL);
 
         // ---------------- phase A: draws + histogram over t1st buckets
         for (int h = tid; h < 80; h += BLOCK) hist[h] = 0;
@@ -845,7 +846,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             if (tid < takeoff_t) {
                 tabk[tid] = __ldg(&s.kink[(size_t)pair * s.t_max + tid]);
                 tabp[tid] = __ldg(&s.p1f[(size_t)j * s.t_max + tid]);
-                if (r.cull) tabr[tid] = __ldg(&s.reach[(size_t)pair * s.t_max + tid]);
+                if (CULL) tabr[tid] = __ldg(&s.reach[(size_t)pair * s.t_max + tid]);
             }
             tab_pair = pair;
         }
@@ -875,7 +876,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     int32_t t1st;
                     if (REPLAY) {
                         t1st = r.replay[(size_t)pair * r.trial_count + chunk_first64 + local].t1st;
-                    } else if (dbg & 4u) {      // profiling aid: no Philox (results meaningless)
+                    } else if (DBG && (dbg & 4u)) {      // profiling aid: no Philox (results meaningless)
                         const uint32_t h = (uint32_t)(chunk_first64 + local) * 2654435761u;
                         t1st = draw_t1st(h, takeoff_t);
                         w1[mm] = h ^ 0x9e3779b9u; w2[mm] = h * 40503u; w3[mm] = h + 0x7f4a7c15u;
@@ -941,7 +942,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             // whatever their targets, and the round needs neither ray set-up nor scan.
             int clo = 0, chi = INT_MAX;
             bool skip_round = false;
-            if (r.cull) {
+            if (CULL) {
                 int lo_l = INT_MAX, hi_l = 0;
                 uint32_t t1s = 0, nv = 0;
 #pragma unroll
@@ -974,7 +975,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                         const Setup32 u = setup_trial32(s, r, *tk, pair, j, s1_first, chunk_first64, q);
                         bx = u.ray.bx; by = u.ray.by; sx = u.ray.sx; sy = u.ray.sy;
                         fmask |= u.force ? (1u << m) : 0u; t1 = u.t1st;
-                    } else if (dbg & 2u) {      // profiling aid: no ray set-up (results meaningless)
+                    } else if (DBG && (dbg & 2u)) {      // profiling aid: no ray set-up (results meaningless)
                         bx = __uint_as_float(q.x >> 9); by = __uint_as_float(q.y >> 9);
                         sx = 1.f; sy = 2.f; t1 = (int32_t)(q.w >> 12);
                     } else {
@@ -988,7 +989,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     }
                     tmin = min(tmin, t1);
                     acc_t1 += (uint32_t)t1;
-                    if (r.cull) acc_cull += (uint32_t)((VL - t1) - max(0, min(VL, chi) - max(clo, t1)));
+                    if (CULL) acc_cull += (uint32_t)((VL - t1) - max(0, min(VL, chi) - max(clo, t1)));
                 }
                 bxs[m] = bx; bys[m] = by; sxs[m] = sx; sys[m] = sy;
             }
@@ -1022,7 +1023,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                     else          { mbar_wait(&bars[1], phase1); phase1 ^= 1u; }
                 }
                 const int t0 = tl * tile_steps;
-                const int lo = max(imin, t0), hi = (dbg & 1u) ? lo : min(iend, t0 + tile_steps);   // dbg 1: no scan
+                const int lo = max(imin, t0), hi = (DBG && (dbg & 1u)) ? lo : min(iend, t0 + tile_steps);   // dbg 1: no scan
                 // LEVEL 1, horizontal screen: d2xy(i) = |Pxy(i) - Axy(i)|^2 <= d2(i), so a trial whose
                 // horizontal separation never drops below R + margin cannot collide at any index, whatever
                 // the altitudes.  6 packed ops per pair-step instead of 9.  P(lo) = B + lo*S is re-based
@@ -1075,7 +1076,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
             const uint32_t adv = c / chunks_per_pair;
             c -= adv * chunks_per_pair;
             po += (int)adv;
-            pair = (r.cull && (uint32_t)po * chunks_per_pair + c < n_items) ? (int)s.alive[po] : po;
+            pair = (CULL && (uint32_t)po * chunks_per_pair + c < n_items) ? (int)s.alive[po] : po;
             a = pair / s.n_drones;
             j = pair - a * s.n_drones;
         }

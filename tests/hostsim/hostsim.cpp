@@ -27,6 +27,12 @@ void hs_make_draw(uint64_t seed, uint64_t trial, uint32_t drone, uint32_t track,
     *out = make_draw(seed, trial, drone, track, takeoff_t, box);
 }
 
+// atan_nonneg over n inputs (tests/test_hostsim_math.py bounds its error against libm's fp64 atan)
+void hs_atan_nonneg(const float* x, long n, float* out)
+{
+    for (long i = 0; i < n; ++i) out[i] = atan_nonneg(x[i]);
+}
+
 double hs_thr_d2(double radius)
 {
     double c = radius * radius;

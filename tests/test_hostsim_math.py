@@ -35,6 +35,20 @@ def test_sqrt_free_threshold_is_exact(hostsim):
         assert np.sqrt(c) >= r and np.sqrt(below) < r
 
 
+def test_polynomial_atan_error_bound(hostsim):
+    """atan_nonneg (the pitch of the screen's ray) against fp64 atan: <= 2.5e-7 rad everywhere the set-up
+    can land (0 .. 1e30, including exactly 1 and the range-reduction seam), monotone enough to be a speed law."""
+    import ctypes as C
+
+    x = np.concatenate([np.linspace(0.0, 1.0, 400001), np.linspace(1.0, 64.0, 400001), np.logspace(-30, 30, 200001),
+                        np.array([0.0, 1.0, np.nextafter(np.float32(1.0), np.float32(2.0)), 1e38])]).astype(np.float32)
+    out = np.empty_like(x)
+    hostsim.L.hs_atan_nonneg(x.ctypes.data_as(C.c_void_p), C.c_long(len(x)), out.ctypes.data_as(C.c_void_p))
+    err = np.abs(out.astype(np.float64) - np.arctan(x.astype(np.float64)))
+    assert err.max() <= 2.5e-7, err.max()
+    assert out[0] == 0.0 and abs(float(out[-1]) - np.pi / 2) < 2e-7
+
+
 def test_fp32_screen_levels_are_conservative_and_accurate(hostsim, golden, tracks, ring1):
     """Level 1 (horizontal, incremental) never exceeds level 2 (3-D, fused) beyond rounding, level 2
     agrees with the fp64 distance on every golden near miss (min in stage 2, < 25 m), and every trial
