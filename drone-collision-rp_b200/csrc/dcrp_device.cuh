@@ -25,6 +25,29 @@
 
 namespace dcrp {
 
+// n / d for a divisor fixed per launch (Granlund-Montgomery): 4 instructions instead of the ~20 of a 32-bit
+// integer division.  q = (t + ((n - t) >> s1)) >> s2 with t = mulhi(m, n).
+struct FastDiv {
+    uint32_t m, s1, s2;
+#if defined(__CUDACC__)
+    __device__ __forceinline__ uint32_t div(uint32_t n) const
+    {
+        const uint32_t t = __umulhi(m, n);
+        return (t + ((n - t) >> s1)) >> s2;
+    }
+#endif
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    uint32_t l = 0;
+    while (l < 32 && (1ull << l) < d) ++l;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+
 struct TrackDev {
     int32_t  n_steps;
     int32_t  takeoff_t;
@@ -63,6 +86,7 @@ struct ScenarioDev {
     unsigned long long* reach_tot;   // [0] n_alive  [1] sum over dead pairs of (n_steps - takeoff_t)
     int32_t n_tracks, n_drones, t_max, n_steps_max;
     int32_t n_sm;                    // SMs of the device (CTA stagger)
+    FastDiv div_drones;              // pair / n_drones
     double ox, oy, oz;               // fp32 origin
     double start_alt, v_straight, v_ascend;
     double radius;                   // R_drone + R_aircraft, summed in fp64 (Drone.cpp:260)
@@ -137,6 +161,7 @@ struct RunDev {
     int32_t   decide_fp32;               // screen kernel: 1 = DCRP_PRECISION_FP32
     int32_t   substep;                   // 1 = DCRP_FLAG_SUBSTEP: interpolated separation between samples
     uint32_t  rk[20];                    // Philox round keys of `seed` (philox_round_keys)
+    FastDiv   div_chunks;                // item / chunks_per_pair of the launch
     int32_t   cull;                      // 1 = DCRP_FLAG_REACH_CULL
 };
 

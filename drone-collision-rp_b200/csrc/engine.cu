@@ -309,6 +309,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     ScenarioDev s{};
     s.n_tracks = n_tracks; s.n_drones = n_drones; s.t_max = t_max; s.n_steps_max = vl_max;
     s.n_sm = e->prop.multiProcessorCount;
+    s.div_drones = make_fastdiv((uint32_t)n_drones);
     s.ox = std::floor(0.5 * (lo[0] + hi[0]));
     s.oy = std::floor(0.5 * (lo[1] + hi[1]));
     s.oz = std::floor(0.5 * (lo[2] + hi[2]));
@@ -623,6 +624,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
             ++e->launches; ++e->launches_this_run;
             CU(cudaGetLastError());
         } else {
+            r.div_chunks = make_fastdiv(chunks);
             const cudaError_t ce = launch_screen2(e, r, chunks, n_items, st);
             if (ce != cudaSuccess) return fail(DCRP_ERR_CUDA, "k_screen launch: %s", cudaGetErrorString(ce));
         }

@@ -740,7 +740,8 @@ __device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const Track
     const float dbs = (float)fma((double)q.y, wy32, kk.y);
     const float ada = fabsf(fmaf((float)q.z, wz32, z0rel));
     const float m2 = fmaf(dls, dls, dbs * dbs);
-    const float inv_m = rsqrtf(m2);
+    float inv_m;                                                // one MUFU.RSQ: m2 > 1e-12 or the trial is forced
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_m) : "f"(m2));
     const float pitch = atan_nonneg(ada * inv_m);               // Drone.cpp:218
     const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
     const float lastf = (float)last;
@@ -1073,11 +1074,11 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 
         c += gridDim.x;                           // next item of this CTA
         if (c >= chunks_per_pair) {
-            const uint32_t adv = c / chunks_per_pair;
+            const uint32_t adv = r.div_chunks.div(c);
             c -= adv * chunks_per_pair;
             po += (int)adv;
             pair = (CULL && (uint32_t)po * chunks_per_pair + c < n_items) ? (int)s.alive[po] : po;
-            a = pair / s.n_drones;
+            a = (int)s.div_drones.div((uint32_t)pair);
             j = pair - a * s.n_drones;
         }
     }
