@@ -358,9 +358,17 @@ def engine_arm(args):
     agg = torch.tensor([total_ms, float(stats_sum["tests_evaluated"]), float(stats_sum["trials"]),
                         float(stats_sum["drone_steps"]), float(stats_sum["tests_shared"])],
                        dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         mx = agg.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm_ = agg.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        # per-rank step and kernel times: tells a slow GPU from an exposed collective when the scaling is off
+        mine = torch.tensor([sum(step_ms) / len(step_ms), sum(trial_ms) / len(trial_ms), tail_ms],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"step_ms": [round(t[0].item(), 4) for t in allr], "screen_kernel_ms": [round(t[1].item(), 4) for t in allr],
+                    "last_allreduce_ms": [round(t[2].item(), 4) for t in allr]}
         total_ms = mx[0].item()
         tests, trials, dsteps, shared = (sm_[i].item() for i in (1, 2, 3, 4))
     else:
@@ -519,6 +527,7 @@ def engine_arm(args):
         "tests_evaluated_per_step": tests / args.steps, "hits_in_timed_steps": stats_sum["hits"],
         "candidates_in_timed_steps": stats_sum["candidates"], "level2_in_timed_steps": stats_sum["level2"],
         "wall_ms_timed_region": wall * 1e3,
+        "per_rank": per_rank,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "dcrp_simulate (host buffers in/out: upload, stage-1, screen, confirm, download)",
