@@ -340,6 +340,8 @@ def engine_arm(args):
         # the last step's reduction has no next step to hide behind: time one isolated all-reduce of
         # the same buffer and charge it to the job
         torch.cuda.synchronize()
+        dist.barrier()                 # the ranks' skew is already in the max-over-ranks of the step times:
+        torch.cuda.synchronize()       # time the collective itself, not the wait for the slowest rank again
         t0e = torch.cuda.Event(enable_timing=True)
         t1e = torch.cuda.Event(enable_timing=True)
         t0e.record(stream)
