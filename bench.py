@@ -34,6 +34,7 @@ TRIALS_PER_DRONE = 101011          # x 99 drones = 1.0000089e7 trials  (BASELINE
 FLOP_PER_TEST = 11                 # 3 add + 3 sub + 3 mul + 2 add, FMA = 2
 SUSTAIN_TRIALS_PER_DRONE = 50_000_000   # 4.95e9 trials per launch for the steady-state figure
 SUSTAIN_LAUNCHES = 10
+RESERVE_SMS = int(os.environ.get("DCRP_BENCH_RESERVE_SMS", "1"))   # multi-GPU only (see engine_arm)
 
 
 def log(*a):
@@ -69,7 +70,8 @@ def config_dict(n_gpus, track):
         "seed": SEED,
         "sharding": "rank g runs trials [(s*N+g)*n, +n) of every (track, drone); counts all-reduced (NCCL) per step "
                     "on a side stream, overlapped with the next step's kernels (one exposed all-reduce per job is "
-                    "added to the timed total)",
+                    "added to the timed total); with N > 1 one SM is kept out of the persistent trial grid "
+                    "(dcrp_engine_reserve_sms) so the NCCL kernel can always run beside the trial kernels",
         "l2": "inputs (3.3 KB track + 2.4 KB ring) are shared-memory/L2 resident by design; a 256 MB buffer "
               "is written between timed steps to flush L2 anyway",
         "parallelism": "dp%d over trial ranges" % n_gpus,
@@ -270,6 +272,10 @@ def engine_arm(args):
             peaks[name] = tf
         log("peaks TFLOP/s:", peaks)
 
+    if world > 1:
+        # the trial kernels fill every SM's register file: keep one SM free so that the NCCL kernel of step s runs
+        # beside the kernels of step s+1 instead of (sometimes) waiting for their last wave to drain
+        eng.reserve_sms(RESERVE_SMS)
     eng.upload(tracks, ring)
     counts = [torch.zeros(n_pairs, dtype=torch.int64, device=dev) for _ in range(2)]
 

@@ -133,6 +133,7 @@ struct dcrp_engine {
     int screen_occ[4] = {0, 0, 0, 0};
     int ap_occ = 0;
     bool allpairs_run = false;
+    int reserve_sms = 0;           // SMs kept free for the caller's communication kernels
     bool run_cull = false;         // the last run used DCRP_FLAG_REACH_CULL
     bool reach_ready = false;      // k_reach has run for the current scenario
     uint64_t ap_rays = 0;
@@ -503,7 +504,7 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     }
     static const int cta_cap = std::getenv("DCRP_MAX_CTAS") ? std::atoi(std::getenv("DCRP_MAX_CTAS")) : 0;
     const int occ = (cta_cap > 0 && cta_cap < e->screen_occ[v]) ? cta_cap : e->screen_occ[v];
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)e->prop.multiProcessorCount * occ);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * occ);
     static const uint32_t stagger_ns =
         std::getenv("DCRP_STAGGER_NS") ? (uint32_t)std::atoi(std::getenv("DCRP_STAGGER_NS")) : 0u;
     ScenarioDev sd = e->sd;
@@ -1061,6 +1062,15 @@ extern "C" int dcrp_flush_l2(dcrp_engine* e, void* stream)
     k_fill<<<e->prop.multiProcessorCount * 8, 256, 0, st>>>(flush.as<float4>(), bytes / sizeof(float4), 1.0f);
     ++e->launches;
     CU(cudaGetLastError());
+    return DCRP_OK;
+}
+
+extern "C" int dcrp_engine_reserve_sms(dcrp_engine* e, int n_sms)
+{
+    if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
+    if (n_sms < 0 || n_sms >= e->prop.multiProcessorCount)
+        return fail(DCRP_ERR_INVALID, "reserve_sms must be in [0, %d)", e->prop.multiProcessorCount);
+    e->reserve_sms = n_sms;
     return DCRP_OK;
 }
 

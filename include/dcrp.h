@@ -263,6 +263,11 @@ int  dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uint32_t n_re
 int  dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms);
 /* Writes `bytes` of a scratch buffer (L2 flush between timed iterations). */
 int  dcrp_flush_l2(dcrp_engine* e, void* stream);
+/* Keeps `n_sms` SMs out of the persistent trial grids (0 = use them all, the default).  A multi-GPU caller
+ * that overlaps a collective with the next run reserves one: the trial kernels fill every SM's register file,
+ * so a communication kernel launched beside them may otherwise have to wait for their last wave to drain
+ * (measured at N=8: the per-step all-reduce was hidden in some runs and fully exposed, +70 us, in others). */
+int  dcrp_engine_reserve_sms(dcrp_engine* e, int n_sms);
 /* Kernels this engine has launched since creation. */
 int  dcrp_launch_count(dcrp_engine* e, uint64_t* n);
 /* Device properties the bench reports. */
