@@ -1,11 +1,13 @@
 // kernels.cu -- hand-written sm_100a kernels of the Monte-Carlo trial path.
 //
-//   k_stage1      once per scenario: stage-1 paths + per-(track,drone) stage-1 tables
+//   k_stage1      once per scenario: stage-1 paths + per-(track,drone) stage-1 tables (one warp per pair)
+//   k_reach       once per scenario, on demand: feasible index ranges for DCRP_FLAG_REACH_CULL
 //   k_screen2     every trial, fp32 packed (FFMA2/FADD2/FMUL2/FMNMX3): Philox draws,
 //                 CTA-level binning by t1st, fp64->fp32 ray set-up, scan of the track
 //                 staged in shared memory by TMA bulk copies, warp-aggregated append
 //                 of the (rare) candidates
-//   k_confirm     candidates only, fp64 in the reference's order of operations
+//   k_confirm_all candidates only, fp64 in the reference's order of operations (one warp per candidate)
+//   k_ap_*        all-pairs stress path (BASELINE config 5): rays sorted once, tracks streamed by a TMA ring
 //   k_exact       every trial in fp64 (DCRP_PRECISION_FP64; the parity kernel)
 //   k_draws       Philox replay-table dump
 //   k_trajectory  full fp64 trajectories of recorded collisions (Drone::Output rows)
@@ -703,15 +705,14 @@ __device__ __forceinline__ float min3d_seg_fp32(const ScenarioDev& s, const Trac
 // =========================================================================
 // k_screen2: the fp32 packed screen, balanced rounds
 // =========================================================================
-// Same contract as k_screen (every trial screened conservatively in fp32, rare
-// candidates appended), restructured after the first ncu profile
-// (profiles/r01_*): per item a CTA bins CH = BLOCK*2*R trials by t1st, then every
-// warp runs R rounds of (set up 2 trials per lane -> scan them as ONE packed
-// pair).  Round pairs take complementary bins (short scan + long scan), so all
-// warps of a CTA do the same amount of scan work per item and do not wait for
-// each other at the next barrier; one pair in flight keeps the kernel at <= 48
-// registers so 5 CTAs of 256 threads overlap their integer (Philox/binning),
-// fp64/conversion (set-up) and FMA-pipe (scan) phases on one SM.
+// Every trial is screened conservatively in fp32 and the rare candidates are appended for the fp64
+// confirm.  Per work item a CTA draws CH = BLOCK * 2*NP * R trials (Philox), bins them by t1st (counting
+// sort in shared memory), then every warp runs R rounds of (set up 2*NP trials per lane -> scan them as NP
+// packed pairs).  Round pairs take complementary bins (short scan + long scan), so all warps of a CTA do
+// the same amount of scan work per item and do not wait for each other at the next barrier.  Production:
+// R = 2, BLOCK = 384, NP = 2 (3072 trials per item, 80 registers, 2 CTAs per SM); DESIGN.md 5.1 has the
+// measurements behind each choice.  Template flags: REPLAY (draws from a table), CULL (reach culling,
+// DESIGN.md 5.3), DBG (phase-ablation switches for profiling; never set in a production variant).
 struct Fast32 {          // horizontal ray of one trial for level 1: position(i) = b + i*s
     float bx, by, sx, sy;
     int32_t t1st;
