@@ -94,12 +94,12 @@ DCRP_SYMBOLS = [
     "dcrp_abi_version", "dcrp_last_error", "dcrp_default_model", "dcrp_engine_create",
     "dcrp_engine_destroy", "dcrp_target_box", "dcrp_simulate", "dcrp_scenario_upload",
     "dcrp_run_async", "dcrp_fetch", "dcrp_last_run_ms", "dcrp_allpairs", "dcrp_dump_draws", "dcrp_trajectories",
-    "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
+    "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_device_count", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
 ]
 DCRP_HOST_SYMBOLS = [
     "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_ring_write",
     "dcrph_aircraft_load",
-    "dcrph_ring_row", "dcrph_monte_carlo", "dcrph_monte_carlo_batch", "dcrph_set_run_flags", "dcrph_write_block",
+    "dcrph_ring_row", "dcrph_monte_carlo", "dcrph_monte_carlo_batch", "dcrph_set_run_flags", "dcrph_set_gpus", "dcrph_write_block",
 ]
 
 
@@ -130,6 +130,7 @@ def lib():
         L.dcrp_trajectories.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, c_double_p, C.POINTER(C.c_int32)]
         L.dcrp_measure_peak.argtypes = [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_float)]
         L.dcrp_flush_l2.argtypes = [C.c_void_p, C.c_void_p]
+        L.dcrp_device_count.argtypes = [C.POINTER(C.c_int)]
         L.dcrp_engine_reserve_sms.argtypes = [C.c_void_p, C.c_int]
         L.dcrp_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.dcrp_device_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int),
@@ -162,6 +163,8 @@ def host():
                                               C.POINTER(C.c_uint64)]
         H.dcrph_set_run_flags.argtypes = [C.c_uint32]
         H.dcrph_set_run_flags.restype = None
+        H.dcrph_set_gpus.argtypes = [C.c_int]
+        H.dcrph_set_gpus.restype = None
         H.dcrph_write_block.argtypes = [C.c_char_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_long]
         _host = H
     return _host

@@ -1065,6 +1065,19 @@ extern "C" int dcrp_flush_l2(dcrp_engine* e, void* stream)
     return DCRP_OK;
 }
 
+extern "C" int dcrp_device_count(int* n)
+{
+    if (!n) return fail(DCRP_ERR_INVALID, "dcrp_device_count: NULL argument");
+    *n = 0;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess || c <= 0) {
+        cudaGetLastError();
+        return fail(DCRP_ERR_NO_DEVICE, "no CUDA device visible");
+    }
+    *n = c;
+    return DCRP_OK;
+}
+
 extern "C" int dcrp_engine_reserve_sms(dcrp_engine* e, int n_sms)
 {
     if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");

@@ -1,6 +1,7 @@
 // Batch.cpp -- see Batch.h.
 #include "Batch.h"
 
+#include <algorithm>
 #include <fstream>
 #include <memory>
 #include <vector>
@@ -13,7 +14,7 @@ namespace dcrp_host {
 BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols, int aircraft_begin,
                               int aircraft_end, const std::string& drone_csv, int drone_cols, int drone_total,
                               uint64_t number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
-                              int precision, const std::string& out_dir, uint32_t run_flags)
+                              int precision, const std::string& out_dir, uint32_t run_flags, int n_gpus)
 {
     BatchResult out;
     auto fail = [&](int status, const std::string& what) { out.status = status; out.error = what; return out; };
@@ -69,8 +70,66 @@ BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols
     dcrp_result res{};
     res.counts = counts.data();
     res.records = records.data();
-    int rc = dcrp_simulate(eng, tracks.data(), n_tracks, drones.data(), drone_total, &model, &run, &res);
-    if (rc != DCRP_OK) return fail(rc, dcrp_last_error());
+    int rc = DCRP_OK;
+    int visible = 1;
+    if (n_gpus != 1 && dcrp_device_count(&visible) != DCRP_OK) return fail(DCRP_ERR_NO_DEVICE, dcrp_last_error());
+    const int G = n_gpus <= 0 ? visible : std::min(n_gpus, visible);
+    if (G <= 1) {
+        rc = dcrp_simulate(eng, tracks.data(), n_tracks, drones.data(), drone_total, &model, &run, &res);
+        if (rc != DCRP_OK) return fail(rc, dcrp_last_error());
+    } else {
+        // One process, G devices: the same scenario on every device, device g runs the contiguous trial range
+        // [g n / G, (g+1) n / G) of every (track, drone) -- the Philox counter carries the global trial id, so the
+        // union is the single-GPU result bit for bit -- all launches queued before the first fetch; counts are
+        // summed and records merged here (one process needs no collective).
+        std::vector<dcrp_engine*> engs(G, nullptr);
+        engs[0] = eng;
+        auto cleanup = [&]() { for (int g = 1; g < G; ++g) if (engs[g]) dcrp_engine_destroy(engs[g]); };
+        for (int g = 1; g < G; ++g)
+            if ((rc = dcrp_engine_create(g, &engs[g])) != DCRP_OK) { cleanup(); return fail(rc, dcrp_last_error()); }
+        for (int g = 0; g < G && rc == DCRP_OK; ++g) {
+            rc = dcrp_scenario_upload(engs[g], tracks.data(), n_tracks, drones.data(), drone_total, &model);
+            if (rc != DCRP_OK) break;
+            dcrp_run part = run;
+            part.trial_begin = number_runs * (uint64_t)g / (uint64_t)G;
+            part.trial_count = number_runs * (uint64_t)(g + 1) / (uint64_t)G - part.trial_begin;
+            rc = dcrp_run_async(engs[g], &part, nullptr, nullptr);
+        }
+        if (rc != DCRP_OK) { const std::string why = dcrp_last_error(); cleanup(); return fail(rc, why); }
+        uint32_t n_rec = 0;
+        int overflow = 0;
+        std::vector<uint64_t> part_counts(counts.size());
+        dcrp_stats total{};
+        for (int g = 0; g < G; ++g) {
+            std::fill(part_counts.begin(), part_counts.end(), 0);
+            dcrp_result pr{};
+            pr.counts = part_counts.data();
+            pr.records = records.data() + n_rec;
+            // dcrp_fetch fills at most the run's record_capacity; keep the merged buffer within bounds
+            rc = dcrp_fetch(engs[g], &pr);
+            if (rc != DCRP_OK) { const std::string why = dcrp_last_error(); cleanup(); return fail(rc, why); }
+            for (size_t k = 0; k < counts.size(); ++k) counts[k] += part_counts[k];
+            overflow |= pr.overflow;
+            n_rec += pr.n_records;
+            if ((size_t)n_rec + run.record_capacity > records.size()) records.resize((size_t)n_rec + run.record_capacity);
+            total.trials += pr.stats.trials; total.tests_evaluated += pr.stats.tests_evaluated;
+            total.tests_shared += pr.stats.tests_shared; total.tests_issued += pr.stats.tests_issued;
+            total.tests_culled += pr.stats.tests_culled; total.trials_culled += pr.stats.trials_culled;
+            total.candidates += pr.stats.candidates; total.level2 += pr.stats.level2; total.hits += pr.stats.hits;
+            total.kernel_launches += pr.stats.kernel_launches;
+            total.ms_trials = std::max(total.ms_trials, pr.stats.ms_trials);
+            total.ms_device_total = std::max(total.ms_device_total, pr.stats.ms_device_total);
+        }
+        cleanup();
+        std::sort(records.begin(), records.begin() + n_rec, [](const dcrp_record& a, const dcrp_record& b) {
+            if (a.track != b.track) return a.track < b.track;
+            if (a.drone != b.drone) return a.drone < b.drone;
+            return a.trial < b.trial;
+        });
+        res.n_records = n_rec;
+        res.overflow = overflow;
+        res.stats = total;
+    }
     for (uint64_t c : counts) out.collisions += c;
     out.trials = (uint64_t)n_tracks * drone_total * number_runs;
     out.stats = res.stats;

@@ -24,7 +24,7 @@ struct BatchResult {
 BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols, int aircraft_begin,
                               int aircraft_end, const std::string& drone_csv, int drone_cols, int drone_total,
                               uint64_t number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
-                              int precision, const std::string& out_dir, uint32_t run_flags = 0);
+                              int precision, const std::string& out_dir, uint32_t run_flags = 0, int n_gpus = 1);
 
 }  // namespace dcrp_host
 

@@ -22,7 +22,7 @@ using namespace std;
 static void usage(const char* argv0)
 {
     cout << "usage: " << argv0 << " [--aircraft-csv F] [--drone-csv F] [--aircraft N] [--drones N]\n"
-            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS] [--batch] [--cull]\n"
+            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS] [--batch [--gpus N]] [--cull]\n"
             "defaults are the reference's constants (Monte_Carlo.cpp:11-18,28,33)\n";
 }
 
@@ -42,6 +42,7 @@ int main(int argc, char** argv)
     int precision = DCRP_PRECISION_MIXED;
     int synthetic = 0;
     bool batch = false;          // one GPU launch for all (aircraft, drone) pairs instead of one per pair
+    int n_gpus = 1;              // --gpus N (0 = all): --batch only, trial ranges split over the devices of this process
     uint32_t run_flags = 0;      // --cull: DCRP_FLAG_REACH_CULL (exact culling by reachability, same results)
 
     for (int i = 1; i < argc; ++i) {
@@ -59,6 +60,7 @@ int main(int argc, char** argv)
         else if (a == "--synthetic") synthetic = atoi(next("--synthetic"));
         else if (a == "--batch") batch = true;
         else if (a == "--cull") run_flags |= DCRP_FLAG_REACH_CULL;
+        else if (a == "--gpus") n_gpus = atoi(next("--gpus"));
         else if (a == "--precision") {
             const string p = next("--precision");
             if (p == "fp64") precision = DCRP_PRECISION_FP64;
@@ -83,7 +85,7 @@ int main(int argc, char** argv)
     if (batch) {
         const dcrp_host::BatchResult r = dcrp_host::monte_carlo_batch(
             FilePath_aircraft, no_col_aircraft, 0, aircraft_total, FilePath_drone, no_col_drone, drone_total,
-            (uint64_t)number_runs, aircraft_radius, drone_radius, seed, precision, "Drone_Collisions", run_flags);
+            (uint64_t)number_runs, aircraft_radius, drone_radius, seed, precision, "Drone_Collisions", run_flags, n_gpus);
         if (r.status != 0) { cout << "ERROR - " << r.error << endl; return 1; }
         cout << "Number of collisions: " << (double)r.collisions << endl;
         dcrp_host::release_shared_engine();

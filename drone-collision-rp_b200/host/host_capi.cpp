@@ -78,6 +78,9 @@ extern "C" int dcrph_ring_row(const char* path, int total_cols, int drone_index,
 // the reference's main() and carry no flag word).
 static uint32_t g_host_run_flags = 0;
 extern "C" void dcrph_set_run_flags(uint32_t flags) { g_host_run_flags = flags; }
+// Devices dcrph_monte_carlo_batch spreads the trial range over (1 = default, 0 = all visible).
+static int g_host_gpus = 1;
+extern "C" void dcrph_set_gpus(int n_gpus) { g_host_gpus = n_gpus; }
 
 extern "C" int dcrph_monte_carlo(const char* aircraft_csv, int aircraft_cols, int aircraft_begin,
                                  int aircraft_end, const char* drone_csv, int drone_cols, int drone_total,
@@ -125,7 +128,7 @@ extern "C" int dcrph_monte_carlo_batch(const char* aircraft_csv, int aircraft_co
     const dcrp_host::BatchResult r = dcrp_host::monte_carlo_batch(
         aircraft_csv, aircraft_cols, aircraft_begin, aircraft_end, drone_csv, drone_cols, drone_total, number_runs,
         aircraft_radius, drone_radius, seed, precision, (out_dir && *out_dir) ? out_dir : "Drone_Collisions",
-        g_host_run_flags);
+        g_host_run_flags, g_host_gpus);
     if (r.status != 0) { g_host_err = r.error; return r.status; }
     *total_collisions = r.collisions;
     return 0;

@@ -263,6 +263,8 @@ int  dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uint32_t n_re
 int  dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms);
 /* Writes `bytes` of a scratch buffer (L2 flush between timed iterations). */
 int  dcrp_flush_l2(dcrp_engine* e, void* stream);
+/* Number of CUDA devices visible to the process (0 and DCRP_ERR_NO_DEVICE when there is none). */
+int  dcrp_device_count(int* n);
 /* Keeps `n_sms` SMs out of the persistent trial grids (0 = use them all, the default).  A multi-GPU caller
  * that overlaps a collective with the next run reserves one: the trial kernels fill every SM's register file,
  * so a communication kernel launched beside them may otherwise have to wait for their last wave to drain

@@ -57,6 +57,9 @@ int dcrph_monte_carlo_batch(const char* aircraft_csv, int aircraft_cols, int air
 /* DCRP_FLAG_* (dcrp.h) applied to every later dcrph_monte_carlo / dcrph_monte_carlo_batch call of the
  * process, e.g. DCRP_FLAG_REACH_CULL.  Extension: the reference's main() has no such knob. */
 void dcrph_set_run_flags(uint32_t flags);
+/* Devices later dcrph_monte_carlo_batch calls split their trial range over, inside this one process (1 = default,
+ * 0 = all visible).  Same counts and files as one device: the Philox counters carry the global trial id. */
+void dcrph_set_gpus(int n_gpus);
 
 /* Drone::Output's row format (Drone.cpp:237-241) applied to one trajectory;
  * appends to `path`. */

@@ -133,3 +133,29 @@ def test_out_of_band_runway_is_an_error_not_stale_values(engine, tracks, ring1, 
     with pytest.raises(capi.DcrpError) as e:
         engine.simulate([bad], ring1, trial_count=100)
     assert e.value.status == capi.ERR_RUNWAY
+
+
+def test_batch_driver_on_all_gpus_of_the_process(day, tmp_path):
+    """Batch.cpp with n_gpus > 1: one process, the trial range split over its devices -- same count and
+    byte-identical collision files as one device.  Skipped on a single-GPU box."""
+    n = C.c_int(0)
+    capi._check(capi.lib().dcrp_device_count(C.byref(n)))
+    if n.value < 2:
+        pytest.skip("needs at least 2 GPUs in the process")
+    tracks, csv = day
+    one_dir, all_dir = tmp_path / "one", tmp_path / "all"
+    one_dir.mkdir(); all_dir.mkdir()
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    capi._hcheck(capi.host().dcrph_monte_carlo_batch(csv.encode(), 22, 0, 4, pk.RING_1KM.encode(), 4, 99, 30001, 3.5,
+                                                     0.19, SEED, capi.MIXED, str(one_dir).encode(), C.byref(a)))
+    capi.host().dcrph_set_gpus(0)
+    try:
+        capi._hcheck(capi.host().dcrph_monte_carlo_batch(csv.encode(), 22, 0, 4, pk.RING_1KM.encode(), 4, 99, 30001,
+                                                         3.5, 0.19, SEED, capi.MIXED, str(all_dir).encode(),
+                                                         C.byref(b)))
+    finally:
+        capi.host().dcrph_set_gpus(1)
+    assert a.value == b.value > 0
+    for k in range(4):
+        name = "Drone_coords_%d.csv" % k
+        assert open(one_dir / name).read() == open(all_dir / name).read()
