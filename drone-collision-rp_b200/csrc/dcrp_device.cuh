@@ -25,29 +25,6 @@
 
 namespace dcrp {
 
-// n / d for a divisor fixed per launch (Granlund-Montgomery): 4 instructions instead of the ~20 of a 32-bit
-// integer division.  q = (t + ((n - t) >> s1)) >> s2 with t = mulhi(m, n).
-struct FastDiv {
-    uint32_t m, s1, s2;
-#if defined(__CUDACC__)
-    __device__ __forceinline__ uint32_t div(uint32_t n) const
-    {
-        const uint32_t t = __umulhi(m, n);
-        return (t + ((n - t) >> s1)) >> s2;
-    }
-#endif
-};
-inline FastDiv make_fastdiv(uint32_t d)
-{
-    FastDiv f;
-    uint32_t l = 0;
-    while (l < 32 && (1ull << l) < d) ++l;
-    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
-    f.s1 = l < 1 ? l : 1;
-    f.s2 = l > 0 ? l - 1 : 0;
-    return f;
-}
-
 struct TrackDev {
     int32_t  n_steps;
     int32_t  takeoff_t;

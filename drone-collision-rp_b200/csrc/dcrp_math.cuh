@@ -141,6 +141,29 @@ DCRP_HD Draw make_draw(uint64_t seed, uint64_t trial, uint32_t drone, uint32_t t
     return d;
 }
 
+// ---------------------------------------------------------------- division by a launch constant
+// n / d for a divisor fixed per launch (Granlund-Montgomery): 4 instructions instead of the ~20 of a 32-bit
+// integer division.  q = (t + ((n - t) >> s1)) >> s2 with t = mulhi(m, n); exact for every 32-bit n and d >= 1
+// (tests/test_hostsim_math.py).
+struct FastDiv {
+    uint32_t m, s1, s2;
+    DCRP_HD uint32_t div(uint32_t n) const
+    {
+        const uint32_t t = mulhi32(m, n);
+        return (t + ((n - t) >> s1)) >> s2;
+    }
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    uint32_t l = 0;
+    while (l < 32 && (1ull << l) < d) ++l;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+
 // ---------------------------------------------------------------- stage 2 set-up
 struct Ray64 {           // the trial's second-stage ray, fp64
     double x, y, z;      // position at index t1st-1 (the kink)

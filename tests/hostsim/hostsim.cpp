@@ -33,6 +33,17 @@ void hs_atan_nonneg(const float* x, long n, float* out)
     for (long i = 0; i < n; ++i) out[i] = atan_nonneg(x[i]);
 }
 
+// FastDiv against the machine's own division; returns the number of mismatches over a strided sweep of n
+long hs_fastdiv_mismatches(uint32_t d, uint32_t stride)
+{
+    const FastDiv f = make_fastdiv(d);
+    long bad = 0;
+    for (uint64_t n = 0; n <= 0xffffffffull; n += stride) bad += f.div((uint32_t)n) != (uint32_t)n / d;
+    const uint32_t edge[] = {0u, 1u, d - 1u, d, d + 1u, 2u * d - 1u, 2u * d, 0x7fffffffu, 0x80000000u, 0xfffffffeu, 0xffffffffu};
+    for (uint32_t n : edge) bad += f.div(n) != n / d;
+    return bad;
+}
+
 double hs_thr_d2(double radius)
 {
     double c = radius * radius;

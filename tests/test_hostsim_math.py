@@ -35,6 +35,18 @@ def test_sqrt_free_threshold_is_exact(hostsim):
         assert np.sqrt(c) >= r and np.sqrt(below) < r
 
 
+def test_magic_number_division_is_exact(hostsim):
+    """FastDiv (pair / n_drones and item / chunks_per_pair in k_screen2) equals integer division for every divisor
+    class: 1, powers of two, odd, just below / above powers of two, huge."""
+    import ctypes as C
+
+    hostsim.L.hs_fastdiv_mismatches.restype = C.c_long
+    hostsim.L.hs_fastdiv_mismatches.argtypes = [C.c_uint32, C.c_uint32]
+    for d in (1, 2, 3, 5, 7, 25, 33, 99, 100, 127, 128, 129, 296, 1000, 4095, 4096, 4097, 65535, 65536, 1000003,
+              0x7fffffff, 0x80000000, 0x80000001, 0xfffffffe, 0xffffffff):
+        assert hostsim.L.hs_fastdiv_mismatches(d, 65521) == 0, d
+
+
 def test_polynomial_atan_error_bound(hostsim):
     """atan_nonneg (the pitch of the screen's ray) against fp64 atan: <= 2.5e-7 rad everywhere the set-up
     can land (0 .. 1e30, including exactly 1 and the range-reduction seam), monotone enough to be a speed law."""
