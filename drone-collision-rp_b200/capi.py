@@ -16,6 +16,7 @@ FP64, MIXED, FP32 = 0, 1, 2
 FLAG_PER_TRIAL = 1
 FLAG_SUBSTEP = 2
 FLAG_REACH_CULL = 4
+FLAG_SCREEN_2D = 8
 INT32_MAX = 2**31 - 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -67,7 +68,7 @@ class Stats(C.Structure):
                 ("hits", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
                 ("ms_prepare", C.c_float), ("ms_trials", C.c_float), ("ms_confirm", C.c_float),
                 ("ms_device_total", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("trials_culled", C.c_uint64), ("tests_culled", C.c_uint64)]
+                ("trials_culled", C.c_uint64), ("tests_culled", C.c_uint64), ("slab_survivors", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}

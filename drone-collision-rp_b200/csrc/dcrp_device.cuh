@@ -61,6 +61,7 @@ struct ScenarioDev {
     int2*           reach;           // [n_pairs*t_max] entry t1st-1; empty = (INT32_MAX, 0)
     uint32_t*       alive;           // [n_pairs] pair ids, n_alive of them valid (unordered)
     unsigned long long* reach_tot;   // [0] n_alive  [1] sum over dead pairs of (n_steps - takeoff_t)
+    float2*         slab_dir;        // [n_pairs] unit vector n of the 1-D slab level (k_slab_axis; screen3.cu)
     int32_t n_tracks, n_drones, t_max, n_steps_max;
     int32_t n_sm;                    // SMs of the device (CTA stagger)
     FastDiv div_drones;              // pair / n_drones
@@ -71,6 +72,7 @@ struct ScenarioDev {
     double radius2;                  // radius * radius: the sub-step mode's threshold on |D(t)|^2
     float  thr2_screen;              // (radius + margin)^2 : fp32 screen, conservative
     float  thr2_fp32;                // radius^2 in fp32    : DCRP_PRECISION_FP32 decisions
+    float  thr_slab;                 // radius + slab margin (NOT squared): 1-D slab level, conservative
     float  v_straight_f, coef_f;     // 19, 2*(19-8)/pi
     int32_t bucket_shift;            // t1st bucket = (t1st-1) >> bucket_shift   (<= 64 buckets)
 };
@@ -116,7 +118,7 @@ struct AllPairsDev {
 };
 
 enum StatSlot { ST_EVALUATED = 0, ST_SHARED, ST_ISSUED, ST_STEPS, ST_CANDIDATES, ST_HITS, ST_LEVEL2,
-                ST_CULLED_TRIALS, ST_CULLED_TESTS, ST_DEAD_TESTS, ST_PROCESSED_TESTS, ST_COUNT };
+                ST_CULLED_TRIALS, ST_CULLED_TESTS, ST_DEAD_TESTS, ST_PROCESSED_TESTS, ST_SLAB_SURVIVORS, ST_COUNT };
 
 struct RunDev {
     uint64_t seed, trial_begin, trial_count;   // the whole run: trials [begin, begin+count) per pair
@@ -140,6 +142,7 @@ struct RunDev {
     uint32_t  rk[20];                    // Philox round keys of `seed` (philox_round_keys)
     FastDiv   div_chunks;                // item / chunks_per_pair of the launch
     int32_t   cull;                      // 1 = DCRP_FLAG_REACH_CULL
+    uint32_t* work_counter;              // k_screen3: next unclaimed work item of the launch
 };
 
 }  // namespace dcrp

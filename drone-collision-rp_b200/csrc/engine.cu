@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cu"
+#include "screen3.cu"
 
 using namespace dcrp;
 
@@ -84,9 +85,9 @@ struct PinnedBuf {         // grow-only pinned host buffer (async copies need pa
 
 static inline size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
-// screen kernel configuration: 512 threads, 4 rounds x 2 trials per thread per item
-// (4096-trial chunks), 2 CTAs per SM, 64 registers, no spills: best of the sweeps in
-// profiles/r01_screen_cfg_sweep.txt
+// Screen kernels: k_screen3 (screen3.cu; 1-D slab level + queued 2-D re-scan, 256-trial warp
+// items) for plain MIXED runs; k_screen2<R=2, BLOCK=384, NP=2> (kernels.cu; sorted 2-D scan, 3072-trial CTA
+// items) for replay tables, reach culling, the sub-step extension, fp32 decisions and long tracks.
 constexpr uint32_t DEFAULT_RECORD_CAP = 1u << 16;
 constexpr uint32_t CAND_CAP = 1u << 22;
 constexpr uint64_t MAX_ITEMS_PER_LAUNCH = 1ull << 30;
@@ -111,6 +112,10 @@ struct dcrp_engine {
     PinnedBuf h_scn;
     DevBuf d_p1x, d_p1y, d_s1fh, d_s1pm, d_kink, d_p1f, d_s1sub_pm, d_s1sub_fs, d_s1sub_ft;
     DevBuf d_reach, d_alive, d_reach_tot;
+    DevBuf d_slab_dir, d_work;     // k_screen3: slab direction per pair; the launch's work-item counter
+    bool slab_ready = false;       // k_slab_axis has run for the current scenario
+    size_t s3_smem = 0;
+    int s3_occ = 0;
     bool prepare_timed = false;
 
     // run
@@ -135,6 +140,7 @@ struct dcrp_engine {
     bool allpairs_run = false;
     int reserve_sms = 0;           // SMs kept free for the caller's communication kernels
     bool run_cull = false;         // the last run used DCRP_FLAG_REACH_CULL
+    bool run_screen3 = false;      // the last run went through k_screen3
     bool reach_ready = false;      // k_reach has run for the current scenario
     uint64_t ap_rays = 0;
     DevBuf d_ap_hist, d_ap_rank, d_ap_rayA, d_ap_rayB, d_ap_meta, d_ap_l2;
@@ -204,7 +210,8 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
                       &e->d_s1sub_ft, &e->d_out, &e->d_records,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
                       &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
-                      &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2, &e->d_reach, &e->d_alive, &e->d_reach_tot};
+                      &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2, &e->d_reach, &e->d_alive, &e->d_reach_tot,
+                      &e->d_slab_dir, &e->d_work};
     for (DevBuf* b : bufs) b->release();
     e->h_scn.release();
     e->h_out.release();
@@ -361,6 +368,12 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
                                                 4e-6 * (s.radius + E) * (s.radius + E)), INFINITY);
     }
     s.thr2_fp32 = (float)(s.radius * s.radius);
+    {   // 1-D slab level (screen3.cu): the same error sources, on coordinates projected on a unit vector
+        // (magnitudes up to sqrt(2) x extent, three more roundings for the projections), re-based every 128
+        const double ulp_p = (double)ulp32_of(1.4143 * extent);
+        const double margin_slab = 0.02 + (0.5 * 128.0 + 12.0) * ulp_p + (double)vl_max * vmax * std::ldexp(1.0, -20);
+        s.thr_slab = std::nextafterf((float)(s.radius + margin_slab), INFINITY);
+    }
     s.v_straight_f = (float)model->v_straight;
     s.coef_f = (float)(2.0 * (model->v_straight - model->v_ascend) / DCRP_PI);
     s.bucket_shift = 0;
@@ -419,6 +432,8 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     CU(e->d_reach.need(sizeof(int2) * n_pairs * (size_t)t_max));
     CU(e->d_alive.need(sizeof(uint32_t) * n_pairs));
     CU(e->d_reach_tot.need(sizeof(unsigned long long) * 2));
+    CU(e->d_slab_dir.need(sizeof(float2) * n_pairs));
+    CU(e->d_work.need(256));
     CU(cudaEventRecord(e->ev_a, st));
     CU(cudaMemcpyAsync(e->d_scn.p, hb, scn_bytes, cudaMemcpyHostToDevice, st));
     e->h2d_scenario = scn_bytes;
@@ -443,11 +458,13 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     s.reach = e->d_reach.as<int2>();
     s.alive = e->d_alive.as<uint32_t>();
     s.reach_tot = e->d_reach_tot.as<unsigned long long>();
+    s.slab_dir = e->d_slab_dir.as<float2>();
 
     k_stage1<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s);            // one warp per pair
     ++e->launches;
     CU(cudaGetLastError());
     e->reach_ready = false;        // the reach table is built by the first run that asks for it
+    e->slab_ready = false;         // likewise the slab directions of k_screen3
     CU(cudaEventRecord(e->ev_b, st));   // no host sync here: runs queue behind it on the same stream
     e->prepare_timed = false;
     e->sd = s;
@@ -511,6 +528,35 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     RunDev rr = r;
     void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &tile_steps, (void*)&stagger_ns, (void*)&dbg};
     cudaError_t ce = cudaLaunchKernel(kern, dim3(grid), dim3((unsigned)c.block), args, smem, st);
+    ++e->launches; ++e->launches_this_run;
+    return ce != cudaSuccess ? ce : cudaGetLastError();
+}
+
+static cudaError_t launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
+                                  cudaStream_t st)
+{
+    const void* kern = (const void*)k_screen3<3>;
+    int vl_pad = (e->sd.n_steps_max + 3) & ~3;
+    int tk_pad = (e->sd.t_max + 3) & ~3;
+    const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);
+    if (e->s3_smem != smem) {
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ce != cudaSuccess) return ce;
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ, kern, S3_BLOCK, smem);
+        if (ce != cudaSuccess) return ce;
+        if (e->s3_occ < 1) e->s3_occ = 1;
+        e->s3_smem = smem;
+    }
+    const uint64_t ctas_wanted = ((uint64_t)n_items + (S3_BLOCK / 32) - 1) / (S3_BLOCK / 32);   // one item per warp at least
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
+        ctas_wanted, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ));
+    cudaError_t ce = cudaMemsetAsync(e->d_work.p, 0, 4, st);
+    if (ce != cudaSuccess) return ce;
+    ScenarioDev sd = e->sd;
+    RunDev rr = r;
+    rr.work_counter = e->d_work.as<uint32_t>();
+    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad};
+    ce = cudaLaunchKernel(kern, dim3(grid), dim3(S3_BLOCK), args, smem, st);
     ++e->launches; ++e->launches_this_run;
     return ce != cudaSuccess ? ce : cudaGetLastError();
 }
@@ -606,7 +652,18 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
 
     // slices keep the item count of one launch below 2^30
     const bool exact = (run->precision == DCRP_PRECISION_FP64);
-    const uint64_t per_item = exact ? (uint64_t)EXB : screen_chunk();
+    // the slab-first screen serves plain MIXED runs on tracks its per-warp tables hold; everything else
+    // (replay tables, reach culling, sub-step mode, fp32 decisions, long tracks) goes through k_screen2
+    const bool use3 = run->precision == DCRP_PRECISION_MIXED && !r.replay && !r.cull && !r.substep &&
+                      !(run->flags & DCRP_FLAG_SCREEN_2D) && s.n_steps_max <= S3_MAX_VL && s.t_max <= S3_MAX_T;
+    e->run_screen3 = use3;
+    if (use3 && !e->slab_ready && run->trial_count) {
+        k_slab_axis<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s, 4.0f * s.thr_slab);   // once per scenario
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+        e->slab_ready = true;
+    }
+    const uint64_t per_item = exact ? (uint64_t)EXB : (use3 ? (uint64_t)S3_CHW : screen_chunk());
     // DCRP_MAX_ITEMS: test aid, forces the slicing below at small sizes (tests/test_gpu_parity.py)
     static const uint64_t max_items = std::getenv("DCRP_MAX_ITEMS")
         ? std::max<uint64_t>(1, std::strtoull(std::getenv("DCRP_MAX_ITEMS"), nullptr, 10)) : MAX_ITEMS_PER_LAUNCH;
@@ -626,7 +683,8 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
             CU(cudaGetLastError());
         } else {
             r.div_chunks = make_fastdiv(chunks);
-            const cudaError_t ce = launch_screen2(e, r, chunks, n_items, st);
+            const cudaError_t ce = use3 ? launch_screen3(e, r, chunks, n_items, st)
+                                        : launch_screen2(e, r, chunks, n_items, st);
             if (ce != cudaSuccess) return fail(DCRP_ERR_CUDA, "k_screen launch: %s", cudaGetErrorString(ce));
         }
     }
@@ -741,6 +799,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     }
     o.candidates = stats[ST_CANDIDATES];
     o.level2 = stats[ST_LEVEL2];
+    o.slab_survivors = stats[ST_SLAB_SURVIVORS];
     o.hits = stats[ST_HITS];
     o.kernel_launches = e->launches_this_run;
     if (!e->prepare_timed) {

@@ -1,0 +1,359 @@
+// screen3.cu -- k_screen3: the Monte-Carlo screen with a 1-D slab level in front of the 2-D scan.
+//
+// Every (trial, index) separation test is first evaluated along ONE horizontal direction n chosen per
+// (track, drone) pair: |D(i) . n| <= |D_xy(i)| <= |D(i)|, so a trial whose projected separation never
+// drops below R + margin cannot collide at any index.  That costs two packed adds and half an FMNMX3
+// per two tests instead of six packed ops, and with a well-chosen n it clears 90-99 % of the trials
+// (5 km ring: 99 %); the survivors queue up per warp and are re-scanned 128 at a time by the 2-D
+// level-1 scan of kernels.cu (scan_tile_xy), then level 2 (3-D fp32) and level 3 (fp64 confirm) as before.
+// Decisions are those of the all-fp64 kernel by construction: every level is conservative and the last
+// one is exact (tests/test_gpu_parity.py, test_gpu_fuzz.py).
+//
+// No sort: the slab test of an index before the trial's kink (i < t1st) evaluates the stage-2 ray
+// extrapolated backwards, which can only ADD survivors, so all lanes scan the whole track from index 0
+// with warp-uniform bounds and nothing is staged in shared memory per trial.  Warps are independent
+// (no CTA barrier in steady state): each pulls 256-trial items from a device-side counter, keeps its
+// pair's projected track and kink tables in its own shared-memory slice, and keeps its own survivor queue.
+//
+// Reference semantics: /root/reference/Drone.cpp:107-127,164-231,253-265 (restated in dcrp_math.cuh).
+#include "dcrp_device.cuh"
+
+namespace dcrp {
+
+constexpr int S3_NPL = 4;                 // packed pairs per lane in the slab phase
+constexpr int S3_TL = 2 * S3_NPL;         // trials per lane per item
+constexpr int S3_CHW = 32 * S3_TL;        // trials per warp item
+constexpr int S3_RESCAN = 128;            // survivors per 2-D re-scan round (4 per lane = 2 packed pairs)
+constexpr int S3_LIST = S3_RESCAN + S3_CHW;
+constexpr int S3_BLOCK = 256;
+constexpr int S3_MAX_VL = 512;            // longest track the per-warp projected table holds
+constexpr int S3_MAX_T = 128;             // largest takeoff_t the per-warp kink tables hold
+constexpr int S3_REBASE = 128;            // exact re-base of the running position every so many indices
+constexpr int S3_DIRS = 8;                // candidate slab directions k*pi/8
+constexpr int S3_AXIS_TL = 8;             // sample trials per lane of the direction choice (256 per pair)
+
+static_assert(S3_CHW <= 4096, "local trial index is packed in 12 bits");
+
+__host__ __device__ inline size_t s3_warp_smem(int vl_pad, int tk_pad)
+{
+    // [tabk: tk_pad double2][tabT: vl_pad float][list: S3_LIST uint2][tabpn: tk_pad float], 16-B multiple
+    size_t b = (size_t)tk_pad * 16 + (size_t)vl_pad * 4 + (size_t)S3_LIST * 8 + (size_t)tk_pad * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+// Slab direction of every pair, once per scenario: of S3_DIRS candidate directions the one whose slab
+// passes the fewest of 256 deterministic sample trials (at 4x the real threshold, to rank rare events with
+// few samples).  A heuristic only: any unit vector gives the same decisions, just more or fewer survivors.
+__global__ void __launch_bounds__(128) k_slab_axis(const ScenarioDev s, float thr_rank)
+{
+    const int pair = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= s.n_tracks * s.n_drones) return;
+    const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
+    const TrackDev* __restrict__ tk = s.tracks + a;
+    const int VL = tk->n_steps, takeoff_t = tk->takeoff_t;
+    TrackScale ts;
+    ts.wx32 = tk->wx32; ts.wy32 = tk->wy32; ts.wz32 = tk->wz32; ts.z0rel = tk->z0rel;
+    const float2* __restrict__ g = s.trkxy + (size_t)tk->off_xy;
+    float cs[S3_DIRS], sn[S3_DIRS];
+#pragma unroll
+    for (int k = 0; k < S3_DIRS; ++k) sincospif((float)k / (float)S3_DIRS, &sn[k], &cs[k]);
+    uint32_t cnt[S3_DIRS];
+#pragma unroll
+    for (int k = 0; k < S3_DIRS; ++k) cnt[k] = 0;
+#pragma unroll 1
+    for (int m = 0; m < S3_AXIS_TL; ++m) {
+        const U4 w = philox4x32_10((uint32_t)(m * 32 + lane), 0u, (uint32_t)j, (uint32_t)a, 0xA511E9B3u, 0x5AB5A5E1u);
+        const int t1st = draw_t1st(w.x, takeoff_t);
+        const uint4 q = make_uint4(w.y, w.z, w.w, (uint32_t)t1st << 12);
+        const Fast32 u = setup_fast32(s, ts, s.kink + (size_t)pair * s.t_max, s.p1f + (size_t)j * s.t_max, INT_MAX, q);
+        uint32_t bits = 0;
+        if (!u.force) {
+            for (int i = 1; i < VL; ++i) {
+                const float2 p = __ldg(&g[i]);
+                const float fi = (float)i;
+                const float dx = fmaf(fi, u.sx, u.bx) + p.x, dy = fmaf(fi, u.sy, u.by) + p.y;
+#pragma unroll
+                for (int k = 0; k < S3_DIRS; ++k)
+                    if (fabsf(fmaf(cs[k], dx, sn[k] * dy)) < thr_rank) bits |= 1u << k;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < S3_DIRS; ++k) cnt[k] += (uint32_t)__popc(__ballot_sync(0xffffffffu, (bits >> k) & 1u));
+    }
+    int best = 0;
+#pragma unroll
+    for (int k = 1; k < S3_DIRS; ++k) if (cnt[k] < cnt[best]) best = k;
+    float bc = cs[0], bs = sn[0];
+#pragma unroll
+    for (int k = 1; k < S3_DIRS; ++k) if (k == best) { bc = cs[k]; bs = sn[k]; }
+    if (lane == 0) s.slab_dir[pair] = make_float2(bc, bs);
+}
+
+// One survivor of the slab level: level 2 (3-D fp32, fused form) and the candidate append.
+__device__ __forceinline__ void s3_level2(const ScenarioDev& s, const RunDev& r, const TrackDev& tk, int pair, int j,
+                                          int s1_first, uint64_t trial, const uint4 q, uint32_t& npass,
+                                          uint32_t& ncand)
+{
+    ++npass;
+    const Setup32 u = setup_trial32(s, r, tk, pair, j, s1_first, 0, q);
+    if (u.force || min3d_fp32(s, tk, u) < s.thr2_screen) {
+        ++ncand;
+        const uint32_t slot = warp_claim_slot(r.cand_count);
+        if (slot < r.cand_cap) {
+            Candidate cd; cd.pair = (uint32_t)pair; cd.pad = 0; cd.trial = trial;
+            r.cands[slot] = cd;
+        }
+    }
+}
+
+// 2-D level-1 re-scan of n <= S3_RESCAN queued survivors of track a (4 per lane as two packed pairs);
+// the draws are regenerated from the trial id (nothing but (item, local) was kept), the track is read
+// through L1 with warp-uniform addresses.
+__device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
+                                       uint32_t chunks_per_pair)
+{
+    const int lane = (int)lane_id();
+    uint32_t acc_is = 0, npass = 0, ncand = 0;
+    const TrackDev* __restrict__ tk = s.tracks + a;
+    const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
+    TrackScale ts;
+    ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
+    const float2* __restrict__ gtrk = s.trkxy + (size_t)__ldg(&tk->off_xy);
+    constexpr int TR = 4, NP = 2;
+    float bxs[TR], bys[TR], sxs[TR], sys[TR];
+    uint32_t fmask = 0;
+    int tmin = INT_MAX;
+#pragma unroll
+    for (int m = 0; m < TR; ++m) {
+        const int idx = m * 32 + lane;
+        float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
+        if (idx < n) {
+            const uint2 e = list[idx];
+            const int pair = (int)r.div_chunks.div(e.x);
+            const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
+            const int j = pair - a * s.n_drones;
+            const uint64_t trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
+            const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
+                                          r.track_base + (uint32_t)a, r.rk);
+            const int t1st = draw_t1st(w.x, takeoff_t);
+            const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
+            const Fast32 u = setup_fast32(s, ts, s.kink + (size_t)pair * s.t_max, s.p1f + (size_t)j * s.t_max,
+                                          __ldg(&s.s1_first_hit[pair]), q);
+            bx = u.bx; by = u.by; sx = u.sx; sy = u.sy;
+            fmask |= u.force ? (1u << m) : 0u;
+            tmin = min(tmin, t1st);
+        }
+        bxs[m] = bx; bys[m] = by; sxs[m] = sx; sys[m] = sy;
+    }
+    f2_t BX[NP], BY[NP], SX[NP], SY[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        BX[p] = pk2(bxs[2 * p], bxs[2 * p + 1]); BY[p] = pk2(bys[2 * p], bys[2 * p + 1]);
+        SX[p] = pk2(sxs[2 * p], sxs[2 * p + 1]); SY[p] = pk2(sys[2 * p], sys[2 * p + 1]);
+    }
+    const int imin = __reduce_min_sync(0xffffffffu, tmin);
+    if (imin < VL) acc_is += (uint32_t)(VL - imin) * (uint32_t)TR;
+    float mn[TR];
+#pragma unroll
+    for (int m = 0; m < TR; ++m) mn[m] = 3.0e38f;
+    for (int t0 = 0; t0 < VL; t0 += S3_REBASE) {
+        const int lo = max(imin, t0), hi = min(VL, t0 + S3_REBASE);
+        if (lo < hi) {
+            const float lof = (float)lo;
+            const f2_t lo2 = pk2(lof, lof);
+            f2_t PX[NP], PY[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) { PX[p] = ffma2(lo2, SX[p], BX[p]); PY[p] = ffma2(lo2, SY[p], BY[p]); }
+            scan_tile_xy<NP>(gtrk + t0, t0, lo, hi, PX, PY, SX, SY, mn);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < TR; ++m) if (mn[m] < s.thr2_screen) fmask |= 1u << m;
+    if (fmask) {
+#pragma unroll 1
+        for (int m = 0; m < TR; ++m) {
+            if (!((fmask >> m) & 1u)) continue;
+            const int idx = m * 32 + lane;
+            if (idx >= n) continue;
+            const uint2 e = list[idx];
+            const int pair = (int)r.div_chunks.div(e.x);
+            const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
+            const int j = pair - a * s.n_drones;
+            const uint64_t trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
+            const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
+                                          r.track_base + (uint32_t)a, r.rk);
+            const int t1st = draw_t1st(w.x, takeoff_t);
+            const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
+            s3_level2(s, r, *tk, pair, j, __ldg(&s.s1_first_hit[pair]), trial, q, npass, ncand);
+        }
+    }
+    // a rare path (one call per 128 survivors): its own warp-reduced statistics
+    const unsigned long long is = warp_sum_u64(acc_is), np = warp_sum_u64(npass), nc = warp_sum_u64(ncand);
+    if (lane == 0) {
+        atomicAdd(&r.stats[ST_ISSUED], is);
+        if (np) atomicAdd(&r.stats[ST_LEVEL2], np);
+        if (nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
+    }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(S3_BLOCK, MINB)
+k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wb = smem_raw + (size_t)warp * s3_warp_smem(vl_pad, tk_pad);
+    double2* tabk  = reinterpret_cast<double2*>(wb);
+    float*   tabT  = reinterpret_cast<float*>(wb + (size_t)tk_pad * 16);
+    uint2*   list  = reinterpret_cast<uint2*>(wb + (size_t)tk_pad * 16 + (size_t)vl_pad * 4);
+    float*   tabpn = reinterpret_cast<float*>(wb + (size_t)tk_pad * 16 + (size_t)vl_pad * 4 + (size_t)S3_LIST * 8);
+
+    uint32_t acc_t1 = 0, acc_is = 0, nsurv = 0;       // per-lane partial sums
+    int list_n = 0, list_track = -1;       // warp-uniform
+
+    auto grab = [&]() -> uint32_t {
+        uint32_t v = 0;
+        if (lane == 0) v = atomicAdd(r.work_counter, 1u);
+        return __shfl_sync(0xffffffffu, v, 0);
+    };
+
+    uint32_t item = grab();
+    while (item < n_items) {
+        const uint32_t next_item = grab();        // in flight while this item is processed
+        const int pair = (int)r.div_chunks.div(item);
+        const uint32_t c = item - (uint32_t)pair * chunks_per_pair;
+        const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
+        if (a != list_track) {                    // queued survivors share one track: drain before it changes
+            if (list_n) { s3_rescan(s, r, list, list_n, list_track, chunks_per_pair); list_n = 0; }
+            list_track = a;
+        }
+        const TrackDev* __restrict__ tk = s.tracks + a;
+        const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
+        const uint32_t n_valid = (uint32_t)min((uint64_t)S3_CHW, r.slice_count - (uint64_t)c * S3_CHW);
+        const int s1_first = __ldg(&s.s1_first_hit[pair]);
+        const float2 nd = __ldg(&s.slab_dir[pair]);
+        TrackScale ts;
+        ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
+
+        // ---- this pair's tables: projected track T_i = n . (-A_i) (index 0 and the padding never pass),
+        // kink tables (target-box corner minus kink in fp64; kink projected on n)
+        {
+            const float2* __restrict__ g = s.trkxy + (size_t)__ldg(&tk->off_xy);
+            const int vlr = (VL + 3) & ~3;
+            __syncwarp();
+            for (int i = lane; i < vlr; i += 32) {
+                float v = 1e15f;
+                if (i >= 1 && i < VL) { const float2 p = __ldg(&g[i]); v = fmaf(nd.x, p.x, nd.y * p.y); }
+                tabT[i] = v;
+            }
+            for (int t = lane; t < takeoff_t; t += 32) {
+                tabk[t] = __ldg(&s.kink[(size_t)pair * s.t_max + t]);
+                const float2 pl = __ldg(&s.p1f[(size_t)j * s.t_max + t]);
+                tabpn[t] = fmaf(nd.x, pl.x, nd.y * pl.y);
+            }
+            __syncwarp();
+        }
+
+        // ---- draws + slab ray of this lane's S3_TL trials
+        float bn[S3_TL], sn[S3_TL];
+        uint32_t fmask = 0;
+        const uint64_t trial0 = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW;
+#pragma unroll
+        for (int m = 0; m < S3_TL; ++m) {
+            const uint32_t local = (uint32_t)(m * 32 + lane);
+            float b = 1e15f, sv = 0.f;
+            if (local < n_valid) {
+                const uint64_t trial = trial0 + local;
+                const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
+                                              r.track_base + (uint32_t)a, r.rk);
+                const int t1st = draw_t1st(w.x, takeoff_t);
+                const int last = t1st - 1;
+                const double2 kk = tabk[last];
+                const float dls = (float)fma((double)w.y, ts.wx32, kk.x);     // target - kink, rounded once
+                const float dbs = (float)fma((double)w.z, ts.wy32, kk.y);
+                const float ada = fabsf(fmaf((float)w.w, ts.wz32, ts.z0rel));
+                const float m2 = fmaf(dls, dls, dbs * dbs);
+                float inv_m;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_m) : "f"(m2));
+                const float pitch = atan_nonneg(ada * inv_m);                 // Drone.cpp:218
+                const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
+                sv = fmaf(dls, nd.x, dbs * nd.y) * k;                         // n . step
+                b = fmaf(-(float)last, sv, tabpn[last]);                      // n . position(0)
+                if (!(m2 > 1e-12f) || s1_first <= last) fmask |= 1u << m;    // degenerate ray / stage-1 conflict
+                acc_t1 += (uint32_t)t1st;
+                acc_is += (uint32_t)VL;                                       // slab lane-steps of this trial
+            }
+            bn[m] = b; sn[m] = sv;
+        }
+        if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {      // rare: keep the 32-bit partial sums exact
+            atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
+            atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
+            acc_t1 = acc_is = 0;
+        }
+
+        // ---- LEVEL 1a, the slab: min over the indices of |n . D(i)|, D(i) = P(i) - A(i), P(i) = B + i*S
+        f2_t BN[S3_NPL], SN[S3_NPL], PN[S3_NPL];
+#pragma unroll
+        for (int p = 0; p < S3_NPL; ++p) { BN[p] = pk2(bn[2 * p], bn[2 * p + 1]); SN[p] = pk2(sn[2 * p], sn[2 * p + 1]); }
+        float mn[S3_TL];
+#pragma unroll
+        for (int m = 0; m < S3_TL; ++m) mn[m] = 3.0e38f;
+        const float4* __restrict__ t4 = reinterpret_cast<const float4*>(tabT);
+        for (int t0 = 0; t0 < VL; t0 += S3_REBASE) {
+            const float t0f = (float)t0;
+            const f2_t t02 = pk2(t0f, t0f);
+#pragma unroll
+            for (int p = 0; p < S3_NPL; ++p) PN[p] = ffma2(t02, SN[p], BN[p]);      // exact re-base
+            const int nq = (min(VL, t0 + S3_REBASE) - t0 + 3) >> 2;
+#pragma unroll 2
+            for (int k = 0; k < nq; ++k) {
+                const float4 cq = t4[(t0 >> 2) + k];
+#define S3_STEP2(va, vb)                                                                      \
+                {                                                                             \
+                    const f2_t ca_ = pk2((va), (va)), cb_ = pk2((vb), (vb));                  \
+                    _Pragma("unroll") for (int p_ = 0; p_ < S3_NPL; ++p_) {                   \
+                        const float2 d0_ = up2(fadd2(PN[p_], ca_));                           \
+                        PN[p_] = fadd2(PN[p_], SN[p_]);                                       \
+                        const float2 d1_ = up2(fadd2(PN[p_], cb_));                           \
+                        PN[p_] = fadd2(PN[p_], SN[p_]);                                       \
+                        mn[2 * p_] = fminf(fminf(mn[2 * p_], fabsf(d0_.x)), fabsf(d1_.x));    \
+                        mn[2 * p_ + 1] = fminf(fminf(mn[2 * p_ + 1], fabsf(d0_.y)), fabsf(d1_.y)); \
+                    }                                                                         \
+                }
+                S3_STEP2(cq.x, cq.y)
+                S3_STEP2(cq.z, cq.w)
+#undef S3_STEP2
+            }
+        }
+
+        // ---- survivors -> this warp's queue (item, local); a full round of them goes through the 2-D scan
+        uint32_t pass = fmask;
+#pragma unroll
+        for (int m = 0; m < S3_TL; ++m) if (mn[m] < s.thr_slab) pass |= 1u << m;
+        if (__any_sync(0xffffffffu, pass != 0u)) {
+#pragma unroll
+            for (int m = 0; m < S3_TL; ++m) {
+                const bool on = (pass >> m) & 1u;
+                const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                if (on) list[list_n + __popc(bal & ((1u << lane) - 1u))] = make_uint2(item, (uint32_t)(m * 32 + lane));
+                list_n += __popc(bal);
+            }
+            nsurv += (uint32_t)__popc(pass);
+            __syncwarp();
+            while (list_n >= S3_RESCAN) {
+                list_n -= S3_RESCAN;
+                s3_rescan(s, r, list + list_n, S3_RESCAN, list_track, chunks_per_pair);
+                __syncwarp();
+            }
+        }
+        item = next_item;
+    }
+    if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair);
+
+    flush_stats(r, 0, acc_t1, acc_is, 0, 0);
+    const unsigned long long ns = warp_sum_u64(nsurv);
+    if (lane == 0 && ns) atomicAdd(&r.stats[ST_SLAB_SURVIVORS], ns);
+}
+
+}  // namespace dcrp

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DCRP_ABI_VERSION 3
+#define DCRP_ABI_VERSION 4
 
 /* status codes */
 #define DCRP_OK               0
@@ -63,6 +63,10 @@ extern "C" {
                                      count is 0 by the bound, no draws are made).  Counts, colliding trial
                                      ids and records are identical to the un-culled run; stats report what
                                      was computed (tests_issued) and what the bound decided (tests_culled). */
+
+#define DCRP_FLAG_SCREEN_2D   8u  /* MIXED mode: skip the 1-D slab level and put every trial through the sorted
+                                     2-D level-1 scan (the round-1 kernel, k_screen2).  Same results; for A/B
+                                     measurements and as a cross-check of the two screens.                    */
 
 typedef struct dcrp_engine dcrp_engine;
 
@@ -162,6 +166,9 @@ typedef struct dcrp_stats {
                                   exact for the pairs that ran (there tests_evaluated + tests_culled =
                                   sum of n_steps - t1st), the GUARANTEED minimum n_steps - takeoff_t per
                                   trial for the cleared pairs; never part of tests_evaluated             */
+    uint64_t slab_survivors;   /* MIXED runs through the slab-first screen: trials the 1-D slab level could not
+                                  clear and queued for the 2-D level-1 re-scan (0 when every trial goes through
+                                  the 2-D scan: DCRP_FLAG_SCREEN_2D, replay, culling, sub-step, long tracks)  */
 } dcrp_stats;
 
 /* Result buffers (host, caller-owned).  counts is required; the rest optional. */

@@ -75,10 +75,17 @@ def test_random_shapes_mixed_and_cull_equal_fp64(engine, tracks, ring1, ring5, c
     ref = engine.simulate(trks, drones, precision=capi.FP64, **kw)
     if ref.overflow:
         pytest.skip("more hits than the record buffer: counts-only case")
-    mixed = engine.simulate(trks, drones, precision=capi.MIXED, **kw)
+    mixed = engine.simulate(trks, drones, precision=capi.MIXED, **kw)                  # slab-first screen where eligible
+    mixed2d = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_SCREEN_2D, **kw)   # sorted 2-D screen
     cull = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_REACH_CULL, **kw)
     _same(ref, mixed, "mixed")
+    _same(ref, mixed2d, "mixed, 2-D screen")
     _same(ref, cull, "cull")
+    assert mixed2d.stats["slab_survivors"] == 0
+    eligible = max(t["n_steps"] for t in trks) <= 512 and max(t["takeoff_t"] for t in trks) <= 128
+    if eligible:      # every trial the later levels see is a slab survivor
+        assert mixed.stats["slab_survivors"] >= mixed.stats["level2"] >= mixed.stats["candidates"] >= ref.hits
+    mixed = mixed2d
     # (with takeoff_t > 64 a t1st bucket holds several values and its internal order comes from atomics:
     # the issued lane-steps then vary by a few warp-steps from run to run)
     assert cull.stats["tests_issued"] <= mixed.stats["tests_issued"] * 1.01 + 4096
