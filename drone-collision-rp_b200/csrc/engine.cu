@@ -112,7 +112,7 @@ struct dcrp_engine {
     PinnedBuf h_scn;
     DevBuf d_p1x, d_p1y, d_s1fh, d_s1pm, d_kink, d_p1f, d_s1sub_pm, d_s1sub_fs, d_s1sub_ft;
     DevBuf d_reach, d_alive, d_reach_tot;
-    DevBuf d_slab_dir, d_work;     // k_screen3: slab direction per pair; the launch's work-item counter
+    DevBuf d_slab_dir;             // k_screen3: slab direction per pair
     bool slab_ready = false;       // k_slab_axis has run for the current scenario
     size_t s3_smem = 0;
     int s3_occ = 0;
@@ -127,7 +127,7 @@ struct dcrp_engine {
     uint32_t launches_this_run = 0;
     uint64_t h2d_run = 0;
     // per-run outputs live in ONE device arena read back by ONE D2H copy into a pinned mirror:
-    //   [rec_count, cand_count, pad | stats[ST_COUNT] | counts[n_pairs] | first_conflict[n_pairs]]
+    //   [rec_count, cand_count, work_counter, pad | stats[ST_COUNT] | counts[n_pairs] | first_conflict[n_pairs]]
     DevBuf d_out;
     PinnedBuf h_out;
     size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;
@@ -211,7 +211,7 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
                       &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
                       &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2, &e->d_reach, &e->d_alive, &e->d_reach_tot,
-                      &e->d_slab_dir, &e->d_work};
+                      &e->d_slab_dir};
     for (DevBuf* b : bufs) b->release();
     e->h_scn.release();
     e->h_out.release();
@@ -433,7 +433,6 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     CU(e->d_alive.need(sizeof(uint32_t) * n_pairs));
     CU(e->d_reach_tot.need(sizeof(unsigned long long) * 2));
     CU(e->d_slab_dir.need(sizeof(float2) * n_pairs));
-    CU(e->d_work.need(256));
     CU(cudaEventRecord(e->ev_a, st));
     CU(cudaMemcpyAsync(e->d_scn.p, hb, scn_bytes, cudaMemcpyHostToDevice, st));
     e->h2d_scenario = scn_bytes;
@@ -550,11 +549,13 @@ static cudaError_t launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chun
     const uint64_t ctas_wanted = ((uint64_t)n_items + (S3_BLOCK / 32) - 1) / (S3_BLOCK / 32);   // one item per warp at least
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
         ctas_wanted, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ));
-    cudaError_t ce = cudaMemsetAsync(e->d_work.p, 0, 4, st);
+    // the first launch of a run finds the counter cleared by k_run_init (word 2 of the output arena)
+    cudaError_t ce = cudaSuccess;
+    if (r.slice_first != 0) ce = cudaMemsetAsync(e->d_out.as<uint32_t>() + 2, 0, 4, st);
     if (ce != cudaSuccess) return ce;
     ScenarioDev sd = e->sd;
     RunDev rr = r;
-    rr.work_counter = e->d_work.as<uint32_t>();
+    rr.work_counter = e->d_out.as<uint32_t>() + 2;
     void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad};
     ce = cudaLaunchKernel(kern, dim3(grid), dim3(S3_BLOCK), args, smem, st);
     ++e->launches; ++e->launches_this_run;
@@ -689,7 +690,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         }
     }
     CU(cudaEventRecord(e->ev_trials, st));
-    if (run->precision == DCRP_PRECISION_MIXED && run->trial_count) {
+    if (run->precision == DCRP_PRECISION_MIXED && run->trial_count && !use3) {    // k_screen3 confirms in-kernel
         // grid-stride over the candidate list whose length lives on the device
         k_confirm_all<<<e->prop.multiProcessorCount * 4, 128, 0, st>>>(s, r);
         ++e->launches; ++e->launches_this_run;

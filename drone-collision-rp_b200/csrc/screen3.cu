@@ -5,7 +5,8 @@
 // drops below R + margin cannot collide at any index.  That costs two packed adds and half an FMNMX3
 // per two tests instead of six packed ops, and with a well-chosen n it clears 90-99 % of the trials
 // (5 km ring: 99 %); the survivors queue up per warp and are re-scanned 128 at a time by the 2-D
-// level-1 scan of kernels.cu (scan_tile_xy), then level 2 (3-D fp32) and level 3 (fp64 confirm) as before.
+// level-1 scan of kernels.cu (scan_tile_xy), then level 2 (3-D fp32) and level 3 (the fp64 decision in the
+// reference's order of operations, one warp per candidate) -- all inside this one kernel.
 // Decisions are those of the all-fp64 kernel by construction: every level is conservative and the last
 // one is exact (tests/test_gpu_parity.py, test_gpu_fuzz.py).
 //
@@ -90,21 +91,19 @@ __global__ void __launch_bounds__(128) k_slab_axis(const ScenarioDev s, float th
     if (lane == 0) s.slab_dir[pair] = make_float2(bc, bs);
 }
 
-// One survivor of the slab level: level 2 (3-D fp32, fused form) and the candidate append.
-__device__ __forceinline__ void s3_level2(const ScenarioDev& s, const RunDev& r, const TrackDev& tk, int pair, int j,
-                                          int s1_first, uint64_t trial, const uint4 q, uint32_t& npass,
-                                          uint32_t& ncand)
+// LEVEL 3 inside the screen kernel: the fp64 decision of ONE candidate by the whole warp (exact_any_warp:
+// the reference's order of operations, lanes = indices), with warp-uniform arguments.  Candidates are
+// ~3e-7 of the trials, so confirming them where they are found costs nothing measurable and saves the
+// candidate list, a kernel launch and its ~10 us of latency per run.
+__device__ __noinline__ uint32_t s3_confirm(const ScenarioDev& s, const RunDev& r, int pair, uint64_t trial)
 {
-    ++npass;
-    const Setup32 u = setup_trial32(s, r, tk, pair, j, s1_first, 0, q);
-    if (u.force || min3d_fp32(s, tk, u) < s.thr2_screen) {
-        ++ncand;
-        const uint32_t slot = warp_claim_slot(r.cand_count);
-        if (slot < r.cand_cap) {
-            Candidate cd; cd.pair = (uint32_t)pair; cd.pad = 0; cd.trial = trial;
-            r.cands[slot] = cd;
-        }
-    }
+    const int lane = (int)lane_id();
+    const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
+    const TrackDev t = s.tracks[a];
+    const Draw d = make_draw(r.seed, trial, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a, t.takeoff_t, t.box);
+    const TrialOut o = exact_any_warp(s, r, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d, lane);
+    if (o.first >= 0 && lane == 0) publish_hit(s, r, pair, a, j, trial, d, o);
+    return o.first >= 0 ? 1u : 0u;
 }
 
 // 2-D level-1 re-scan of n <= S3_RESCAN queued survivors of track a (4 per lane as two packed pairs);
@@ -170,22 +169,39 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
     }
 #pragma unroll
     for (int m = 0; m < TR; ++m) if (mn[m] < s.thr2_screen) fmask |= 1u << m;
-    if (fmask) {
+    // ---- rare: LEVEL 2 (3-D fp32, fused form) of the flagged trials, then LEVEL 3 (fp64) of what survives
+    uint32_t hits = 0;
+    if (__any_sync(0xffffffffu, fmask != 0u)) {
 #pragma unroll 1
         for (int m = 0; m < TR; ++m) {
-            if (!((fmask >> m) & 1u)) continue;
             const int idx = m * 32 + lane;
-            if (idx >= n) continue;
-            const uint2 e = list[idx];
-            const int pair = (int)r.div_chunks.div(e.x);
-            const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
-            const int j = pair - a * s.n_drones;
-            const uint64_t trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
-            const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
-                                          r.track_base + (uint32_t)a, r.rk);
-            const int t1st = draw_t1st(w.x, takeoff_t);
-            const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
-            s3_level2(s, r, *tk, pair, j, __ldg(&s.s1_first_hit[pair]), trial, q, npass, ncand);
+            bool cand = false;
+            int pair = 0;
+            uint64_t trial = 0;
+            if (((fmask >> m) & 1u) && idx < n) {
+                const uint2 e = list[idx];
+                pair = (int)r.div_chunks.div(e.x);
+                const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
+                const int j = pair - a * s.n_drones;
+                trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
+                const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
+                                              r.track_base + (uint32_t)a, r.rk);
+                const int t1st = draw_t1st(w.x, takeoff_t);
+                const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
+                ++npass;
+                const Setup32 u = setup_trial32(s, r, *tk, pair, j, __ldg(&s.s1_first_hit[pair]), 0, q);
+                cand = u.force || min3d_fp32(s, *tk, u) < s.thr2_screen;
+                ncand += cand ? 1u : 0u;
+            }
+            uint32_t bal = __ballot_sync(0xffffffffu, cand);
+            while (bal) {                              // one candidate at a time, the whole warp on it
+                const int src = __ffs((int)bal) - 1;
+                bal &= bal - 1u;
+                const int cp = __shfl_sync(0xffffffffu, pair, src);
+                const uint64_t ct = __shfl_sync(0xffffffffu, (unsigned long long)trial, src);
+                const uint32_t h = s3_confirm(s, r, cp, ct);
+                if (lane == 0) hits += h;
+            }
         }
     }
     // a rare path (one call per 128 survivors): its own warp-reduced statistics
@@ -194,6 +210,7 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
         atomicAdd(&r.stats[ST_ISSUED], is);
         if (np) atomicAdd(&r.stats[ST_LEVEL2], np);
         if (nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
+        if (hits) atomicAdd(&r.stats[ST_HITS], (unsigned long long)hits);
     }
 }
 
@@ -201,7 +218,7 @@ template <int MINB>
 __global__ void __launch_bounds__(S3_BLOCK, MINB)
 k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wb = smem_raw + (size_t)warp * s3_warp_smem(vl_pad, tk_pad);
     double2* tabk  = reinterpret_cast<double2*>(wb);
@@ -255,37 +272,40 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             __syncwarp();
         }
 
-        // ---- draws + slab ray of this lane's S3_TL trials
+        // ---- draws + slab ray of this lane's S3_TL trials.  Branch-free: the slots past a ragged last item
+        // compute a (harmless) trial beyond the range and are masked afterwards.
         float bn[S3_TL], sn[S3_TL];
-        uint32_t fmask = 0;
-        const uint64_t trial0 = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW;
+        uint32_t fmask = 0, t1s = 0;               // item-local: the run-long accumulators are touched once per item
+        const uint64_t trial0 = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + (uint32_t)lane;
+        const uint32_t t0lo = (uint32_t)trial0, t0hi = (uint32_t)(trial0 >> 32);
+        const uint32_t pj = r.drone_base + (uint32_t)j, pa = r.track_base + (uint32_t)a;
 #pragma unroll
         for (int m = 0; m < S3_TL; ++m) {
-            const uint32_t local = (uint32_t)(m * 32 + lane);
-            float b = 1e15f, sv = 0.f;
-            if (local < n_valid) {
-                const uint64_t trial = trial0 + local;
-                const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
-                                              r.track_base + (uint32_t)a, r.rk);
-                const int t1st = draw_t1st(w.x, takeoff_t);
-                const int last = t1st - 1;
-                const double2 kk = tabk[last];
-                const float dls = (float)fma((double)w.y, ts.wx32, kk.x);     // target - kink, rounded once
-                const float dbs = (float)fma((double)w.z, ts.wy32, kk.y);
-                const float ada = fabsf(fmaf((float)w.w, ts.wz32, ts.z0rel));
-                const float m2 = fmaf(dls, dls, dbs * dbs);
-                float inv_m;
-                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_m) : "f"(m2));
-                const float pitch = atan_nonneg(ada * inv_m);                 // Drone.cpp:218
-                const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
-                sv = fmaf(dls, nd.x, dbs * nd.y) * k;                         // n . step
-                b = fmaf(-(float)last, sv, tabpn[last]);                      // n . position(0)
-                if (!(m2 > 1e-12f) || s1_first <= last) fmask |= 1u << m;    // degenerate ray / stage-1 conflict
-                acc_t1 += (uint32_t)t1st;
-                acc_is += (uint32_t)VL;                                       // slab lane-steps of this trial
-            }
-            bn[m] = b; sn[m] = sv;
+            const bool valid = (uint32_t)(m * 32 + lane) < n_valid;
+            const uint32_t c0 = t0lo + (uint32_t)(m * 32);
+            const U4 w = philox4x32_10_rk(c0, t0hi + (c0 < t0lo ? 1u : 0u), pj, pa, r.rk);
+            const int t1st = draw_t1st(w.x, takeoff_t);
+            const int last = t1st - 1;
+            const double2 kk = tabk[last];
+            const float dls = (float)fma((double)w.y, ts.wx32, kk.x);     // target - kink, rounded once
+            const float dbs = (float)fma((double)w.z, ts.wy32, kk.y);
+            const float ada = fabsf(fmaf((float)w.w, ts.wz32, ts.z0rel));
+            const float m2 = fmaf(dls, dls, dbs * dbs);
+            float inv_m;
+            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_m) : "f"(m2));
+            const float pitch = atan_nonneg(ada * inv_m);                 // Drone.cpp:218
+            const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
+            const float sv = fmaf(dls, nd.x, dbs * nd.y) * k;             // n . step
+            const float b = fmaf(-(float)last, sv, tabpn[last]);          // n . position(0)
+            const bool force = !(m2 > 1e-12f) || s1_first <= last;        // degenerate ray / stage-1 conflict
+            fmask |= (valid && force) ? (1u << m) : 0u;
+            t1s += valid ? (uint32_t)t1st : 0u;
+            bn[m] = valid ? b : 1e15f;
+            sn[m] = valid ? sv : 0.f;
         }
+        const uint32_t nv = n_valid > (uint32_t)lane ? (n_valid - (uint32_t)lane + 31u) >> 5 : 0u;   // this lane's valid slots
+        acc_t1 += t1s;
+        acc_is += nv * (uint32_t)VL;                 // slab lane-steps of this lane's trials
         if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {      // rare: keep the 32-bit partial sums exact
             atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
             atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
