@@ -17,6 +17,7 @@ FLAG_PER_TRIAL = 1
 FLAG_SUBSTEP = 2
 FLAG_REACH_CULL = 4
 FLAG_SCREEN_2D = 8
+STAT_SCENARIO_CACHED, STAT_FP64_FALLBACK, STAT_CULL_IGNORED = 1, 2, 4
 INT32_MAX = 2**31 - 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -65,7 +66,7 @@ class Stats(C.Structure):
     _fields_ = [("trials", C.c_uint64), ("tests_evaluated", C.c_uint64), ("tests_shared", C.c_uint64),
                 ("tests_issued", C.c_uint64), ("drone_steps", C.c_uint64), ("level2", C.c_uint64),
                 ("candidates", C.c_uint64),
-                ("hits", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("hits", C.c_uint64), ("kernel_launches", C.c_uint32), ("status", C.c_uint32),
                 ("ms_prepare", C.c_float), ("ms_trials", C.c_float), ("ms_confirm", C.c_float),
                 ("ms_device_total", C.c_float), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("trials_culled", C.c_uint64), ("tests_culled", C.c_uint64), ("slab_survivors", C.c_uint64)]
@@ -98,7 +99,8 @@ DCRP_SYMBOLS = [
     "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_device_count", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
 ]
 DCRP_HOST_SYMBOLS = [
-    "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_ring_write",
+    "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_synth_day_write_mixed",
+    "dcrph_ring_write",
     "dcrph_aircraft_load",
     "dcrph_ring_row", "dcrph_monte_carlo", "dcrph_monte_carlo_batch", "dcrph_set_run_flags", "dcrph_set_gpus", "dcrph_write_block",
 ]
@@ -151,6 +153,7 @@ def host():
         H.dcrph_last_error.restype = C.c_char_p
         H.dcrph_reference_aircraft_csv.restype = C.c_char_p
         H.dcrph_synth_day_write.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_int]
+        H.dcrph_synth_day_write_mixed.argtypes = [C.c_char_p, C.c_int, C.c_uint64, C.c_int, C.c_int]
         H.dcrph_ring_write.argtypes = [C.c_char_p, C.c_double, C.c_int]
         H.dcrph_aircraft_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_int), c_double_p, c_double_p, c_double_p, c_double_p,

@@ -106,6 +106,9 @@ struct dcrp_engine {
     dcrp_model model{};
     float ms_prepare = 0.f;
     uint64_t h2d_scenario = 0;
+    // what the resident scenario was built from (dcrp_simulate skips the upload when the caller passes it again)
+    std::vector<dcrp_drone> h_drones;
+    size_t scn_o_ax = 0, scn_o_ay = 0, scn_o_az = 0;
     // inputs live in ONE device arena filled by ONE H2D copy from a pinned mirror:
     //   [tracks | ax | ay | az | trk32 | drones], each segment 256-B aligned
     DevBuf d_scn;
@@ -130,8 +133,10 @@ struct dcrp_engine {
     //   [rec_count, cand_count, work_counter, pad | stats[ST_COUNT] | counts[n_pairs] | first_conflict[n_pairs]]
     DevBuf d_out;
     PinnedBuf h_out;
-    size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;
-    DevBuf d_records, d_cands, d_replay;
+    size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;     // out_bytes: the part before the records
+    uint32_t run_status = 0;       // DCRP_STAT_* bits of the current run (reported in dcrp_stats.status)
+    bool reuse_device_replay = false;   // dcrp_fetch's fp64 fallback: d_replay already holds the run's table
+    DevBuf d_cands, d_replay;      // (records live in the tail of d_out)
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
     // launch configuration caches (per engine = per device: function attributes are per device)
     size_t screen_smem[4] = {0, 0, 0, 0};
@@ -147,6 +152,22 @@ struct dcrp_engine {
     DevBuf d_scratch;    // peak kernels / draws / trajectories
     DevBuf d_flush;      // 256 MB written by dcrp_flush_l2 (> 126 MB of L2)
 };
+
+// Records kept in the first D2H copy of a fetch (one copy, one sync for the usual handful of hits).
+constexpr uint32_t INLINE_RECORDS = 32;
+
+// Sizes the per-run output arena: [rec_count, cand_count, work_counter, pad | stats | counts | first_conflict]
+// (cleared by k_run_init) followed by rec_cap records.
+static cudaError_t size_out_arena(dcrp_engine* e, size_t n_pairs)
+{
+    e->out_counts_off = align256(16 + sizeof(unsigned long long) * ST_COUNT);
+    e->out_first_off = align256(e->out_counts_off + sizeof(uint64_t) * n_pairs);
+    e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
+    cudaError_t ce = e->d_out.need(e->out_bytes + sizeof(Record) * (size_t)e->rec_cap);
+    if (ce != cudaSuccess) return ce;
+    return e->h_out.need(e->out_bytes + sizeof(Record) * (size_t)std::min(e->rec_cap, INLINE_RECORDS));
+}
+static Record* out_records(dcrp_engine* e) { return reinterpret_cast<Record*>(e->d_out.as<unsigned char>() + e->out_bytes); }
 
 static uint32_t* small_rec_count(dcrp_engine* e) { return e->d_out.as<uint32_t>(); }
 static uint32_t* small_cand_count(dcrp_engine* e) { return e->d_out.as<uint32_t>() + 1; }
@@ -207,7 +228,7 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_s1sub_pm, &e->d_s1sub_fs,
-                      &e->d_s1sub_ft, &e->d_out, &e->d_records,
+                      &e->d_s1sub_ft, &e->d_out,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
                       &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
                       &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2, &e->d_reach, &e->d_alive, &e->d_reach_tot,
@@ -293,6 +314,13 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         d.wy32 = (t.box[3] - t.box[2]) * (1.0 / 4294967296.0);
         d.wz32 = (float)((t.box[5] - t.box[4]) * (1.0 / 4294967296.0));
         d.z0rel = (float)(t.box[4] - model->start_alt);
+        {   // default slab direction (screen3.cu): where the aircraft goes after take-off
+            const int i0 = std::min(t.takeoff_t, t.n_steps) - 1;
+            double ux = t.x[t.n_steps - 1] - t.x[i0], uy = t.y[t.n_steps - 1] - t.y[i0];
+            const double um = std::hypot(ux, uy);
+            if (!(um > 1e-6) || !std::isfinite(um)) { ux = 1.0; uy = 0.0; } else { ux /= um; uy /= um; }
+            d.dir0x = (float)ux; d.dir0y = (float)uy;
+        }
         total += (uint64_t)t.n_steps;
         if (total > (1ull << 31)) return fail(DCRP_ERR_INVALID, "tracks too long in total");
         t_max = std::max(t_max, t.takeoff_t);
@@ -468,8 +496,36 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     e->prepare_timed = false;
     e->sd = s;
     e->model = *model;
+    e->h_drones.assign(drones, drones + n_drones);
+    e->scn_o_ax = o_ax; e->scn_o_ay = o_ay; e->scn_o_az = o_az;
     e->has_scenario = true;
     return DCRP_OK;
+}
+
+// Is the resident scenario bit for bit what the caller passes (again)?  Exact comparison against the
+// pinned mirror of the last upload -- memory-speed, no hashing, no false positives.
+static bool scenario_is_resident(const dcrp_engine* e, const dcrp_track* tracks, int32_t n_tracks,
+                                 const dcrp_drone* drones, int32_t n_drones, const dcrp_model* model)
+{
+    if (!e->has_scenario || !tracks || !drones || !model) return false;
+    if (n_tracks != e->sd.n_tracks || n_drones != e->sd.n_drones) return false;
+    if (std::memcmp(model, &e->model, sizeof *model) != 0) return false;
+    if (std::memcmp(drones, e->h_drones.data(), sizeof(dcrp_drone) * (size_t)n_drones) != 0) return false;
+    const unsigned char* hb = e->h_scn.as<unsigned char>();
+    const double* hx = reinterpret_cast<const double*>(hb + e->scn_o_ax);
+    const double* hy = reinterpret_cast<const double*>(hb + e->scn_o_ay);
+    const double* hz = reinterpret_cast<const double*>(hb + e->scn_o_az);
+    for (int a = 0; a < n_tracks; ++a) {
+        const dcrp_track& t = tracks[a];
+        const TrackDev& d = e->h_tracks[(size_t)a];
+        if (!t.x || !t.y || !t.z || t.n_steps != d.n_steps || t.takeoff_t != d.takeoff_t) return false;
+        if (std::memcmp(t.box, d.box, sizeof d.box) != 0) return false;
+        const size_t bytes = sizeof(double) * (size_t)t.n_steps;
+        if (std::memcmp(t.x, hx + d.off, bytes) != 0 || std::memcmp(t.y, hy + d.off, bytes) != 0 ||
+            std::memcmp(t.z, hz + d.off, bytes) != 0)
+            return false;
+    }
+    return true;
 }
 
 // ------------------------------------------------------------------ run
@@ -589,12 +645,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     e->rec_cap = run->record_capacity ? run->record_capacity : DEFAULT_RECORD_CAP;
     e->external_counts = (d_counts != nullptr);
 
-    e->out_counts_off = align256(16 + sizeof(unsigned long long) * ST_COUNT);
-    e->out_first_off = align256(e->out_counts_off + sizeof(uint64_t) * n_pairs);
-    e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
-    CU(e->d_out.need(e->out_bytes));
-    CU(e->h_out.need(e->out_bytes));
-    CU(e->d_records.need(sizeof(Record) * (size_t)e->rec_cap));
+    CU(size_out_arena(e, n_pairs));
     CU(e->d_cands.need(sizeof(Candidate) * (size_t)CAND_CAP));
     if (st != e->stream) CU(cudaStreamWaitEvent(st, e->ev_b, 0));   // after the scenario upload + stage 1
 
@@ -604,16 +655,32 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     r.replay = nullptr;
     if (run->replay && run->trial_count) {
         const size_t bytes = sizeof(Draw) * n_pairs * (size_t)run->trial_count;
-        CU(e->d_replay.need(bytes));
-        CU(cudaMemcpyAsync(e->d_replay.p, run->replay, bytes, cudaMemcpyHostToDevice, st));
-        e->h2d_run += bytes;
+        if (!e->reuse_device_replay) {
+            // The kernels index per-pair tables with t1st: a row from another track's table (or garbage) must be
+            // DCRP_ERR_INVALID here, not an out-of-bounds access on the device.
+            for (size_t p = 0; p < n_pairs; ++p) {
+                const int tk = e->h_tracks[p / (size_t)s.n_drones].takeoff_t;
+                const dcrp_draw* row = run->replay + p * (size_t)run->trial_count;
+                for (uint64_t k = 0; k < run->trial_count; ++k) {
+                    const dcrp_draw& d = row[k];
+                    if (d.t1st < 1 || d.t1st > tk || !std::isfinite(d.tx) || !std::isfinite(d.ty) || !std::isfinite(d.tz))
+                        return fail(DCRP_ERR_INVALID,
+                                    "replay table: row %llu of pair %zu has t1st=%d (must be in [1, takeoff_t=%d]) or a "
+                                    "non-finite target", (unsigned long long)k, p, d.t1st, tk);
+                }
+            }
+            CU(e->d_replay.need(bytes));
+            CU(cudaMemcpyAsync(e->d_replay.p, run->replay, bytes, cudaMemcpyHostToDevice, st));
+            e->h2d_run += bytes;
+        }
+        e->reuse_device_replay = false;
         r.replay = e->d_replay.as<Draw>();
     }
     unsigned long long* own_counts =
         reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + e->out_counts_off);
     r.counts = d_counts ? reinterpret_cast<unsigned long long*>(d_counts) : own_counts;
     r.first_conflict = reinterpret_cast<int32_t*>(e->d_out.as<unsigned char>() + e->out_first_off);
-    r.records = e->d_records.as<Record>();
+    r.records = out_records(e);
     r.rec_count = small_rec_count(e);
     r.rec_cap = e->rec_cap;
     r.cands = e->d_cands.as<Candidate>();
@@ -627,6 +694,8 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     r.cull = ((run->flags & DCRP_FLAG_REACH_CULL) && run->precision == DCRP_PRECISION_MIXED && !r.substep &&
               !(run->flags & DCRP_FLAG_PER_TRIAL) && !run->replay) ? 1 : 0;
     e->run_cull = r.cull != 0;
+    e->run_status &= DCRP_STAT_FP64_FALLBACK;      // (set by dcrp_fetch just before it re-runs in fp64)
+    if ((run->flags & DCRP_FLAG_REACH_CULL) && !r.cull) e->run_status |= DCRP_STAT_CULL_IGNORED;
     if (r.cull && !e->reach_ready) {
         CU(cudaMemsetAsync(e->d_reach_tot.p, 0, sizeof(unsigned long long) * 2, st));
         k_reach<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s);      // one warp per pair, once per scenario
@@ -658,8 +727,10 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     const bool use3 = run->precision == DCRP_PRECISION_MIXED && !r.replay && !r.cull && !r.substep &&
                       !(run->flags & DCRP_FLAG_SCREEN_2D) && s.n_steps_max <= S3_MAX_VL && s.t_max <= S3_MAX_T;
     e->run_screen3 = use3;
-    if (use3 && !e->slab_ready && run->trial_count) {
-        k_slab_axis<<<(unsigned)((n_pairs + 3) / 4), 128, 0, st>>>(s, 4.0f * s.thr_slab);   // once per scenario
+    // the per-pair choice of the slab direction costs ~10 us plus 256 sample trials per pair: worth it from a few
+    // 1e4 trials per pair on (Drone::Simulation's 10 000-trial calls keep the per-track default)
+    if (use3 && !e->slab_ready && run->trial_count >= 20000) {
+        k_slab_axis<<<(unsigned)n_pairs, 128, 0, st>>>(s, 4.0f * s.thr_slab);   // once per scenario
         ++e->launches; ++e->launches_this_run;
         CU(cudaGetLastError());
         e->slab_ready = true;
@@ -719,8 +790,9 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     cudaStream_t st = e->run_stream;
     const ScenarioDev& s = e->sd;
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
-    // one D2H copy of the whole output arena into its pinned mirror
-    CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, e->out_bytes, cudaMemcpyDeviceToHost, st));
+    // one D2H copy of the output arena and the first few records into the pinned mirror
+    const uint32_t inl = res->records ? std::min(e->rec_cap, INLINE_RECORDS) : 0u;
+    CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, e->out_bytes + sizeof(Record) * (size_t)inl, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     const unsigned char* small = e->h_out.as<unsigned char>();
     uint32_t rec_count, cand_count;
@@ -728,7 +800,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     std::memcpy(&rec_count, small, 4);
     std::memcpy(&cand_count, small + 4, 4);
     std::memcpy(stats, small + 16, sizeof stats);
-    uint64_t d2h = e->out_bytes;
+    uint64_t d2h = e->out_bytes + sizeof(Record) * (size_t)inl;
 
     if (e->run.precision == DCRP_PRECISION_MIXED && cand_count > CAND_CAP) {
         // More candidates than the list holds (absurd hit rates, e.g. a huge radius):
@@ -737,10 +809,14 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
             return fail(DCRP_ERR_STATE, "candidate list overflow with caller-owned counts: rerun with DCRP_PRECISION_FP64");
         dcrp_run again = e->run;
         again.precision = DCRP_PRECISION_FP64;
+        e->reuse_device_replay = again.replay != nullptr;   // the table is already in d_replay: the caller's copy may be gone
+        e->run_status = DCRP_STAT_FP64_FALLBACK;
         int rc = dcrp_run_async(e, &again, (void*)st, nullptr);
-        if (rc != DCRP_OK) return rc;
+        if (rc != DCRP_OK) { e->run_status = 0; return rc; }
         e->run.precision = DCRP_PRECISION_MIXED;   // report what was asked for
-        return dcrp_fetch(e, res);
+        rc = dcrp_fetch(e, res);
+        e->run_status = 0;
+        return rc;
     }
 
     if (res->counts && !e->external_counts) {
@@ -754,8 +830,11 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     if (res->records) {
         const uint32_t n = std::min(rec_count, e->rec_cap);
         if (n) {
-            CU(cudaMemcpy(res->records, e->d_records.p, sizeof(Record) * (size_t)n, cudaMemcpyDeviceToHost));
-            d2h += sizeof(Record) * (size_t)n;
+            std::memcpy(res->records, small + e->out_bytes, sizeof(Record) * (size_t)std::min(n, inl));
+            if (n > inl) {      // more hits than travel with the first copy
+                CU(cudaMemcpy(res->records + inl, out_records(e) + inl, sizeof(Record) * (size_t)(n - inl), cudaMemcpyDeviceToHost));
+                d2h += sizeof(Record) * (size_t)(n - inl);
+            }
             std::sort(res->records, res->records + n, [](const dcrp_record& a, const dcrp_record& b) {
                 if (a.track != b.track) return a.track < b.track;
                 if (a.drone != b.drone) return a.drone < b.drone;
@@ -803,6 +882,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     o.slab_survivors = stats[ST_SLAB_SURVIVORS];
     o.hits = stats[ST_HITS];
     o.kernel_launches = e->launches_this_run;
+    o.status = e->run_status;
     if (!e->prepare_timed) {
         CU(cudaEventElapsedTime(&e->ms_prepare, e->ev_a, e->ev_b));
         e->prepare_timed = true;
@@ -825,7 +905,11 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
     static const bool timing = std::getenv("DCRP_HOST_TIMING") != nullptr;     // profiling aid (tools/e2e_breakdown.py)
     using clk = std::chrono::steady_clock;
     const clk::time_point t0 = clk::now();
-    int rc = dcrp_scenario_upload(e, tracks, n_tracks, drones, n_drones, model);
+    if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
+    // Drone::Simulation calls this once per (aircraft, drone) with the same arrays, a bench once per step:
+    // the scenario already in HBM (tables of stage 1 included) is reused when the inputs are unchanged.
+    const bool cached = scenario_is_resident(e, tracks, n_tracks, drones, n_drones, model);
+    int rc = cached ? DCRP_OK : dcrp_scenario_upload(e, tracks, n_tracks, drones, n_drones, model);
     if (rc != DCRP_OK) return rc;
     const clk::time_point t1 = clk::now();
     rc = dcrp_run_async(e, run, nullptr, nullptr);
@@ -833,7 +917,8 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
     const clk::time_point t2 = clk::now();
     rc = dcrp_fetch(e, result);
     if (rc != DCRP_OK) return rc;
-    result->stats.h2d_bytes += e->h2d_scenario;
+    if (cached) result->stats.status |= DCRP_STAT_SCENARIO_CACHED;
+    else        result->stats.h2d_bytes += e->h2d_scenario;
     if (timing) {
         const clk::time_point t3 = clk::now();
         auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
@@ -874,12 +959,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     e->external_counts = false;
     e->rec_cap = run->record_capacity ? run->record_capacity : DEFAULT_RECORD_CAP;
 
-    e->out_counts_off = align256(16 + sizeof(unsigned long long) * ST_COUNT);
-    e->out_first_off = align256(e->out_counts_off + sizeof(uint64_t) * n_pairs);
-    e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
-    CU(e->d_out.need(e->out_bytes));
-    CU(e->h_out.need(e->out_bytes));
-    CU(e->d_records.need(sizeof(Record) * (size_t)e->rec_cap));
+    CU(size_out_arena(e, n_pairs));
     constexpr uint32_t L2_CAP = 1u << 22;
     const size_t hist_bytes = sizeof(uint32_t) * ((size_t)s.n_drones * run->ref_takeoff_t + 1);
     CU(e->d_ap_hist.need(hist_bytes));
@@ -896,7 +976,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     r.drone_base = run->drone_id_base;
     r.counts = reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + e->out_counts_off);
     r.first_conflict = reinterpret_cast<int32_t*>(e->d_out.as<unsigned char>() + e->out_first_off);
-    r.records = e->d_records.as<Record>();
+    r.records = out_records(e);
     r.rec_count = small_rec_count(e);
     r.rec_cap = e->rec_cap;
     r.cand_count = small_cand_count(e);

@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(128) k_stage1(const ScenarioDev s)
         s.s1_first_hit[pair] = first;
         s.s1sub_first_seg[pair] = sfirst;
         s.s1sub_first_time[pair] = stime;
+        s.slab_dir[pair] = make_float2(t.dir0x, t.dir0y);   // refined by k_slab_axis when a run is large enough to pay for it
     }
 }
 

@@ -22,7 +22,7 @@ using namespace std;
 static void usage(const char* argv0)
 {
     cout << "usage: " << argv0 << " [--aircraft-csv F] [--drone-csv F] [--aircraft N] [--drones N]\n"
-            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS] [--batch [--gpus N]] [--cull]\n"
+            "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS [--arrival-every K]] [--batch [--gpus N]] [--cull]\n"
             "defaults are the reference's constants (Monte_Carlo.cpp:11-18,28,33)\n";
 }
 
@@ -40,7 +40,7 @@ int main(int argc, char** argv)
     int number_runs = 10000;         // Monte_Carlo.cpp:33
     uint64_t seed = 20170630ull;
     int precision = DCRP_PRECISION_MIXED;
-    int synthetic = 0;
+    int synthetic = 0, arrival_every = 0;
     bool batch = false;          // one GPU launch for all (aircraft, drone) pairs instead of one per pair
     int n_gpus = 1;              // --gpus N (0 = all): --batch only, trial ranges split over the devices of this process
     uint32_t run_flags = 0;      // --cull: DCRP_FLAG_REACH_CULL (exact culling by reachability, same results)
@@ -58,6 +58,7 @@ int main(int argc, char** argv)
         else if (a == "--runs") number_runs = atoi(next("--runs"));
         else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
         else if (a == "--synthetic") synthetic = atoi(next("--synthetic"));
+        else if (a == "--arrival-every") arrival_every = atoi(next("--arrival-every"));
         else if (a == "--batch") batch = true;
         else if (a == "--cull") run_flags |= DCRP_FLAG_REACH_CULL;
         else if (a == "--gpus") n_gpus = atoi(next("--gpus"));
@@ -73,7 +74,7 @@ int main(int argc, char** argv)
     if (synthetic > 0) {
         ifstream probe(FilePath_aircraft);
         if (!probe) {
-            if (dcrp_host::write_synthetic_day(FilePath_aircraft, synthetic, seed, true) != 0) {
+            if (dcrp_host::write_synthetic_day_mixed(FilePath_aircraft, synthetic, seed, true, arrival_every) != 0) {
                 cout << "ERROR - cannot write " << FilePath_aircraft << endl;
                 return 1;
             }

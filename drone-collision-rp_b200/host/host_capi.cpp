@@ -24,6 +24,17 @@ extern "C" int dcrph_synth_day_write(const char* path, int n_flights, uint64_t s
     return 0;
 }
 
+extern "C" int dcrph_synth_day_write_mixed(const char* path, int n_flights, uint64_t seed, int trailing_dummy,
+                                          int arrival_every)
+{
+    if (!path || n_flights <= 0 || arrival_every < 0) { g_host_err = "bad arguments"; return -1; }
+    if (dcrp_host::write_synthetic_day_mixed(path, n_flights, seed, trailing_dummy != 0, arrival_every) != 0) {
+        g_host_err = std::string("cannot write ") + path;
+        return -6;
+    }
+    return 0;
+}
+
 extern "C" int dcrph_ring_write(const char* path, double radius_m, int n_rows)
 {
     if (!path) { g_host_err = "path is NULL"; return -1; }

@@ -27,6 +27,47 @@ struct SplitMix64 {
 
 int write_synthetic_day(const std::string& path, int n_flights, uint64_t seed, bool trailing_dummy)
 {
+    return write_synthetic_day_mixed(path, n_flights, seed, trailing_dummy, 0);
+}
+
+// One arrival (Drone.cpp:47-52: first altitude != 0 selects the arrival box of Drone.cpp:138-141,152-155):
+// a 3-degree approach to runway 27L / 27R from the east at constant speed, touchdown near the eastern
+// threshold, roll-out with the on-ground flag set.  Aircraft::Takeoff_Time (Aircraft.cpp:102-110) then
+// yields the number of airborne rows minus one, i.e. the drone kinks while the aircraft is on approach.
+static void write_arrival(FILE* f, SplitMix64& rng, int k, long& row)
+{
+    const int n = rng.range(92, 105);
+    const int air = rng.range(40, 60);                    // airborne rows before touchdown
+    const bool north = (k & 1) != 0;
+    const double centre = north ? 5705983.0 : 5704545.0;
+    const double northing0 = centre + (rng.unit() * 16.0 - 8.0);
+    const double vapp = 66.0 + 8.0 * rng.unit();          // approach speed, m/s
+    const double sink = vapp * 0.0524;                    // 3 degree glide path
+    const double decel = 1.8 + 0.6 * rng.unit();
+    const double drift = rng.unit() - 0.5;
+    const double touchdown = 678300.0 + (rng.unit() * 60.0 - 30.0);
+    double easting = touchdown + vapp * (double)air;
+    double v = vapp;
+    char callsign[16];
+    std::snprintf(callsign, sizeof callsign, "ARR%04d", k);
+    for (int i = 0; i < n; ++i, ++row) {
+        const bool on_ground = i >= air;
+        const double alt = on_ground ? 0.0 : sink * (double)(air - i);
+        const double northing = northing0 + (on_ground ? 0.0 : drift * (double)(air - i));
+        std::fprintf(f, "%ld,2017-06-30 %02d:%02d:%02d,4ca%03x,%s,XXXX,EGLL,A320,", row, 4 + (k / 60) % 20, k % 60,
+                     i % 60, k & 0xfff, callsign);
+        if (on_ground) std::fprintf(f, "0,");
+        else std::fprintf(f, "%.3f,", alt);
+        std::fprintf(f, "%.3f,270.0,%.1f,1000,False,%.3f,%.3f,%s,%ld,%d,%.3f,False,%d,%d\n", v * 1.943844,
+                     on_ground ? 0.0 : -sink * 196.85, northing, easting, on_ground ? "True" : "False",
+                     1498795200L + row, 4 + (k / 60) % 20, alt, k, k + 1);
+        if (on_ground) { v -= decel; if (v < 8.0) v = 8.0; }
+        easting -= v;
+    }
+}
+
+int write_synthetic_day_mixed(const std::string& path, int n_flights, uint64_t seed, bool trailing_dummy, int arrival_every)
+{
     FILE* f = std::fopen(path.c_str(), "w");
     if (!f) return -1;
     // 22 header cells; only columns 3, 7, 8, 13, 14, 15 are ever read (Aircraft.cpp:14-24)
@@ -37,6 +78,10 @@ int write_synthetic_day(const std::string& path, int n_flights, uint64_t seed, b
     long row = 0;
     for (int k = 0; k < total; ++k) {
         SplitMix64 rng(seed * 0x100000001B3ull + (uint64_t)k * 0x9E3779B97F4A7C15ull + 1);
+        if (arrival_every > 0 && k < n_flights && (k % arrival_every) == arrival_every - 1) {
+            write_arrival(f, rng, k, row);
+            continue;
+        }
         const int n = rng.range(92, 105);
         const int ground = rng.range(24, 34);
         const bool north = (k & 1) != 0;                      // 27R when odd, 27L when even

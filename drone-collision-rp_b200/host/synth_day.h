@@ -24,6 +24,13 @@ extern const char* const kReferenceAircraftCsv;
 // Returns 0, or -1 if the file cannot be written.
 int write_synthetic_day(const std::string& path, int n_flights, uint64_t seed, bool trailing_dummy);
 
+// The same day with every `arrival_every`-th flight (k % arrival_every == arrival_every - 1) replaced by an
+// ARRIVAL: airborne first row (altitude != 0, so Drone.cpp:47-52 selects the arrival box of
+// Drone.cpp:138-141,152-155), 3-degree approach from the east to 27L / 27R, 40..60 airborne rows, then the
+// roll-out with the on-ground flag set.  arrival_every = 0 writes departures only (identical to the above).
+int write_synthetic_day_mixed(const std::string& path, int n_flights, uint64_t seed, bool trailing_dummy,
+                              int arrival_every);
+
 // Drone start ring in the format of drone_inital_positions_{1km,5km}.csv (header
 // ",longitude,latitude,heading", rows "k,easting,northing,heading", CRLF): n_rows points on a circle of
 // `radius_m` metres about the Heathrow reference point, row k at true bearing 2*pi*k/(n_rows-1) from it

@@ -24,8 +24,10 @@ def load_ring(path=RING_1KM, n=DRONE_TOTAL, total_cols=DRONE_COLS):
     return out
 
 
-def write_synthetic_day(path, n_flights, seed=SYNTH_DAY_SEED, trailing_dummy=True):
-    capi._hcheck(capi.host().dcrph_synth_day_write(path.encode(), int(n_flights), int(seed), int(trailing_dummy)))
+def write_synthetic_day(path, n_flights, seed=SYNTH_DAY_SEED, trailing_dummy=True, arrival_every=0):
+    """arrival_every=K > 0 makes every K-th flight an arrival (first altitude != 0)."""
+    capi._hcheck(capi.host().dcrph_synth_day_write_mixed(path.encode(), int(n_flights), int(seed),
+                                                         int(trailing_dummy), int(arrival_every)))
     return path
 
 
@@ -47,12 +49,12 @@ def load_flight(path, index, n_cols=AIRCRAFT_COLS, cap=65536):
             "takeoff_t": tk.value, "n_steps": vl.value}
 
 
-def synthetic_tracks(workdir, n_flights, seed=SYNTH_DAY_SEED):
+def synthetic_tracks(workdir, n_flights, seed=SYNTH_DAY_SEED, arrival_every=0):
     """Write a synthetic day under workdir and load its first n_flights tracks."""
     os.makedirs(workdir, exist_ok=True)
-    path = os.path.join(workdir, "synthetic_day_%d_%d.csv" % (n_flights, seed))
+    path = os.path.join(workdir, "synthetic_day_%d_%d_%d.csv" % (n_flights, seed, arrival_every))
     if not os.path.exists(path):
-        write_synthetic_day(path, n_flights, seed, True)
+        write_synthetic_day(path, n_flights, seed, True, arrival_every)
     return [load_flight(path, i) for i in range(n_flights)], path
 
 

@@ -139,6 +139,14 @@ typedef struct dcrp_record {
                                   segment + t in [0,1) with DCRP_FLAG_SUBSTEP                         */
 } dcrp_record;
 
+/* dcrp_stats.status bits */
+#define DCRP_STAT_SCENARIO_CACHED 1u  /* dcrp_simulate: tracks/drones/model equal the resident scenario bit for bit;
+                                         nothing was validated, packed or uploaded again (h2d_bytes counts 0 for it) */
+#define DCRP_STAT_FP64_FALLBACK   2u  /* MIXED run: the candidate list overflowed (absurd hit rates) and the whole
+                                         run was redone by the fp64 kernel -- same answers, ~4x the time             */
+#define DCRP_STAT_CULL_IGNORED    4u  /* DCRP_FLAG_REACH_CULL was set but does not apply to this run (FP64 / FP32
+                                         precision, per-trial outputs, replay table, sub-step mode): un-culled run   */
+
 typedef struct dcrp_stats {
     uint64_t trials;           /* trials simulated                                                    */
     uint64_t tests_evaluated;  /* stage-2 (trial, index) separation tests the kernels computed:
@@ -152,7 +160,8 @@ typedef struct dcrp_stats {
     uint64_t candidates;       /* trials level 2 passed on to the fp64 confirm (level 3)              */
     uint64_t hits;             /* total collisions                                                    */
     uint32_t kernel_launches;  /* engine kernels launched by the call                                 */
-    uint32_t reserved;
+    uint32_t status;           /* DCRP_STAT_* bits: what the engine did differently from what was asked,
+                                  or did not have to do (never an error; results are the same)           */
     float    ms_prepare;       /* stage-1 / per-pair tables                                           */
     float    ms_trials;        /* trial kernel(s): screen or exact                                    */
     float    ms_confirm;       /* fp64 confirm of candidates                                          */

@@ -23,6 +23,10 @@ const char* dcrph_reference_aircraft_csv(void);      /* Monte_Carlo.cpp:11 file 
 
 /* Seeded synthetic ADS-B day in the reference's 22-column schema (synth_day.h). */
 int dcrph_synth_day_write(const char* path, int n_flights, uint64_t seed, int trailing_dummy);
+/* The same with every arrival_every-th flight an ARRIVAL (first altitude != 0: the depart_or_arrive = 1
+ * branch of Drone.cpp:47-52,138-141,152-155); arrival_every = 0 writes departures only. */
+int dcrph_synth_day_write_mixed(const char* path, int n_flights, uint64_t seed, int trailing_dummy,
+                                int arrival_every);
 
 /* Drone start ring of any radius in the format of drone_inital_positions_{1km,5km}.csv (synth_day.h). */
 int dcrph_ring_write(const char* path, double radius_m, int n_rows);

@@ -73,6 +73,13 @@ void orc_make_draw(uint64_t seed, uint64_t trial, uint32_t drone, uint32_t track
     out->tz = u3 * (box[5] - box[4]) + box[4];
 }
 
+/* n consecutive trials' draws (the replay table of one (track, drone) pair) */
+void orc_make_draws(uint64_t seed, uint64_t trial_begin, int64_t n, uint32_t drone, uint32_t track,
+                    int32_t takeoff_t, const double box[6], orc_draw* out)
+{
+    for (int64_t r = 0; r < n; ++r) orc_make_draw(seed, trial_begin + (uint64_t)r, drone, track, takeoff_t, box, out + r);
+}
+
 /* --------------------------------------------------------------- target box */
 int orc_target_box(double ay0, double az0, double box[6])
 {

@@ -60,6 +60,8 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  * (libstdc++ uniform_real_distribution form, Drone.cpp:175-187). */
 void orc_make_draw(uint64_t seed, uint64_t trial, uint32_t drone, uint32_t track,
                    int32_t takeoff_t, const double box[6], orc_draw* out);
+void orc_make_draws(uint64_t seed, uint64_t trial_begin, int64_t n, uint32_t drone, uint32_t track,
+                    int32_t takeoff_t, const double box[6], orc_draw* out);
 
 /* Drone::CubedVolume, Drone.cpp:129-161 (+ depart_or_arrive, Drone.cpp:47-52).
  * box = {min_long,max_long,min_lat,max_lat,min_alt,max_alt}.  Returns 0, or -1

@@ -50,6 +50,7 @@ class Oracle:
         L.orc_default_model.argtypes = [C.POINTER(Model)]
         L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         L.orc_make_draw.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, dp, C.c_void_p]
+        L.orc_make_draws.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int32, dp, C.c_void_p]
         L.orc_target_box.argtypes = [C.c_double, C.c_double, dp]
         L.orc_run_trials.restype = C.c_int64
         L.orc_run_trials.argtypes = [dp, dp, dp, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_void_p,
@@ -85,9 +86,8 @@ class Oracle:
     def draws(self, seed, trial_begin, n, drone, track, takeoff_t, box):
         out = np.zeros(n, dtype=DRAW_DTYPE)
         b = np.ascontiguousarray(box, dtype=np.float64)
-        for r in range(n):
-            self.L.orc_make_draw(int(seed), int(trial_begin + r), int(drone), int(track), int(takeoff_t), _d(b),
-                                 out.ctypes.data + r * 32)
+        self.L.orc_make_draws(int(seed), int(trial_begin), int(n), int(drone), int(track), int(takeoff_t), _d(b),
+                              out.ctypes.data)
         return out
 
     def run_trials(self, trk, drone, draws, model=None):

@@ -1,0 +1,71 @@
+"""GPU tier: BASELINE configs[1] -- the configuration bench.py times -- at FULL size against the reference.
+5 km ring x the bench's synthetic departure x 101 011 trials per drone = 1.0e7 trials (SURVEY 8(d) C2,
+/root/reference/Drone.cpp:253-265 is the semantic under test).  Counts are near-vacuous at 5 km (2 hits in
+1.0e7 trials), so the comparison is per trial: the GPU's Philox table is dumped, replayed through the
+UNMODIFIED reference (oracle/_ref, forked over the host cores; the C restatement when _ref did not travel),
+and the fp64 kernel's flag / first-hit index (bit-exact) and minimum distance (<= 1e-9 m) are compared for
+ALL 1.0e7 trials; the mixed path's counts and colliding ids against the same; and both against the committed
+answers of the reference (tests/golden/ref_config2_5km.json, made by tests/golden/make_config2_fixture.py)."""
+import hashlib
+import tempfile
+
+import numpy as np
+import pytest
+
+import config2_common as c2
+import drone_collision_rp_b200 as pk
+from drone_collision_rp_b200 import capi, scenario
+
+pytestmark = pytest.mark.gpu
+POS_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def workload():
+    with tempfile.TemporaryDirectory() as tmp:
+        tracks, _ = scenario.synthetic_tracks(tmp, 1)       # exactly bench.py's workload()
+    return tracks[0], scenario.load_ring(pk.RING_5KM)
+
+
+def test_config2_full_size_vs_reference(engine, workload):
+    import oracle_api as oa
+
+    t, ring = workload
+    fx = c2.load_fixture()
+    n = c2.TRIALS_PER_DRONE
+    assert c2.track_digest(t) == fx["track_sha256"] and fx["trials_per_drone"] == n and fx["seed"] == c2.SEED
+
+    engine.upload([t], ring)
+    draws = [engine.dump_draws(0, j, c2.SEED, 0, n) for j in range(c2.N_DRONES)]
+    for j in range(c2.N_DRONES):          # the GPU's table is the table the fixture was made on
+        assert hashlib.sha256(draws[j].tobytes()).hexdigest() == fx["per_drone"][j]["draws_sha256"], j
+
+    f64 = engine.simulate([t], ring, seed=c2.SEED, trial_count=n, precision=capi.FP64, flags=capi.FLAG_PER_TRIAL)
+    g_hit, g_first, g_min = (f64.per_trial[k] for k in ("hit", "first_hit", "min_dist"))
+
+    # ---- live: every one of the 1.0e7 trials against the unmodified reference on the same draws
+    hit, first, mind = c2.replay_all(t, ring, draws, use_ref=oa.RefReplay.available())
+    assert np.array_equal(g_hit, hit)
+    assert np.array_equal(g_first, first)
+    assert np.abs(g_min - mind).max() < POS_TOL
+    assert int(hit.sum()) == fx["total_hits"]
+
+    # ---- committed answers of the reference
+    for j, p in enumerate(fx["per_drone"]):
+        assert int(g_hit[j].sum()) == p["hits"], j
+        assert c2.per_trial_digest(g_hit[j], g_first[j]) == p["sha256_hit_first"], j
+        assert abs(g_min[j].min() - p["min_dist_min"]) < POS_TOL
+        assert abs(g_min[j].sum() - p["min_dist_sum"]) < n * POS_TOL
+        for k, d in p["closest"]:
+            assert abs(g_min[j, k] - d) < POS_TOL, (j, k)
+    want = sorted((c["drone"], c["trial"], c["first_hit"]) for c in fx["collisions"])
+    assert sorted((int(r["drone"]), int(r["trial"]), int(r["first_hit"])) for r in f64.records) == want
+
+    # ---- the mixed path (what bench.py times): slab-first and 2-D screens
+    for flags in (0, capi.FLAG_SCREEN_2D, capi.FLAG_REACH_CULL):
+        mx = engine.simulate([t], ring, seed=c2.SEED, trial_count=n, precision=capi.MIXED, flags=flags)
+        assert np.array_equal(mx.counts, hit.sum(axis=1).astype(np.uint64)), flags
+        assert sorted((int(r["drone"]), int(r["trial"]), int(r["first_hit"])) for r in mx.records) == want, flags
+        for r in mx.records:
+            c = next(c for c in fx["collisions"] if c["drone"] == r["drone"] and c["trial"] == r["trial"])
+            assert abs(r["min_dist"] - c["min_dist"]) < POS_TOL
