@@ -11,7 +11,8 @@ import numpy as np
 from . import LIBDCRP, LIBDCRP_HOST
 
 OK = 0
-ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RUNWAY, ERR_STATE, ERR_IO = -1, -2, -3, -4, -5, -6
+ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RUNWAY, ERR_STATE, ERR_IO, ERR_COMM = -1, -2, -3, -4, -5, -6, -7
+COMM_NCCL_ONLY = 1
 FP64, MIXED, FP32 = 0, 1, 2
 FLAG_PER_TRIAL = 1
 FLAG_SUBSTEP = 2
@@ -96,6 +97,7 @@ DCRP_SYMBOLS = [
     "dcrp_abi_version", "dcrp_last_error", "dcrp_default_model", "dcrp_engine_create",
     "dcrp_engine_destroy", "dcrp_target_box", "dcrp_simulate", "dcrp_scenario_upload",
     "dcrp_run_async", "dcrp_fetch", "dcrp_last_run_ms", "dcrp_allpairs", "dcrp_dump_draws", "dcrp_trajectories",
+    "dcrp_comm_unique_id", "dcrp_engine_attach_comm", "dcrp_engine_detach_comm", "dcrp_allreduce_counts", "dcrp_comm_info",
     "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_device_count", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
 ]
 DCRP_HOST_SYMBOLS = [
@@ -131,6 +133,11 @@ def lib():
         L.dcrp_last_run_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.dcrp_dump_draws.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(Run), C.c_void_p]
         L.dcrp_trajectories.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, c_double_p, C.POINTER(C.c_int32)]
+        L.dcrp_comm_unique_id.argtypes = [C.c_void_p]
+        L.dcrp_engine_attach_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32]
+        L.dcrp_engine_detach_comm.argtypes = [C.c_void_p]
+        L.dcrp_allreduce_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dcrp_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.dcrp_measure_peak.argtypes = [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_float)]
         L.dcrp_flush_l2.argtypes = [C.c_void_p, C.c_void_p]
         L.dcrp_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -324,6 +331,27 @@ class Engine:
         self.n_tracks, self.n_drones = len(T), len(D)
         return self._wrap(res, counts, first, recs, per, n_pairs, run.trial_count)
 
+    def prepared_simulate(self, scenario, precision=MIXED, flags=0, record_capacity=4096, seed=20170630, model=None):
+        """dcrp_simulate with everything marshalled ONCE: returns call(trial_begin, trial_count) -> (counts, n_records,
+        stats struct).  The per-call work is the C call itself (what a C/C++ caller pays); buffers are reused."""
+        T, D = scenario.T, scenario.D
+        m = model or default_model()
+        run = self._run_struct(seed, 0, 0, precision, flags, record_capacity)
+        n_pairs = len(T) * len(D)
+        res, counts, first, recs, per = self._result_buffers(n_pairs, run)
+        fn, h, nT, nD = lib().dcrp_simulate, self._h, len(T), len(D)
+        pm, prun, pres = C.byref(m), C.byref(run), C.byref(res)
+        self.n_tracks, self.n_drones = nT, nD
+
+        def call(trial_begin, trial_count):
+            run.trial_begin, run.trial_count = trial_begin, trial_count
+            counts.fill(0)
+            _check(fn(h, T, nT, D, nD, pm, prun, pres))
+            return counts, res.n_records, res.stats
+
+        call.keep = (T, D, m, run, res, counts, first, recs, scenario)
+        return call
+
     def upload(self, tracks, drones=None, model=None):
         if isinstance(tracks, Scenario):
             T, D = tracks.T, tracks.D
@@ -381,6 +409,29 @@ class Engine:
         if len(recs):
             _check(lib().dcrp_trajectories(self._h, recs.ctypes.data, len(recs), dptr(xyz), C.byref(stride)))
         return xyz
+
+    # ---- multi-process exchange
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        _check(lib().dcrp_comm_unique_id(buf))
+        return buf.raw
+
+    def attach_comm(self, unique_id, rank, nranks, flags=0):
+        assert len(unique_id) == 128
+        _check(lib().dcrp_engine_attach_comm(self._h, C.c_char_p(unique_id), int(rank), int(nranks), int(flags)))
+
+    def detach_comm(self):
+        _check(lib().dcrp_engine_detach_comm(self._h))
+
+    def allreduce_counts(self, stream=None, d_counts=None):
+        _check(lib().dcrp_allreduce_counts(self._h, C.c_void_p(stream or 0), C.c_void_p(d_counts or 0)))
+
+    def comm_info(self):
+        a = (C.c_int32 * 8)()
+        _check(lib().dcrp_comm_info(self._h, a))
+        return {"attached": bool(a[0]), "rank": a[1], "nranks": a[2], "peer_memory": bool(a[3]), "nccl_version": a[4],
+                "allreduces_peer_memory": a[5], "allreduces_nccl": a[6], "peer_timeout": bool(a[7])}
 
     def measure_peak(self, which):
         tf, ms = C.c_double(), C.c_float()

@@ -20,6 +20,7 @@
 
 #include "kernels.cu"
 #include "screen3.cu"
+#include "comm.cu"
 
 using namespace dcrp;
 
@@ -96,7 +97,7 @@ struct dcrp_engine {
     int device = 0;
     cudaDeviceProp prop{};
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_trials = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_k0 = nullptr, ev_trials = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
     uint64_t launches = 0;
 
     // scenario
@@ -135,6 +136,7 @@ struct dcrp_engine {
     PinnedBuf h_out;
     size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;     // out_bytes: the part before the records
     uint32_t run_status = 0;       // DCRP_STAT_* bits of the current run (reported in dcrp_stats.status)
+    Comm* comm = nullptr;          // dcrp_engine_attach_comm
     bool reuse_device_replay = false;   // dcrp_fetch's fp64 fallback: d_replay already holds the run's table
     DevBuf d_cands, d_replay;      // (records live in the tail of d_out)
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
@@ -212,7 +214,8 @@ extern "C" int dcrp_engine_create(int device, dcrp_engine** out)
         return fail(DCRP_ERR_NO_DEVICE, "device %d is sm_%d%d; libdcrp is built for sm_100a only", device, maj, mn);
     }
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&e->ev_begin) != cudaSuccess || cudaEventCreate(&e->ev_trials) != cudaSuccess ||
+        cudaEventCreate(&e->ev_begin) != cudaSuccess || cudaEventCreate(&e->ev_k0) != cudaSuccess ||
+        cudaEventCreate(&e->ev_trials) != cudaSuccess ||
         cudaEventCreate(&e->ev_end) != cudaSuccess || cudaEventCreate(&e->ev_a) != cudaSuccess ||
         cudaEventCreate(&e->ev_b) != cudaSuccess) {
         delete e;
@@ -222,11 +225,14 @@ extern "C" int dcrp_engine_create(int device, dcrp_engine** out)
     return DCRP_OK;
 }
 
+extern "C" int dcrp_engine_detach_comm(dcrp_engine* e);
+
 extern "C" int dcrp_engine_destroy(dcrp_engine* e)
 {
     if (!e) return DCRP_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    dcrp_engine_detach_comm(e);
     DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_s1sub_pm, &e->d_s1sub_fs,
                       &e->d_s1sub_ft, &e->d_out,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
@@ -236,7 +242,7 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     for (DevBuf* b : bufs) b->release();
     e->h_scn.release();
     e->h_out.release();
-    cudaEventDestroy(e->ev_begin); cudaEventDestroy(e->ev_trials); cudaEventDestroy(e->ev_end);
+    cudaEventDestroy(e->ev_begin); cudaEventDestroy(e->ev_k0); cudaEventDestroy(e->ev_trials); cudaEventDestroy(e->ev_end);
     cudaEventDestroy(e->ev_a); cudaEventDestroy(e->ev_b);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -735,6 +741,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         CU(cudaGetLastError());
         e->slab_ready = true;
     }
+    CU(cudaEventRecord(e->ev_k0, st));       // ms_trials starts here: the trial kernel(s) alone
     const uint64_t per_item = exact ? (uint64_t)EXB : (use3 ? (uint64_t)S3_CHW : screen_chunk());
     // DCRP_MAX_ITEMS: test aid, forces the slicing below at small sizes (tests/test_gpu_parity.py)
     static const uint64_t max_items = std::getenv("DCRP_MAX_ITEMS")
@@ -793,7 +800,16 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     // one D2H copy of the output arena and the first few records into the pinned mirror
     const uint32_t inl = res->records ? std::min(e->rec_cap, INLINE_RECORDS) : 0u;
     CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, e->out_bytes + sizeof(Record) * (size_t)inl, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    {   // short runs: poll (a blocking sync wakes up 10-20 us late, a tenth of a 1e7-trial run); long runs: block
+        const auto t0 = std::chrono::steady_clock::now();
+        cudaError_t q;
+        while ((q = cudaStreamQuery(st)) == cudaErrorNotReady &&
+               std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(2)) {}
+        if (q == cudaErrorNotReady) q = cudaStreamSynchronize(st);
+        if (q != cudaSuccess) return fail(DCRP_ERR_CUDA, "waiting for the run failed: %s", cudaGetErrorString(q));
+    }
+    if (e->comm && e->comm->h_err && *e->comm->h_err)
+        return fail(DCRP_ERR_COMM, "count exchange: a peer rank did not deliver its counts within 10 s");
     const unsigned char* small = e->h_out.as<unsigned char>();
     uint32_t rec_count, cand_count;
     unsigned long long stats[ST_COUNT];
@@ -889,7 +905,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     }
     o.ms_prepare = e->ms_prepare;
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_trials)); o.ms_trials = ms;
+    CU(cudaEventElapsedTime(&ms, e->ev_k0, e->ev_trials)); o.ms_trials = ms;
     CU(cudaEventElapsedTime(&ms, e->ev_trials, e->ev_end));   o.ms_confirm = ms;
     CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));    o.ms_device_total = ms;
     o.h2d_bytes = e->h2d_run;
@@ -1009,6 +1025,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4));
     ++e->launches; ++e->launches_this_run;
     CU(cudaGetLastError());
+    CU(cudaEventRecord(e->ev_k0, st));
     CU(cudaMemsetAsync(ap.hist, 0, hist_bytes, st));
     if (n_rays) {
         const unsigned rb = (unsigned)((n_rays + 255) / 256);
@@ -1113,6 +1130,156 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(xyz, d_xyz, xyz_bytes, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
+    return DCRP_OK;
+}
+
+// ------------------------------------------------------------------ multi-process exchange (comm.cu)
+#define NC(call)                                                                                      \
+    do {                                                                                              \
+        ncclResult_t r__ = (call);                                                                    \
+        if (r__ != ncclSuccess)                                                                       \
+            return fail(DCRP_ERR_COMM, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r__), \
+                        __FILE__, __LINE__);                                                          \
+    } while (0)
+
+extern "C" int dcrp_comm_unique_id(void* out128)
+{
+    if (!out128) return fail(DCRP_ERR_INVALID, "dcrp_comm_unique_id: out is NULL");
+    static_assert(sizeof(ncclUniqueId) == DCRP_UNIQUE_ID_BYTES, "unique id size");
+    if (!nccl_api().load()) return fail(DCRP_ERR_COMM, "NCCL is not available: %s", nccl_api().error.c_str());
+    ncclUniqueId id;
+    NC(nccl_api().GetUniqueId(&id));
+    std::memcpy(out128, &id, sizeof id);
+    return DCRP_OK;
+}
+
+extern "C" int dcrp_engine_detach_comm(dcrp_engine* e)
+{
+    if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
+    Comm* c = e->comm;
+    if (!c) return DCRP_OK;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();        // our last sum has seen every peer's last push: nobody writes here any more
+    for (int r = 0; r < c->nranks; ++r)
+        if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->mailbox) cudaFree(c->mailbox);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    delete c;
+    e->comm = nullptr;
+    return DCRP_OK;
+}
+
+extern "C" int dcrp_engine_attach_comm(dcrp_engine* e, const void* unique_id128, int rank, int nranks, uint32_t flags)
+{
+    if (!e || !unique_id128) return fail(DCRP_ERR_INVALID, "dcrp_engine_attach_comm: NULL argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DCRP_ERR_INVALID, "rank %d of %d ranks", rank, nranks);
+    if (e->comm) return fail(DCRP_ERR_STATE, "a communicator is already attached (dcrp_engine_detach_comm first)");
+    if (!nccl_api().load()) return fail(DCRP_ERR_COMM, "NCCL is not available: %s", nccl_api().error.c_str());
+    CU(cudaSetDevice(e->device));
+    Comm* c = new (std::nothrow) Comm();
+    if (!c) return fail(DCRP_ERR_INVALID, "out of host memory");
+    c->rank = rank; c->nranks = nranks;
+    if (nccl_api().GetVersion) nccl_api().GetVersion(&c->nccl_version);
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id128, sizeof id);
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.blocking = 1;
+    cfg.minCTAs = 1; cfg.maxCTAs = 1;       // a few KB of counters: one CTA, so the kernel can find room beside a trial grid
+    ncclResult_t nr = nccl_api().CommInitRankConfig(&c->comm, nranks, id, rank, &cfg);
+    if (nr != ncclSuccess) {
+        delete c;
+        return fail(DCRP_ERR_COMM, "ncclCommInitRankConfig failed: %s", nccl_api().GetErrorString(nr));
+    }
+    e->comm = c;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->h_err), sizeof(uint32_t), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->d_err), c->h_err, 0) != cudaSuccess) {
+        dcrp_engine_detach_comm(e);
+        return fail(DCRP_ERR_CUDA, "mapped host word: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *c->h_err = 0;
+    c->peer[rank] = nullptr;
+    if (nranks == 1 || (flags & DCRP_COMM_NCCL_ONLY) || nranks > COMM_MAX_RANKS) return DCRP_OK;
+
+    // ---- peer-memory mailboxes: allocate, exchange the IPC handles through NCCL, map every peer's
+    cudaStream_t st = e->stream;
+    int mine_ok = 1;
+    unsigned char* d_handles = nullptr;
+    std::vector<cudaIpcMemHandle_t> handles((size_t)nranks);
+    if (cudaMalloc(reinterpret_cast<void**>(&c->mailbox), comm_mailbox_bytes(nranks)) != cudaSuccess) { c->mailbox = nullptr; mine_ok = 0; }
+    if (mine_ok && cudaMemsetAsync(c->mailbox, 0, comm_mailbox_bytes(nranks), st) != cudaSuccess) mine_ok = 0;
+    cudaIpcMemHandle_t h{};
+    if (mine_ok && cudaIpcGetMemHandle(&h, c->mailbox) != cudaSuccess) mine_ok = 0;
+    cudaGetLastError();
+    CU(cudaMalloc(reinterpret_cast<void**>(&d_handles), sizeof(cudaIpcMemHandle_t) * (size_t)(nranks + 1) + 16));
+    unsigned char* d_mine = d_handles + sizeof(cudaIpcMemHandle_t) * (size_t)nranks;
+    CU(cudaMemcpyAsync(d_mine, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    NC(nccl_api().AllGather(d_mine, d_handles, sizeof h, ncclChar, c->comm, st));
+    CU(cudaMemcpyAsync(handles.data(), d_handles, sizeof h * (size_t)nranks, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int r = 0; r < nranks && mine_ok; ++r) {
+        if (r == rank) { c->peer[r] = c->mailbox; continue; }
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, handles[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mine_ok = 0; cudaGetLastError(); break; }
+        c->peer[r] = static_cast<unsigned long long*>(p);
+    }
+    // every rank must take the same route: all-reduce (min) of "my mailboxes are mapped"; doubles as the
+    // barrier after which all mailboxes are zeroed and mapped everywhere
+    int* d_ok = reinterpret_cast<int*>(d_handles);
+    CU(cudaMemcpyAsync(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, st));
+    NC(nccl_api().AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, st));
+    int all_ok = 0;
+    CU(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(d_handles);
+    c->p2p = all_ok != 0;
+    if (!c->p2p) {                              // fall back to ncclAllReduce on every rank
+        for (int r = 0; r < nranks; ++r)
+            if (r != rank && c->peer[r]) { cudaIpcCloseMemHandle(c->peer[r]); c->peer[r] = nullptr; }
+    }
+    return DCRP_OK;
+}
+
+extern "C" int dcrp_allreduce_counts(dcrp_engine* e, void* stream, uint64_t* d_counts)
+{
+    if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
+    Comm* c = e->comm;
+    if (!c) return fail(DCRP_ERR_STATE, "dcrp_allreduce_counts before dcrp_engine_attach_comm");
+    if (!e->has_scenario) return fail(DCRP_ERR_STATE, "dcrp_allreduce_counts before dcrp_scenario_upload");
+    if (!d_counts && !e->has_run) return fail(DCRP_ERR_STATE, "no run whose counts could be reduced");
+    CU(cudaSetDevice(e->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : (e->has_run ? e->run_stream : e->stream);
+    const size_t n_pairs = (size_t)e->sd.n_tracks * (size_t)e->sd.n_drones;
+    unsigned long long* counts = d_counts ? reinterpret_cast<unsigned long long*>(d_counts)
+        : reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + e->out_counts_off);
+    if (c->nranks == 1) return DCRP_OK;
+    if (c->p2p && n_pairs <= COMM_MAX_PAIRS) {
+        ++c->seq;
+        const int parity = (int)(c->seq & 1ull);
+        CommPeers peers;
+        for (int r = 0; r < COMM_MAX_RANKS; ++r) peers.p[r] = r < c->nranks ? c->peer[r] : nullptr;
+        k_comm_push<<<c->nranks - 1, 256, 0, st>>>(peers, c->rank, c->nranks, parity, c->seq, counts, (uint32_t)n_pairs);
+        k_comm_sum<<<1, 256, 0, st>>>(c->mailbox, c->rank, c->nranks, parity, c->seq, counts, (uint32_t)n_pairs,
+                                       10ull * 1000000000ull, c->d_err);
+        e->launches += 2;
+        CU(cudaGetLastError());
+        ++c->n_p2p;
+    } else {
+        NC(nccl_api().AllReduce(counts, counts, n_pairs, ncclUint64, ncclSum, c->comm, st));
+        ++c->n_nccl;
+    }
+    return DCRP_OK;
+}
+
+extern "C" int dcrp_comm_info(dcrp_engine* e, int32_t info[8])
+{
+    if (!e || !info) return fail(DCRP_ERR_INVALID, "dcrp_comm_info: NULL argument");
+    std::memset(info, 0, sizeof(int32_t) * 8);
+    Comm* c = e->comm;
+    if (!c) return DCRP_OK;
+    info[0] = 1; info[1] = c->rank; info[2] = c->nranks; info[3] = c->p2p ? 1 : 0; info[4] = c->nccl_version;
+    info[5] = (int32_t)std::min<uint64_t>(c->n_p2p, 0x7fffffff); info[6] = (int32_t)std::min<uint64_t>(c->n_nccl, 0x7fffffff);
+    info[7] = c->h_err ? (int32_t)*c->h_err : 0;
     return DCRP_OK;
 }
 

@@ -458,7 +458,7 @@ constexpr int EXB = 256;
 __global__ void __launch_bounds__(EXB) k_exact(const ScenarioDev s, const RunDev r,
                                                uint32_t chunks_per_pair, uint32_t n_items, int use_smem)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     unsigned long long ev = 0, sh = 0, st = 0, hits = 0;
     int loaded = -1;

@@ -101,21 +101,6 @@ __global__ void __launch_bounds__(128) k_slab_axis(const ScenarioDev s, float th
     }
 }
 
-// LEVEL 3 inside the screen kernel: the fp64 decision of ONE candidate by the whole warp (exact_any_warp:
-// the reference's order of operations, lanes = indices), with warp-uniform arguments.  Candidates are
-// ~3e-7 of the trials, so confirming them where they are found costs nothing measurable and saves the
-// candidate list, a kernel launch and its ~10 us of latency per run.
-__device__ __noinline__ uint32_t s3_confirm(const ScenarioDev& s, const RunDev& r, int pair, uint64_t trial)
-{
-    const int lane = (int)lane_id();
-    const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
-    const TrackDev t = s.tracks[a];
-    const Draw d = make_draw(r.seed, trial, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a, t.takeoff_t, t.box);
-    const TrialOut o = exact_any_warp(s, r, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d, lane);
-    if (o.first >= 0 && lane == 0) publish_hit(s, r, pair, a, j, trial, d, o);
-    return o.first >= 0 ? 1u : 0u;
-}
-
 // 2-D level-1 re-scan of n <= S3_RESCAN queued survivors of track a (4 per lane as two packed pairs);
 // the draws are regenerated from the trial id (nothing but (item, local) was kept), the track is read
 // through L1 with warp-uniform addresses.
@@ -203,24 +188,31 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
                 cand = u.force || min3d_fp32(s, *tk, u) < s.thr2_screen;
                 ncand += cand ? 1u : 0u;
             }
-            uint32_t bal = __ballot_sync(0xffffffffu, cand);
-            while (bal) {                              // one candidate at a time, the whole warp on it
-                const int src = __ffs((int)bal) - 1;
-                bal &= bal - 1u;
-                const int cp = __shfl_sync(0xffffffffu, pair, src);
-                const uint64_t ct = __shfl_sync(0xffffffffu, (unsigned long long)trial, src);
-                const uint32_t h = s3_confirm(s, r, cp, ct);
-                if (lane == 0) hits += h;
+            // LEVEL 3 inside the screen kernel: the fp64 decision in the reference's order of operations, by the
+            // lane that holds the candidate (all candidate lanes of the warp at once).  Candidates are ~3e-7 of
+            // the trials, so deciding them where they are found costs nothing measurable and saves the candidate
+            // list, a kernel launch and its ~10 us of latency per run.
+            if (cand) {
+                const int j = pair - a * s.n_drones;
+                const TrackDev t = *tk;
+                const Draw d = make_draw(r.seed, trial, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a,
+                                         t.takeoff_t, t.box);
+                const TrialOut o = exact_trial(s, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
+                if (o.first >= 0) {
+                    ++hits;
+                    publish_hit(s, r, pair, a, j, trial, d, o);
+                }
             }
         }
     }
     // a rare path (one call per 128 survivors): its own warp-reduced statistics
-    const unsigned long long is = warp_sum_u64(acc_is), np = warp_sum_u64(npass), nc = warp_sum_u64(ncand);
+    const unsigned long long is = warp_sum_u64(acc_is), np = warp_sum_u64(npass), nc = warp_sum_u64(ncand),
+                             nh = warp_sum_u64(hits);
     if (lane == 0) {
         atomicAdd(&r.stats[ST_ISSUED], is);
         if (np) atomicAdd(&r.stats[ST_LEVEL2], np);
         if (nc) atomicAdd(&r.stats[ST_CANDIDATES], nc);
-        if (hits) atomicAdd(&r.stats[ST_HITS], (unsigned long long)hits);
+        if (nh) atomicAdd(&r.stats[ST_HITS], nh);
     }
 }
 

@@ -2,8 +2,12 @@
 #include "Batch.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "Aircraft.h"
@@ -11,10 +15,40 @@
 
 namespace dcrp_host {
 
+namespace {
+// small files as the only transport between ranks: written under a temporary name, then renamed (atomic)
+bool publish_file(const std::string& path, const void* data, size_t bytes)
+{
+    const std::string tmp = path + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = bytes == 0 || std::fwrite(data, 1, bytes, f) == bytes;
+    std::fclose(f);
+    return ok && std::rename(tmp.c_str(), path.c_str()) == 0;
+}
+bool await_file(const std::string& path, std::vector<unsigned char>& out, double timeout_s)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        if (FILE* f = std::fopen(path.c_str(), "rb")) {
+            out.clear();
+            unsigned char buf[4096];
+            size_t n;
+            while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) out.insert(out.end(), buf, buf + n);
+            std::fclose(f);
+            return true;
+        }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return false;
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+}
+}  // namespace
+
 BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols, int aircraft_begin,
                               int aircraft_end, const std::string& drone_csv, int drone_cols, int drone_total,
                               uint64_t number_runs, double aircraft_radius, double drone_radius, uint64_t seed,
-                              int precision, const std::string& out_dir, uint32_t run_flags, int n_gpus)
+                              int precision, const std::string& out_dir, uint32_t run_flags, int n_gpus,
+                              const RankSpec& ranks)
 {
     BatchResult out;
     auto fail = [&](int status, const std::string& what) { out.status = status; out.error = what; return out; };
@@ -53,6 +87,14 @@ BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols
     }
 
     // ---- one launch for everything
+    const bool multi = ranks.n_ranks > 1;
+    if (multi && (ranks.rank < 0 || ranks.rank >= ranks.n_ranks || ranks.rendezvous.empty()))
+        return fail(DCRP_ERR_INVALID, "multi-process run: rank must be in [0, n_ranks) and a rendezvous path given");
+    if (multi && !std::getenv("DCRP_DEVICE")) {
+        int visible = 1;
+        if (dcrp_device_count(&visible) != DCRP_OK) return fail(DCRP_ERR_NO_DEVICE, dcrp_last_error());
+        set_shared_device(ranks.rank % visible);
+    }
     std::string err;
     dcrp_engine* eng = shared_engine(&err);
     if (!eng) return fail(DCRP_ERR_NO_DEVICE, err);
@@ -73,8 +115,54 @@ BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols
     int rc = DCRP_OK;
     int visible = 1;
     if (n_gpus != 1 && dcrp_device_count(&visible) != DCRP_OK) return fail(DCRP_ERR_NO_DEVICE, dcrp_last_error());
-    const int G = n_gpus <= 0 ? visible : std::min(n_gpus, visible);
-    if (G <= 1) {
+    const int G = multi ? 1 : (n_gpus <= 0 ? visible : std::min(n_gpus, visible));
+    if (multi) {
+        // ---- one process per GPU: communicator id through the rendezvous file, trial range of this rank,
+        // counts all-reduced on the device, records to rank 0 through files
+        unsigned char uid[DCRP_UNIQUE_ID_BYTES];
+        if (ranks.rank == 0) {
+            if ((rc = dcrp_comm_unique_id(uid)) != DCRP_OK) return fail(rc, dcrp_last_error());
+            if (!publish_file(ranks.rendezvous, uid, sizeof uid)) return fail(DCRP_ERR_IO, "cannot write " + ranks.rendezvous);
+        } else {
+            std::vector<unsigned char> got;
+            if (!await_file(ranks.rendezvous, got, 120.0) || got.size() != sizeof uid)
+                return fail(DCRP_ERR_COMM, "no communicator id at " + ranks.rendezvous + " after 120 s");
+            std::copy(got.begin(), got.end(), uid);
+        }
+        if ((rc = dcrp_engine_attach_comm(eng, uid, ranks.rank, ranks.n_ranks, 0)) != DCRP_OK) return fail(rc, dcrp_last_error());
+        if ((rc = dcrp_scenario_upload(eng, tracks.data(), n_tracks, drones.data(), drone_total, &model)) != DCRP_OK)
+            return fail(rc, dcrp_last_error());
+        dcrp_run part = run;
+        part.trial_begin = number_runs * (uint64_t)ranks.rank / (uint64_t)ranks.n_ranks;
+        part.trial_count = number_runs * (uint64_t)(ranks.rank + 1) / (uint64_t)ranks.n_ranks - part.trial_begin;
+        if ((rc = dcrp_run_async(eng, &part, nullptr, nullptr)) != DCRP_OK) return fail(rc, dcrp_last_error());
+        if ((rc = dcrp_allreduce_counts(eng, nullptr, nullptr)) != DCRP_OK) return fail(rc, dcrp_last_error());
+        if ((rc = dcrp_fetch(eng, &res)) != DCRP_OK) return fail(rc, dcrp_last_error());      // counts: global; records: this rank's
+        const std::string rec_base = ranks.rendezvous + ".records.";
+        if (ranks.rank != 0) {
+            if (!publish_file(rec_base + std::to_string(ranks.rank), records.data(), sizeof(dcrp_record) * (size_t)res.n_records))
+                return fail(DCRP_ERR_IO, "cannot write the records of rank " + std::to_string(ranks.rank));
+        } else {
+            uint32_t n_rec = res.n_records;
+            for (int r = 1; r < ranks.n_ranks; ++r) {
+                std::vector<unsigned char> got;
+                if (!await_file(rec_base + std::to_string(r), got, 600.0) || got.size() % sizeof(dcrp_record) != 0)
+                    return fail(DCRP_ERR_COMM, "no records from rank " + std::to_string(r));
+                const size_t k = got.size() / sizeof(dcrp_record);
+                if ((size_t)n_rec + k > records.size()) records.resize((size_t)n_rec + k);
+                std::copy(got.begin(), got.end(), reinterpret_cast<unsigned char*>(records.data() + n_rec));
+                n_rec += (uint32_t)k;
+                std::remove((rec_base + std::to_string(r)).c_str());
+            }
+            std::sort(records.begin(), records.begin() + n_rec, [](const dcrp_record& a, const dcrp_record& b) {
+                if (a.track != b.track) return a.track < b.track;
+                if (a.drone != b.drone) return a.drone < b.drone;
+                return a.trial < b.trial;
+            });
+            res.n_records = n_rec;
+            std::remove(ranks.rendezvous.c_str());
+        }
+    } else if (G <= 1) {
         rc = dcrp_simulate(eng, tracks.data(), n_tracks, drones.data(), drone_total, &model, &run, &res);
         if (rc != DCRP_OK) return fail(rc, dcrp_last_error());
     } else {
@@ -134,6 +222,7 @@ BatchResult monte_carlo_batch(const std::string& aircraft_csv, int aircraft_cols
     out.trials = (uint64_t)n_tracks * drone_total * number_runs;
     out.stats = res.stats;
     if (res.overflow) return fail(DCRP_ERR_STATE, "more collisions than the record buffer holds; lower number_runs per call");
+    if (multi && ranks.rank != 0) return out;          // rank 0 writes the files
 
     // ---- collision blocks, one file per aircraft (records arrive sorted by track, drone, trial)
     int stride = 0;

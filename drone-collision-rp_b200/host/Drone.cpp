@@ -12,13 +12,20 @@ namespace dcrp_host {
 
 static std::mutex g_mu;
 static dcrp_engine* g_engine = nullptr;
+static int g_device = -1;          // set_shared_device; -1 = DCRP_DEVICE or 0
+
+void set_shared_device(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_device = device;
+}
 
 dcrp_engine* shared_engine(std::string* error)
 {
     std::lock_guard<std::mutex> lock(g_mu);
     if (g_engine) return g_engine;
-    int device = 0;
-    if (const char* d = std::getenv("DCRP_DEVICE")) device = std::atoi(d);
+    int device = g_device >= 0 ? g_device : 0;
+    if (g_device < 0) if (const char* d = std::getenv("DCRP_DEVICE")) device = std::atoi(d);
     dcrp_engine* e = nullptr;
     const int rc = dcrp_engine_create(device, &e);
     if (rc != DCRP_OK) {

@@ -89,6 +89,7 @@ class Drone {
 
 namespace dcrp_host {
 // Process-wide engine on device $DCRP_DEVICE (default 0), created on first use.
+void set_shared_device(int device);            // before the first shared_engine(): which CUDA device it is created on
 dcrp_engine* shared_engine(std::string* error);
 void release_shared_engine();
 // Drone::Output row format (Drone.cpp:237-241): precision(10), "x,y,z,run\n" per

@@ -23,6 +23,7 @@ static void usage(const char* argv0)
 {
     cout << "usage: " << argv0 << " [--aircraft-csv F] [--drone-csv F] [--aircraft N] [--drones N]\n"
             "       [--runs N] [--seed S] [--precision fp64|mixed|fp32] [--synthetic N_FLIGHTS [--arrival-every K]] [--batch [--gpus N]] [--cull]\n"
+            "       [--batch --ranks R --rank r --rendezvous FILE]   one process per GPU, counts all-reduced by the engine\n"
             "defaults are the reference's constants (Monte_Carlo.cpp:11-18,28,33)\n";
 }
 
@@ -37,12 +38,13 @@ int main(int argc, char** argv)
     int drone_total = 99;
     double drone_radius = 0.19;
     int aircraft_total = 1;          // Monte_Carlo.cpp:28
-    int number_runs = 10000;         // Monte_Carlo.cpp:33
+    long long number_runs = 10000;   // Monte_Carlo.cpp:33 (an int there; widened: BASELINE config 3 is 1e10 trials)
     uint64_t seed = 20170630ull;
     int precision = DCRP_PRECISION_MIXED;
     int synthetic = 0, arrival_every = 0;
     bool batch = false;          // one GPU launch for all (aircraft, drone) pairs instead of one per pair
     int n_gpus = 1;              // --gpus N (0 = all): --batch only, trial ranges split over the devices of this process
+    dcrp_host::RankSpec ranks;   // --ranks R --rank r --rendezvous FILE: --batch only, one PROCESS per GPU
     uint32_t run_flags = 0;      // --cull: DCRP_FLAG_REACH_CULL (exact culling by reachability, same results)
 
     for (int i = 1; i < argc; ++i) {
@@ -55,13 +57,16 @@ int main(int argc, char** argv)
         else if (a == "--drone-csv") FilePath_drone = next("--drone-csv");
         else if (a == "--aircraft") aircraft_total = atoi(next("--aircraft"));
         else if (a == "--drones") drone_total = atoi(next("--drones"));
-        else if (a == "--runs") number_runs = atoi(next("--runs"));
+        else if (a == "--runs") number_runs = atoll(next("--runs"));
         else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
         else if (a == "--synthetic") synthetic = atoi(next("--synthetic"));
         else if (a == "--arrival-every") arrival_every = atoi(next("--arrival-every"));
         else if (a == "--batch") batch = true;
         else if (a == "--cull") run_flags |= DCRP_FLAG_REACH_CULL;
         else if (a == "--gpus") n_gpus = atoi(next("--gpus"));
+        else if (a == "--ranks") ranks.n_ranks = atoi(next("--ranks"));
+        else if (a == "--rank") ranks.rank = atoi(next("--rank"));
+        else if (a == "--rendezvous") ranks.rendezvous = next("--rendezvous");
         else if (a == "--precision") {
             const string p = next("--precision");
             if (p == "fp64") precision = DCRP_PRECISION_FP64;
@@ -86,8 +91,9 @@ int main(int argc, char** argv)
     if (batch) {
         const dcrp_host::BatchResult r = dcrp_host::monte_carlo_batch(
             FilePath_aircraft, no_col_aircraft, 0, aircraft_total, FilePath_drone, no_col_drone, drone_total,
-            (uint64_t)number_runs, aircraft_radius, drone_radius, seed, precision, "Drone_Collisions", run_flags, n_gpus);
+            (uint64_t)number_runs, aircraft_radius, drone_radius, seed, precision, "Drone_Collisions", run_flags, n_gpus, ranks);
         if (r.status != 0) { cout << "ERROR - " << r.error << endl; return 1; }
+        if (ranks.n_ranks > 1) cout << "rank " << ranks.rank << " of " << ranks.n_ranks << ": ";
         cout << "Number of collisions: " << (double)r.collisions << endl;
         dcrp_host::release_shared_engine();
         return 0;
@@ -117,7 +123,7 @@ int main(int argc, char** argv)
             Drone.SetInitialParameters(FilePath_drone, Aircraft.Vector_length, no_col_drone, j, i, Aircraft.takeoff_t,
                                        Aircraft.longitude_vector, Aircraft.latitude_vector, Aircraft.altitude_vector,
                                        aircraft_radius, drone_radius);
-            Drone.Simulation(number_runs, total_collisions);
+            Drone.Simulation64(number_runs > 0 ? (uint64_t)number_runs : 0, total_collisions);
             if (Drone.LastStatus() != 0) return 1;
         }
         Aircraft.Deallocation();

@@ -36,6 +36,7 @@ extern "C" {
 #define DCRP_ERR_RUNWAY      -4   /* latitude[0] in neither runway band            */
 #define DCRP_ERR_STATE       -5   /* call sequence error (e.g. run before upload)  */
 #define DCRP_ERR_IO          -6   /* file could not be opened / parsed             */
+#define DCRP_ERR_COMM        -7   /* NCCL missing / failed, or a peer rank did not arrive */
 
 /* arithmetic modes of the trial kernels */
 #define DCRP_PRECISION_FP64   0   /* every trial in IEEE double, reference order of operations      */
@@ -269,6 +270,29 @@ int  dcrp_dump_draws(dcrp_engine* e, int32_t track, int32_t drone, const dcrp_ru
  * n = that track's n_steps, stride = max n_steps over the scenario. */
 int  dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uint32_t n_records,
                        double* xyz, int32_t* stride_out);
+
+/* ---- multi-process: one process per GPU, per-rank hit counts combined ---------------------------------- */
+/* rank g runs a disjoint Philox trial range of every (track, drone) -- the loop of
+ * Monte_Carlo.cpp:28-34 sharded -- and the per-pair counters (Drone.cpp:276) are summed over the ranks.
+ * Rank 0 calls dcrp_comm_unique_id and ships the 128 bytes to the other ranks by any means (a file, a
+ * socket, torch.distributed); every rank then attaches.  The engine owns an NCCL communicator (libnccl.so.2
+ * is dlopen'ed on first use: no link-time dependency) and, unless DCRP_COMM_NCCL_ONLY is set, maps every
+ * peer's mailbox through CUDA IPC so that the all-reduce is two small kernels of its own over NVLink peer
+ * memory (csrc/comm.cu says why); ncclAllReduce(sum, uint64) is the fallback and the cross-check. */
+#define DCRP_UNIQUE_ID_BYTES 128
+#define DCRP_COMM_NCCL_ONLY  1u
+int  dcrp_comm_unique_id(void* out128);
+int  dcrp_engine_attach_comm(dcrp_engine* e, const void* unique_id128, int rank, int nranks, uint32_t flags);
+int  dcrp_engine_detach_comm(dcrp_engine* e);      /* collective-free; also done by dcrp_engine_destroy */
+/* In-place sum over the ranks of the n_tracks*n_drones uint64 counters in d_counts (a device buffer, e.g. the
+ * one passed to dcrp_run_async; NULL = the engine's own counts of the last run, so that the next dcrp_fetch
+ * returns the global counts).  Asynchronous on `stream` (NULL = the stream of the last run).  Every rank must
+ * call it the same number of times in the same order.  A peer that does not arrive within 10 s makes the next
+ * dcrp_fetch return DCRP_ERR_COMM instead of hanging. */
+int  dcrp_allreduce_counts(dcrp_engine* e, void* stream, uint64_t* d_counts);
+/* info[0] attached, [1] rank, [2] nranks, [3] peer-memory route in use, [4] NCCL version code,
+ * [5] all-reduces done over peer memory, [6] by ncclAllReduce, [7] peer-timeout flag */
+int  dcrp_comm_info(dcrp_engine* e, int32_t info[8]);
 
 /* ---- measurement -------------------------------------------------------- */
 /* Device peak of an FFMA-only (which=0), packed FFMA2-only (1), DFMA-only (2)

@@ -17,7 +17,11 @@ import drone_collision_rp_b200 as pk
 from drone_collision_rp_b200 import capi, scenario
 
 pytestmark = pytest.mark.gpu
-POS_TOL = 1e-9
+# fp64 positions carry UTM magnitudes (northing 5.7e6 m: one ulp is 9.3e-10 m) through ~95 running additions; where
+# the device's atan/sin/cos differ from glibc's in the last bit the roundings of the running sum take another path.
+# Over 1.0e7 trials the largest deviation seen is 6e-8 m (3 pairs x 5e4 trials stay below 1e-9, test_gpu_parity.py);
+# the north-star bound is 1e-4 m.
+POS_TOL = 1e-6
 
 
 @pytest.fixture(scope="module")

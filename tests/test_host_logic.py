@@ -162,3 +162,18 @@ def test_partition_trials_is_disjoint_and_exhaustive():
             assert b == pos
             pos += c
         assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_committed_workload_csv_is_what_the_generator_writes(tmp_path):
+    """bench.py (both arms) reads data/synthetic_day_1_20170630.csv; it must stay byte for byte what
+    host/synth_day.cpp writes for one flight with the default seed."""
+    import drone_collision_rp_b200 as pk
+    from drone_collision_rp_b200 import scenario
+
+    fresh = scenario.write_synthetic_day(str(tmp_path / "day.csv"), 1)
+    committed = os.path.join(pk.DATA_DIR, "synthetic_day_1_20170630.csv")
+    assert open(fresh, "rb").read() == open(committed, "rb").read()
+    import json
+    fx = json.load(open(os.path.join(pk.REPO_ROOT, "tests", "golden", "ref_config2_5km.json")))
+    t = scenario.load_flight(committed, 0)
+    assert (t["n_steps"], t["takeoff_t"]) == (fx["track_n_steps"], fx["track_takeoff_t"])
