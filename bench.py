@@ -411,13 +411,12 @@ def engine_arm(args):
         c = counts[b]
         if reduced_valid[b]:
             stream.wait_event(reduced[b])          # the reduction that last used this buffer is done
-        c.zero_()
         begin = (s * world + rank) * n
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         run = eng.run_async(seed=SEED, trial_begin=begin, trial_count=n, precision=capi.MIXED, stream=sh,
-                            d_counts=c.data_ptr())
+                            d_counts=c.data_ptr(), flags=capi.FLAG_ZERO_COUNTS)
         if world > 1:
             kdone[b].record(stream)
             if reduced_valid[b ^ 1]:
@@ -457,6 +456,8 @@ def engine_arm(args):
             stats_sum[k] += res.stats[k]
         eng.flush_l2(sh)                          # between timed steps, outside the event pairs
         flush_launches += 1
+    if world == 1:      # the caller-owned device counters (cleared by DCRP_FLAG_ZERO_COUNTS) hold the last step's hits
+        assert int(counts[(args.warmup + args.steps - 1) & 1].sum().item()) == res.hits
     tail_ms = 0.0
     if world > 1:
         # the last step's reduction has no next step to hide behind: time one isolated all-reduce of

@@ -721,8 +721,13 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
 
     CU(cudaEventRecord(e->ev_begin, st));
     // one launch clears the whole output arena (counters, stats, counts) and sets first_conflict = INT32_MAX
-    k_run_init<<<(unsigned)((e->out_bytes / 4 + 255) / 256), 256, 0, st>>>(
-        e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4));
+    {
+        const bool zero_ext = d_counts && (run->flags & DCRP_FLAG_ZERO_COUNTS);
+        const size_t words = std::max(e->out_bytes / 4, zero_ext ? n_pairs : (size_t)0);
+        k_run_init<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(
+            e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4),
+            zero_ext ? reinterpret_cast<unsigned long long*>(d_counts) : nullptr, zero_ext ? (uint32_t)n_pairs : 0u);
+    }
     ++e->launches; ++e->launches_this_run;
     CU(cudaGetLastError());
 
@@ -1022,7 +1027,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
 
     CU(cudaEventRecord(e->ev_begin, st));
     k_run_init<<<(unsigned)((e->out_bytes / 4 + 255) / 256), 256, 0, st>>>(
-        e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4));
+        e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4), nullptr, 0u);
     ++e->launches; ++e->launches_this_run;
     CU(cudaGetLastError());
     CU(cudaEventRecord(e->ev_k0, st));

@@ -1710,10 +1710,13 @@ __global__ void __launch_bounds__(256) k_peak_level1(float* out, int iters, floa
 
 // Clears a run's output arena: words [0, first_off) = 0 (counters, stats, counts),
 // words [first_off, n) = INT32_MAX (first-conflict index "none").
-__global__ void __launch_bounds__(256) k_run_init(uint32_t* out, uint32_t first_off, uint32_t n)
+// ext / n_ext: a caller-owned counts buffer to clear as well (DCRP_FLAG_ZERO_COUNTS), or nullptr / 0.
+__global__ void __launch_bounds__(256) k_run_init(uint32_t* out, uint32_t first_off, uint32_t n,
+                                                  unsigned long long* ext, uint32_t n_ext)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (i < first_off) ? 0u : 0x7fffffffu;
+    if (i < n_ext) ext[i] = 0ull;
 }
 
 __global__ void __launch_bounds__(256) k_fill(float4* p, size_t n, float v)

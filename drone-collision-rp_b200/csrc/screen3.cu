@@ -231,13 +231,16 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     uint32_t acc_t1 = 0, acc_is = 0, nsurv = 0;       // per-lane partial sums
     int list_n = 0, list_track = -1;       // warp-uniform
 
+    // Work items: the first one of every warp is its global warp index (no round trip to the one L2 line all
+    // 3552 warps would queue on at launch: ~10 us for the last of them), the later ones come from the counter.
+    const uint32_t n_warps = gridDim.x * (S3_BLOCK / 32);
     auto grab = [&]() -> uint32_t {
         uint32_t v = 0;
         if (lane == 0) v = atomicAdd(r.work_counter, 1u);
-        return __shfl_sync(0xffffffffu, v, 0);
+        return n_warps + __shfl_sync(0xffffffffu, v, 0);
     };
 
-    uint32_t item = grab();
+    uint32_t item = blockIdx.x * (S3_BLOCK / 32) + (uint32_t)warp;
     while (item < n_items) {
         const uint32_t next_item = grab();        // in flight while this item is processed
         const int pair = (int)r.div_chunks.div(item);
@@ -373,9 +376,19 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     }
     if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair);
 
-    flush_stats(r, 0, acc_t1, acc_is, 0, 0);
-    const unsigned long long ns = warp_sum_u64(nsurv);
-    if (lane == 0 && ns) atomicAdd(&r.stats[ST_SLAB_SURVIVORS], ns);
+    // statistics: one set of global atomics per CTA, not per warp (they all land on the same three L2 lines, and
+    // the warps of a launch finish within microseconds of each other)
+    __shared__ unsigned long long cta_acc[3];
+    if (threadIdx.x < 3) cta_acc[threadIdx.x] = 0ull;
+    __syncthreads();
+    const unsigned long long w1 = warp_sum_u64(acc_t1), w2 = warp_sum_u64(acc_is), w3 = warp_sum_u64(nsurv);
+    if (lane == 0) { atomicAdd(&cta_acc[0], w1); atomicAdd(&cta_acc[1], w2); atomicAdd(&cta_acc[2], w3); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (cta_acc[0]) atomicAdd(&r.stats[ST_SHARED], cta_acc[0]);
+        if (cta_acc[1]) atomicAdd(&r.stats[ST_ISSUED], cta_acc[1]);
+        if (cta_acc[2]) atomicAdd(&r.stats[ST_SLAB_SURVIVORS], cta_acc[2]);
+    }
 }
 
 }  // namespace dcrp

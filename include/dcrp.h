@@ -69,6 +69,9 @@ extern "C" {
                                      2-D level-1 scan (the round-1 kernel, k_screen2).  Same results; for A/B
                                      measurements and as a cross-check of the two screens.                    */
 
+#define DCRP_FLAG_ZERO_COUNTS 16u  /* dcrp_run_async with a caller-owned d_counts: clear it first (in the launch that
+                                     clears the engine's own accumulators), instead of adding to what is there   */
+
 typedef struct dcrp_engine dcrp_engine;
 
 /* One aircraft track = the arrays Aircraft::Vector_Allocation produces
