@@ -287,6 +287,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     if (!(model->v_straight > 0) || !(model->aircraft_radius + model->drone_radius > 0))
         return fail(DCRP_ERR_INVALID, "model: v_straight and the radii must be positive");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     e->has_scenario = false;
     e->has_run = false;
 
@@ -593,18 +594,16 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     return ce != cudaSuccess ? ce : cudaGetLastError();
 }
 
-static cudaError_t launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
-                                  cudaStream_t st)
+static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
+                          cudaStream_t st)
 {
     const void* kern = (const void*)k_screen3<3>;
     int vl_pad = (e->sd.n_steps_max + 3) & ~3;
     int tk_pad = (e->sd.t_max + 3) & ~3;
     const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);
     if (e->s3_smem != smem) {
-        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ, kern, S3_BLOCK, smem);
-        if (ce != cudaSuccess) return ce;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ, kern, S3_BLOCK, smem));
         if (e->s3_occ < 1) e->s3_occ = 1;
         e->s3_smem = smem;
     }
@@ -612,16 +611,18 @@ static cudaError_t launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chun
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
         ctas_wanted, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ));
     // the first launch of a run finds the counter cleared by k_run_init (word 2 of the output arena)
-    cudaError_t ce = cudaSuccess;
-    if (r.slice_first != 0) ce = cudaMemsetAsync(e->d_out.as<uint32_t>() + 2, 0, 4, st);
-    if (ce != cudaSuccess) return ce;
+    if (r.slice_first != 0) CU(cudaMemsetAsync(e->d_out.as<uint32_t>() + 2, 0, 4, st));
     ScenarioDev sd = e->sd;
     RunDev rr = r;
     rr.work_counter = e->d_out.as<uint32_t>() + 2;
     void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad};
-    ce = cudaLaunchKernel(kern, dim3(grid), dim3(S3_BLOCK), args, smem, st);
+    const cudaError_t ce = cudaLaunchKernel(kern, dim3(grid), dim3(S3_BLOCK), args, smem, st);
     ++e->launches; ++e->launches_this_run;
-    return ce != cudaSuccess ? ce : cudaGetLastError();
+    if (ce != cudaSuccess)
+        return fail(DCRP_ERR_CUDA, "k_screen3 launch (grid %u, %zu B shared memory, device %d): %s", grid, smem, e->device,
+                    cudaGetErrorString(ce));
+    CU(cudaGetLastError());
+    return DCRP_OK;
 }
 
 extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream, uint64_t* d_counts)
@@ -639,6 +640,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     if (run->trial_begin + run->trial_count < run->trial_begin)
         return fail(DCRP_ERR_INVALID, "trial range overflows 64 bits");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     const ScenarioDev& s = e->sd;
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
@@ -767,9 +769,13 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
             CU(cudaGetLastError());
         } else {
             r.div_chunks = make_fastdiv(chunks);
-            const cudaError_t ce = use3 ? launch_screen3(e, r, chunks, n_items, st)
-                                        : launch_screen2(e, r, chunks, n_items, st);
-            if (ce != cudaSuccess) return fail(DCRP_ERR_CUDA, "k_screen launch: %s", cudaGetErrorString(ce));
+            if (use3) {
+                const int rc3 = launch_screen3(e, r, chunks, n_items, st);
+                if (rc3 != DCRP_OK) return rc3;
+            } else {
+                const cudaError_t ce = launch_screen2(e, r, chunks, n_items, st);
+                if (ce != cudaSuccess) return fail(DCRP_ERR_CUDA, "k_screen2 launch (device %d): %s", e->device, cudaGetErrorString(ce));
+            }
         }
     }
     CU(cudaEventRecord(e->ev_trials, st));
@@ -789,6 +795,7 @@ extern "C" int dcrp_last_run_ms(dcrp_engine* e, float* ms)
     if (!e || !ms) return fail(DCRP_ERR_INVALID, "dcrp_last_run_ms: NULL argument");
     if (!e->has_run) return fail(DCRP_ERR_STATE, "no run to time");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     CU(cudaEventSynchronize(e->ev_end));
     CU(cudaEventElapsedTime(ms, e->ev_begin, e->ev_end));
     return DCRP_OK;
@@ -799,6 +806,7 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     if (!e || !res) return fail(DCRP_ERR_INVALID, "dcrp_fetch: NULL argument");
     if (!e->has_run) return fail(DCRP_ERR_STATE, "dcrp_fetch before dcrp_run_async");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     cudaStream_t st = e->run_stream;
     const ScenarioDev& s = e->sd;
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
@@ -965,6 +973,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     const uint64_t n_rays = (uint64_t)s.n_drones * run->ray_count;
     if (n_rays >= (1ull << 32)) return fail(DCRP_ERR_INVALID, "at most 2^32 rays per call");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     cudaStream_t st = e->stream;
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
 
@@ -1094,6 +1103,7 @@ extern "C" int dcrp_dump_draws(dcrp_engine* e, int32_t track, int32_t drone, con
     if (n == 0) return DCRP_OK;
     if (n > (1ull << 31)) return fail(DCRP_ERR_INVALID, "at most 2^31 draws per call");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     CU(e->d_scratch.need(sizeof(Draw) * (size_t)n));
     k_draws<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(
         e->sd, track, run->track_id_base + (uint32_t)track, run->drone_id_base + (uint32_t)drone, run->seed,
@@ -1122,6 +1132,7 @@ extern "C" int dcrp_trajectories(dcrp_engine* e, const dcrp_record* records, uin
             return fail(DCRP_ERR_INVALID, "record %u: t1st=%d outside [1,%d]", i, r.t1st, t.takeoff_t);
     }
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     const size_t stride = (size_t)e->sd.n_steps_max;
     const size_t rec_bytes = (sizeof(Record) * (size_t)n_records + 255) & ~size_t(255);
     const size_t xyz_bytes = sizeof(double) * 3 * stride * (size_t)n_records;
@@ -1182,6 +1193,7 @@ extern "C" int dcrp_engine_attach_comm(dcrp_engine* e, const void* unique_id128,
     if (e->comm) return fail(DCRP_ERR_STATE, "a communicator is already attached (dcrp_engine_detach_comm first)");
     if (!nccl_api().load()) return fail(DCRP_ERR_COMM, "NCCL is not available: %s", nccl_api().error.c_str());
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     Comm* c = new (std::nothrow) Comm();
     if (!c) return fail(DCRP_ERR_INVALID, "out of host memory");
     c->rank = rank; c->nranks = nranks;
@@ -1253,6 +1265,7 @@ extern "C" int dcrp_allreduce_counts(dcrp_engine* e, void* stream, uint64_t* d_c
     if (!e->has_scenario) return fail(DCRP_ERR_STATE, "dcrp_allreduce_counts before dcrp_scenario_upload");
     if (!d_counts && !e->has_run) return fail(DCRP_ERR_STATE, "no run whose counts could be reduced");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     cudaStream_t st = stream ? (cudaStream_t)stream : (e->has_run ? e->run_stream : e->stream);
     const size_t n_pairs = (size_t)e->sd.n_tracks * (size_t)e->sd.n_drones;
     unsigned long long* counts = d_counts ? reinterpret_cast<unsigned long long*>(d_counts)
@@ -1294,6 +1307,7 @@ extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, floa
     if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
     if (which < 0 || which > 24) return fail(DCRP_ERR_INVALID, "which must be 0..24");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     const int threads = 256;
     int blocks = e->prop.multiProcessorCount * 8;
     int iters = 2048;
@@ -1367,6 +1381,7 @@ extern "C" int dcrp_flush_l2(dcrp_engine* e, void* stream)
 {
     if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
     CU(cudaSetDevice(e->device));
+    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     DevBuf& flush = e->d_flush;
     const size_t bytes = (size_t)256 << 20;
     CU(flush.need(bytes));
