@@ -574,7 +574,8 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2) + sizeof(int2)) +
                         (2 * c.np * c.rounds > 4 ? (size_t)screen_chunk() * 2 : 0);   // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
-        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // (function, device)-wide attribute: raise it to the opt-in maximum, see launch_screen3
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->prop.sharedMemPerBlockOptin);
         if (ce != cudaSuccess) return ce;
         ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], kern, c.block, smem);
         if (ce != cudaSuccess) return ce;
@@ -602,7 +603,9 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
     int tk_pad = (e->sd.t_max + 3) & ~3;
     const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);
     if (e->s3_smem != smem) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // The attribute belongs to the (function, device), not to this engine: another engine on the device may have
+        // set it for a smaller scenario.  Always raise it to the device's opt-in maximum, never to "what I need now".
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->prop.sharedMemPerBlockOptin));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ, kern, S3_BLOCK, smem));
         if (e->s3_occ < 1) e->s3_occ = 1;
         e->s3_smem = smem;
@@ -1053,7 +1056,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         const void* kern = ap_np == 1 ? (const void*)k_ap_scan_tracks<1> : (const void*)k_ap_scan_tracks<2>;
         int& occ = e->ap_occ;
         if (occ == 0) {
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->prop.sharedMemPerBlockOptin));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AP_BLOCK, smem));
             if (occ < 1) occ = 1;
         }

@@ -122,3 +122,21 @@ def test_replay_table_is_validated(engine, tracks, ring1):
             assert e.value.status == capi.ERR_INVALID
     ok = engine.simulate([t], ring1[:2], seed=0, trial_count=64, precision=capi.MIXED, replay=good)
     assert ok.stats["trials"] == 128
+
+
+def test_two_engines_share_a_device(tracks, ring1):
+    """cudaFuncSetAttribute(MaxDynamicSharedMemorySize) belongs to the (kernel, device) pair, not to an engine: a
+    second engine running a smaller scenario on the same device must not leave the first one unable to launch
+    (found on a 2-GPU box in round 2: 'k_screen3 launch: invalid argument')."""
+    big = [dict(t) for t in tracks[:4]]                                  # larger per-warp tables
+    long_t = dict(tracks[0], takeoff_t=len(tracks[0]["x"]))
+    a, b = capi.Engine(0), capi.Engine(0)
+    for flags in (0, capi.FLAG_SCREEN_2D):
+        r1 = a.simulate(big + [long_t], ring1, seed=9, trial_count=3000, flags=flags)
+        small = dict(tracks[1], x=tracks[1]["x"][:40].copy(), y=tracks[1]["y"][:40].copy(), z=tracks[1]["z"][:40].copy(),
+                     takeoff_t=5, n_steps=40)
+        b.simulate([small], ring1[:1], seed=9, trial_count=3000, flags=flags)
+        r2 = a.simulate(big + [long_t], ring1, seed=9, trial_count=3000, flags=flags)
+        assert np.array_equal(r1.counts, r2.counts)
+    a.close()
+    b.close()
