@@ -457,7 +457,7 @@ def engine_arm(args):
         eng.flush_l2(sh)                          # between timed steps, outside the event pairs
         flush_launches += 1
     if world == 1:      # the caller-owned device counters (cleared by DCRP_FLAG_ZERO_COUNTS) hold the last step's hits
-        assert int(counts[(args.warmup + args.steps - 1) & 1].sum().item()) == res.hits
+        assert int(counts[(args.warmup + args.steps - 1) & 1].sum().item()) == res.stats["hits"]
     tail_ms = 0.0
     if world > 1:
         # the last step's reduction has no next step to hide behind: time one isolated all-reduce of

@@ -562,6 +562,19 @@ static ScreenCfg& screen_cfg()
 }
 static uint64_t screen_chunk() { const ScreenCfg& c = screen_cfg(); return (uint64_t)2 * c.np * c.rounds * c.block; }
 
+// MaxDynamicSharedMemorySize belongs to the (function, device) pair, not to an engine: another engine on the same
+// device may have set it for a smaller scenario.  So it is always RAISED to the most the device allows (opt-in
+// maximum minus the kernel's static shared memory), never set to "what this launch needs".
+static cudaError_t allow_max_dynamic_smem(const dcrp_engine* e, const void* kern)
+{
+    cudaFuncAttributes fa{};
+    cudaError_t ce = cudaFuncGetAttributes(&fa, kern);
+    if (ce != cudaSuccess) return ce;
+    const int most = (int)e->prop.sharedMemPerBlockOptin - (int)fa.sharedSizeBytes;
+    if (fa.maxDynamicSharedSizeBytes >= most) return cudaSuccess;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+}
+
 static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                                   cudaStream_t st)
 {
@@ -574,8 +587,7 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2) + sizeof(int2)) +
                         (2 * c.np * c.rounds > 4 ? (size_t)screen_chunk() * 2 : 0);   // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
-        // (function, device)-wide attribute: raise it to the opt-in maximum, see launch_screen3
-        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->prop.sharedMemPerBlockOptin);
+        cudaError_t ce = allow_max_dynamic_smem(e, kern);
         if (ce != cudaSuccess) return ce;
         ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], kern, c.block, smem);
         if (ce != cudaSuccess) return ce;
@@ -603,9 +615,7 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
     int tk_pad = (e->sd.t_max + 3) & ~3;
     const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);
     if (e->s3_smem != smem) {
-        // The attribute belongs to the (function, device), not to this engine: another engine on the device may have
-        // set it for a smaller scenario.  Always raise it to the device's opt-in maximum, never to "what I need now".
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->prop.sharedMemPerBlockOptin));
+        CU(allow_max_dynamic_smem(e, kern));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ, kern, S3_BLOCK, smem));
         if (e->s3_occ < 1) e->s3_occ = 1;
         e->s3_smem = smem;
@@ -1056,7 +1066,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         const void* kern = ap_np == 1 ? (const void*)k_ap_scan_tracks<1> : (const void*)k_ap_scan_tracks<2>;
         int& occ = e->ap_occ;
         if (occ == 0) {
-            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->prop.sharedMemPerBlockOptin));
+            CU(allow_max_dynamic_smem(e, kern));
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, AP_BLOCK, smem));
             if (occ < 1) occ = 1;
         }
