@@ -369,7 +369,7 @@ def engine_arm(args):
     peaks = {}
     if rank == 0:
         for which, name in ((0, "ffma"), (1, "ffma2"), (2, "dfma"), (3, "scan_mix_11flop")):
-            tf, ms = eng.measure_peak(which)
+            tf, ms = capi.measure_peak(local, which)
             peaks[name] = tf
         log("peaks TFLOP/s:", peaks)
 
@@ -437,7 +437,7 @@ def engine_arm(args):
     for s in range(args.warmup):
         run, e0, e1 = step(s)
         eng.fetch(run)
-        eng.flush_l2(sh)
+        capi.flush_l2(local, sh)
     barrier()
 
     launches0 = eng.launch_count()
@@ -446,7 +446,7 @@ def engine_arm(args):
     keys = ("tests_evaluated", "tests_shared", "tests_issued", "drone_steps", "trials", "candidates", "hits", "level2",
             "slab_survivors")
     step_ms, trial_ms, stats_sum = [], [], {k: 0 for k in keys}
-    flush_launches = 0
+    untimed_launches = 0        # engine launches inside the loop that are not part of the timed steps
     for s in range(args.warmup, args.warmup + args.steps):
         run, e0, e1 = step(s)
         res = eng.fetch(run)                      # syncs the stream; outside the event pair
@@ -454,8 +454,7 @@ def engine_arm(args):
         trial_ms.append(res.stats["ms_trials"])
         for k in stats_sum:
             stats_sum[k] += res.stats[k]
-        eng.flush_l2(sh)                          # between timed steps, outside the event pairs
-        flush_launches += 1
+        capi.flush_l2(local, sh)                  # between timed steps, outside the event pairs (libdcrp_bench.so)
     if world == 1:      # the caller-owned device counters (cleared by DCRP_FLAG_ZERO_COUNTS) hold the last step's hits
         assert int(counts[(args.warmup + args.steps - 1) & 1].sum().item()) == res.stats["hits"]
     tail_ms = 0.0
@@ -470,10 +469,10 @@ def engine_arm(args):
         t1e.record(stream)
         torch.cuda.synchronize()
         tail_ms = t0e.elapsed_time(t1e)
-        flush_launches += 2 if (comm_info and comm_info["peer_memory"]) else 0     # (not part of the timed steps)
+        untimed_launches += 2 if (comm_info and comm_info["peer_memory"]) else 0
     barrier()
     wall = time.perf_counter() - wall0
-    launches = eng.launch_count() - launches0 - flush_launches
+    launches = eng.launch_count() - launches0 - untimed_launches
 
     total_ms = sum(step_ms) + tail_ms
     per_rank = None
@@ -603,7 +602,7 @@ def engine_arm(args):
             rc_eval += r.stats["tests_evaluated"]
             rc_issued += r.stats["tests_issued"]; rc_culled_trials += r.stats["trials_culled"]
             rc_trials += r.stats["trials"]; rc_hits += r.stats["hits"]
-        eng.flush_l2(sh)
+        capi.flush_l2(local, sh)
     callc = eng.prepared_simulate(scn, precision=capi.MIXED, flags=capi.FLAG_REACH_CULL, record_capacity=4096, seed=SEED)
     rc_e2e_secs, rc_e2e_tests = 0.0, 0
     for s in range(args.warmup + args.steps):

@@ -14,6 +14,7 @@ REPO_ROOT = _os.path.dirname(PKG_DIR)
 DATA_DIR = _os.path.join(REPO_ROOT, "data")
 LIBDCRP = _os.path.join(PKG_DIR, "libdcrp.so")
 LIBDCRP_HOST = _os.path.join(PKG_DIR, "libdcrp_host.so")
+LIBDCRP_BENCH = _os.path.join(PKG_DIR, "libdcrp_bench.so")    # measurement only (bench.py, tools/)
 MONTE_CARLO = _os.path.join(PKG_DIR, "Monte_Carlo")
 RING_1KM = _os.path.join(DATA_DIR, "drone_inital_positions_1km.csv")
 RING_5KM = _os.path.join(DATA_DIR, "drone_inital_positions_5km.csv")

@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-from . import LIBDCRP, LIBDCRP_HOST
+from . import LIBDCRP, LIBDCRP_BENCH, LIBDCRP_HOST
 
 OK = 0
 ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_RUNWAY, ERR_STATE, ERR_IO, ERR_COMM = -1, -2, -3, -4, -5, -6, -7
@@ -99,7 +99,7 @@ DCRP_SYMBOLS = [
     "dcrp_engine_destroy", "dcrp_target_box", "dcrp_simulate", "dcrp_scenario_upload",
     "dcrp_run_async", "dcrp_fetch", "dcrp_last_run_ms", "dcrp_allpairs", "dcrp_dump_draws", "dcrp_trajectories",
     "dcrp_comm_unique_id", "dcrp_engine_attach_comm", "dcrp_engine_detach_comm", "dcrp_allreduce_counts", "dcrp_comm_info",
-    "dcrp_measure_peak", "dcrp_flush_l2", "dcrp_device_count", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
+    "dcrp_device_count", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
 ]
 DCRP_HOST_SYMBOLS = [
     "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_synth_day_write_mixed",
@@ -139,8 +139,6 @@ def lib():
         L.dcrp_engine_detach_comm.argtypes = [C.c_void_p]
         L.dcrp_allreduce_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.dcrp_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
-        L.dcrp_measure_peak.argtypes = [C.c_void_p, C.c_int, c_double_p, C.POINTER(C.c_float)]
-        L.dcrp_flush_l2.argtypes = [C.c_void_p, C.c_void_p]
         L.dcrp_device_count.argtypes = [C.POINTER(C.c_int)]
         L.dcrp_engine_reserve_sms.argtypes = [C.c_void_p, C.c_int]
         L.dcrp_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
@@ -180,6 +178,35 @@ def host():
         H.dcrph_write_block.argtypes = [C.c_char_p, c_double_p, c_double_p, c_double_p, C.c_int, C.c_long]
         _host = H
     return _host
+
+
+_bench = None
+
+
+def bench_lib():
+    """libdcrp_bench.so: roofline micro-kernels and the L2 flush (measurement only)."""
+    global _bench
+    if _bench is None:
+        if not os.path.exists(LIBDCRP_BENCH):
+            raise FileNotFoundError(LIBDCRP_BENCH + " is missing: build it first")
+        B = C.CDLL(LIBDCRP_BENCH)
+        B.dcrpb_last_error.restype = C.c_char_p
+        B.dcrpb_measure_peak.argtypes = [C.c_int, C.c_int, c_double_p, C.POINTER(C.c_float)]
+        B.dcrpb_flush_l2.argtypes = [C.c_int, C.c_void_p]
+        _bench = B
+    return _bench
+
+
+def measure_peak(device, which):
+    tf, ms = C.c_double(), C.c_float()
+    if bench_lib().dcrpb_measure_peak(int(device), int(which), C.byref(tf), C.byref(ms)) != 0:
+        raise RuntimeError(bench_lib().dcrpb_last_error().decode())
+    return tf.value, ms.value
+
+
+def flush_l2(device, stream=None):
+    if bench_lib().dcrpb_flush_l2(int(device), C.c_void_p(stream or 0)) != 0:
+        raise RuntimeError(bench_lib().dcrpb_last_error().decode())
 
 
 def _check(status):
@@ -239,6 +266,7 @@ class Engine:
     """One dcrp_engine on one CUDA device."""
 
     def __init__(self, device=0):
+        self.device = int(device)
         self._h = C.c_void_p()
         _check(lib().dcrp_engine_create(int(device), C.byref(self._h)))
         self.n_tracks = self.n_drones = 0
@@ -433,14 +461,6 @@ class Engine:
         _check(lib().dcrp_comm_info(self._h, a))
         return {"attached": bool(a[0]), "rank": a[1], "nranks": a[2], "peer_memory": bool(a[3]), "nccl_version": a[4],
                 "allreduces_peer_memory": a[5], "allreduces_nccl": a[6], "peer_timeout": bool(a[7])}
-
-    def measure_peak(self, which):
-        tf, ms = C.c_double(), C.c_float()
-        _check(lib().dcrp_measure_peak(self._h, int(which), C.byref(tf), C.byref(ms)))
-        return tf.value, ms.value
-
-    def flush_l2(self, stream=None):
-        _check(lib().dcrp_flush_l2(self._h, C.c_void_p(stream or 0)))
 
     def reserve_sms(self, n):
         _check(lib().dcrp_engine_reserve_sms(self._h, int(n)))

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 #include "kernels.cu"
 #include "screen3.cu"
 #include "comm.cu"
@@ -48,6 +50,14 @@ static int fail(int code, const char* fmt, ...)
             return fail(DCRP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
                         __FILE__, __LINE__);                                                       \
     } while (0)
+
+// ------------------------------------------------------------------ tracing (NVTX ranges in the launcher)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ------------------------------------------------------------------ buffers
 struct DevBuf {            // grow-only device buffer
@@ -125,7 +135,7 @@ struct dcrp_engine {
     // run
     bool has_run = false;
     dcrp_run run{};
-    cudaStream_t run_stream = nullptr;
+    cudaStream_t run_stream = nullptr, run_stream_prev = nullptr;
     bool external_counts = false;
     uint32_t rec_cap = 0;
     uint32_t launches_this_run = 0;
@@ -137,6 +147,7 @@ struct dcrp_engine {
     size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;     // out_bytes: the part before the records
     uint32_t run_status = 0;       // DCRP_STAT_* bits of the current run (reported in dcrp_stats.status)
     Comm* comm = nullptr;          // dcrp_engine_attach_comm
+    bool run_event_valid = false;  // ev_end marks the end of the last run on its stream: later calls on OTHER streams wait for it
     bool reuse_device_replay = false;   // dcrp_fetch's fp64 fallback: d_replay already holds the run's table
     DevBuf d_cands, d_replay;      // (records live in the tail of d_out)
     DevBuf d_trial_hit, d_trial_first, d_trial_min;
@@ -151,8 +162,7 @@ struct dcrp_engine {
     bool reach_ready = false;      // k_reach has run for the current scenario
     uint64_t ap_rays = 0;
     DevBuf d_ap_hist, d_ap_rank, d_ap_rayA, d_ap_rayB, d_ap_meta, d_ap_l2;
-    DevBuf d_scratch;    // peak kernels / draws / trajectories
-    DevBuf d_flush;      // 256 MB written by dcrp_flush_l2 (> 126 MB of L2)
+    DevBuf d_scratch;    // draws / trajectories
 };
 
 // Records kept in the first D2H copy of a fetch (one copy, one sync for the usual handful of hits).
@@ -236,7 +246,7 @@ extern "C" int dcrp_engine_destroy(dcrp_engine* e)
     DevBuf* bufs[] = {&e->d_scn, &e->d_p1x, &e->d_p1y, &e->d_s1fh, &e->d_s1pm, &e->d_kink, &e->d_p1f, &e->d_s1sub_pm, &e->d_s1sub_fs,
                       &e->d_s1sub_ft, &e->d_out,
                       &e->d_cands, &e->d_replay, &e->d_trial_hit, &e->d_trial_first,
-                      &e->d_trial_min, &e->d_scratch, &e->d_flush, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
+                      &e->d_trial_min, &e->d_scratch, &e->d_ap_hist, &e->d_ap_rank, &e->d_ap_rayA,
                       &e->d_ap_rayB, &e->d_ap_meta, &e->d_ap_l2, &e->d_reach, &e->d_alive, &e->d_reach_tot,
                       &e->d_slab_dir};
     for (DevBuf* b : bufs) b->release();
@@ -279,13 +289,20 @@ static float ulp32_of(double v)
 extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, int32_t n_tracks,
                                     const dcrp_drone* drones, int32_t n_drones, const dcrp_model* model)
 {
+    NvtxRange nvtx_("dcrp_scenario_upload");
     if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
     if (!tracks || n_tracks <= 0 || !drones || n_drones <= 0 || !model)
         return fail(DCRP_ERR_INVALID, "dcrp_scenario_upload: tracks/drones/model missing or empty");
     if ((uint64_t)n_tracks * (uint64_t)n_drones > (1ull << 31) - 1)
         return fail(DCRP_ERR_INVALID, "too many (track, drone) pairs");
-    if (!(model->v_straight > 0) || !(model->aircraft_radius + model->drone_radius > 0))
-        return fail(DCRP_ERR_INVALID, "model: v_straight and the radii must be positive");
+    if (!(model->v_straight > 0) || !std::isfinite(model->v_straight) ||
+        !(model->aircraft_radius >= 0) || !(model->drone_radius >= 0) ||
+        !(model->aircraft_radius + model->drone_radius > 0) || !std::isfinite(model->aircraft_radius + model->drone_radius))
+        return fail(DCRP_ERR_INVALID, "model: v_straight must be positive and finite, the radii non-negative with a positive finite sum");
+    // pitch lies in [0, pi/2] (Drone.cpp:218), so the speed factor lies between v_straight and v_ascend: a negative
+    // v_ascend would make the drone fly backwards and DESCEND, which the reach bound (k_reach) excludes by construction
+    if (!(model->v_ascend >= 0) || !std::isfinite(model->v_ascend) || !std::isfinite(model->start_alt))
+        return fail(DCRP_ERR_INVALID, "model: v_ascend must be non-negative and finite, start_alt finite");
     CU(cudaSetDevice(e->device));
     (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     e->has_scenario = false;
@@ -360,7 +377,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     // ulp of the largest coordinate met since the tile's exact re-base
     const double extent = std::max({hi[0] - s.ox, s.ox - lo[0], hi[1] - s.oy, s.oy - lo[1],
                                     hi[2] - s.oz, s.oz - lo[2]}) + 1.0 +
-                          model->v_straight * (vl_max <= 128 ? 128.0 : 512.0);
+                          std::max(std::fabs(model->v_straight), std::fabs(model->v_ascend)) * (vl_max <= 128 ? 128.0 : 512.0);
     s.start_alt = model->start_alt; s.v_straight = model->v_straight; s.v_ascend = model->v_ascend;
     s.radius = model->drone_radius + model->aircraft_radius;          // Drone.cpp:260
     {   // sqrt_rn(d2) < R  <=>  d2 < c, c = smallest double whose rounded root reaches R
@@ -426,6 +443,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     const size_t scn_bytes = align256(o_dr + sizeof(double4) * (size_t)n_drones);
     cudaStream_t st = e->stream;
     CU(cudaStreamSynchronize(st));          // the previous upload's copy has left the pinned mirror
+    if (e->run_event_valid) CU(cudaStreamWaitEvent(st, e->ev_end, 0));   // a run on a caller's stream may still read the old scenario
     CU(e->h_scn.need(scn_bytes));
     CU(e->d_scn.need(scn_bytes));
     unsigned char* hb = e->h_scn.as<unsigned char>();
@@ -640,6 +658,7 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
 
 extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream, uint64_t* d_counts)
 {
+    NvtxRange nvtx_("dcrp_run_async");
     if (!e || !run) return fail(DCRP_ERR_INVALID, "dcrp_run_async: NULL argument");
     if (!e->has_scenario) return fail(DCRP_ERR_STATE, "dcrp_run_async before dcrp_scenario_upload");
     if (run->precision < DCRP_PRECISION_FP64 || run->precision > DCRP_PRECISION_FP32)
@@ -660,6 +679,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
 
     e->run = *run;
     e->allpairs_run = false;
+    e->run_stream_prev = e->run_stream;
     e->run_stream = st;
     e->launches_this_run = 0;
     e->h2d_run = 0;
@@ -669,6 +689,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     CU(size_out_arena(e, n_pairs));
     CU(e->d_cands.need(sizeof(Candidate) * (size_t)CAND_CAP));
     if (st != e->stream) CU(cudaStreamWaitEvent(st, e->ev_b, 0));   // after the scenario upload + stage 1
+    if (e->run_event_valid && st != e->run_stream_prev) CU(cudaStreamWaitEvent(st, e->ev_end, 0));   // the arenas are shared between runs
 
     RunDev r{};
     r.seed = run->seed; r.trial_begin = run->trial_begin; r.trial_count = run->trial_count;
@@ -799,6 +820,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(e->ev_end, st));
+    e->run_event_valid = true;
     e->has_run = true;
     return DCRP_OK;
 }
@@ -816,6 +838,7 @@ extern "C" int dcrp_last_run_ms(dcrp_engine* e, float* ms)
 
 extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
 {
+    NvtxRange nvtx_("dcrp_fetch");
     if (!e || !res) return fail(DCRP_ERR_INVALID, "dcrp_fetch: NULL argument");
     if (!e->has_run) return fail(DCRP_ERR_STATE, "dcrp_fetch before dcrp_run_async");
     CU(cudaSetDevice(e->device));
@@ -943,6 +966,7 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
                              const dcrp_drone* drones, int32_t n_drones, const dcrp_model* model,
                              const dcrp_run* run, dcrp_result* result)
 {
+    NvtxRange nvtx_("dcrp_simulate");
     if (!result || !result->counts) return fail(DCRP_ERR_INVALID, "dcrp_simulate: result->counts is required");
     static const bool timing = std::getenv("DCRP_HOST_TIMING") != nullptr;     // profiling aid (tools/e2e_breakdown.py)
     using clk = std::chrono::steady_clock;
@@ -973,6 +997,7 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
 // ------------------------------------------------------------------ all-pairs stress
 extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_result* result)
 {
+    NvtxRange nvtx_("dcrp_allpairs");
     if (!e || !run || !result) return fail(DCRP_ERR_INVALID, "dcrp_allpairs: NULL argument");
     if (!result->counts) return fail(DCRP_ERR_INVALID, "dcrp_allpairs: result->counts is required");
     if (!e->has_scenario) return fail(DCRP_ERR_STATE, "dcrp_allpairs before dcrp_scenario_upload");
@@ -1094,14 +1119,14 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(e->ev_end, st));
+    e->run_event_valid = true;
     e->has_run = true;
     uint32_t l2n = 0;
     CU(cudaMemcpyAsync(&l2n, ap.l2_count, sizeof l2n, cudaMemcpyDeviceToHost, st));
-    int rc = dcrp_fetch(e, result);
-    if (rc != DCRP_OK) return rc;
-    if (l2n > L2_CAP)
+    CU(cudaStreamSynchronize(st));
+    if (l2n > L2_CAP)       // before anything is merged into the caller's buffers: a retry must not double-count
         return fail(DCRP_ERR_STATE, "level-2 list overflow (%u > %u entries): lower ray_count per call", l2n, L2_CAP);
-    return DCRP_OK;
+    return dcrp_fetch(e, result);
 }
 
 // ------------------------------------------------------------------ replay / records
@@ -1201,6 +1226,7 @@ extern "C" int dcrp_engine_detach_comm(dcrp_engine* e)
 
 extern "C" int dcrp_engine_attach_comm(dcrp_engine* e, const void* unique_id128, int rank, int nranks, uint32_t flags)
 {
+    NvtxRange nvtx_("dcrp_engine_attach_comm");
     if (!e || !unique_id128) return fail(DCRP_ERR_INVALID, "dcrp_engine_attach_comm: NULL argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DCRP_ERR_INVALID, "rank %d of %d ranks", rank, nranks);
     if (e->comm) return fail(DCRP_ERR_STATE, "a communicator is already attached (dcrp_engine_detach_comm first)");
@@ -1272,6 +1298,7 @@ extern "C" int dcrp_engine_attach_comm(dcrp_engine* e, const void* unique_id128,
 
 extern "C" int dcrp_allreduce_counts(dcrp_engine* e, void* stream, uint64_t* d_counts)
 {
+    NvtxRange nvtx_("dcrp_allreduce_counts");
     if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
     Comm* c = e->comm;
     if (!c) return fail(DCRP_ERR_STATE, "dcrp_allreduce_counts before dcrp_engine_attach_comm");
@@ -1314,97 +1341,7 @@ extern "C" int dcrp_comm_info(dcrp_engine* e, int32_t info[8])
     return DCRP_OK;
 }
 
-// ------------------------------------------------------------------ measurement
-extern "C" int dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms_out)
-{
-    if (!e || !tflops) return fail(DCRP_ERR_INVALID, "dcrp_measure_peak: NULL argument");
-    if (which < 0 || which > 24) return fail(DCRP_ERR_INVALID, "which must be 0..24");
-    CU(cudaSetDevice(e->device));
-    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
-    const int threads = 256;
-    int blocks = e->prop.multiProcessorCount * 8;
-    int iters = 2048;
-    if (which >= 13) {                // the real kernels' residency: 3-4 CTAs of 256 threads per SM
-        static const int per_sm = std::getenv("DCRP_PEAK_CTAS") ? std::atoi(std::getenv("DCRP_PEAK_CTAS")) : 4;
-        blocks = e->prop.multiProcessorCount * per_sm;
-        iters = 64;
-    }
-    CU(e->d_scratch.need(sizeof(double) * (size_t)threads * blocks));
-    float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep) {
-        CU(cudaEventRecord(e->ev_a, e->stream));
-        switch (which) {
-            case 0: k_peak_ffma<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.999f, 0.001f); break;
-            case 1: k_peak_ffma2<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.999f, 0.001f); break;
-            case 2: k_peak_dfma<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<double>(), iters, 0.999, 0.001); break;
-            case 3: k_peak_scanmix<<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 4: k_peak_variant<4><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 5: k_peak_variant<5><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 6: k_peak_variant<6><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 7: k_peak_variant<7><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 8: k_peak_variant<8><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 9: k_peak_variant<9><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 10: k_peak_variant2<10><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 11: k_peak_variant2<11><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 12: k_peak_variant2<12><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 13: k_peak_scan2d<13><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 14: k_peak_scan2d<14><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 15: k_peak_scan2d<15><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-            case 16: k_peak_scan2d<16><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f); break;
-#define DCRP_L1(F, S, N) k_peak_level1<F, S, N><<<blocks, threads, 0, e->stream>>>(e->d_scratch.as<float>(), iters, 0.5f, -3.0f, 1e-3f)
-            case 17: DCRP_L1(0, 1, 1); break;
-            case 18: DCRP_L1(0, 1, 2); break;
-            case 19: DCRP_L1(0, 1, 4); break;
-            case 20: DCRP_L1(1, 0, 1); break;
-            case 21: DCRP_L1(1, 1, 1); break;
-            case 22: DCRP_L1(1, 1, 2); break;
-            case 23: DCRP_L1(1, 1, 4); break;
-            default: DCRP_L1(1, 0, 2); break;
-#undef DCRP_L1
-        }
-        ++e->launches;
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(e->ev_b, e->stream));
-        CU(cudaEventSynchronize(e->ev_b));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
-        if (rep > 0) best = std::min(best, ms);
-    }
-    const double lanes = (double)threads * blocks;
-    double flops;
-    if (which == 0)      flops = lanes * iters * 16.0 * 8.0 * 2.0;
-    else if (which == 1) flops = lanes * iters * 16.0 * 8.0 * 4.0;
-    else if (which == 2) flops = lanes * iters * 16.0 * 8.0 * 2.0;
-    else if (which == 4 || which == 5) flops = lanes * iters * 8.0 * 9.0 * 4.0 * 2.0;   // packed add/mul: 2 flop
-    else if (which == 8) flops = lanes * iters * 8.0 * 16.0;                            // FMNMX3 count, not flops
-    else if (which == 10) flops = lanes * iters * 8.0 * 4.0 / 10.0;                     // Philox4x32-10 calls
-    else if (which == 12) flops = lanes * iters * 8.0 * 2.0 * 2.0 * 2.0 * 11.0;         // 2 steps x 2 pairs x 2 tests
-    else if (which >= 17) {
-        static const int np_of[] = {1, 2, 4, 1, 1, 2, 4, 2};
-        flops = lanes * iters * 512.0 * 2.0 * np_of[which - 17] * 11.0;                  // 512 steps x 2 NP tests
-    }
-    else if (which >= 13) flops = lanes * iters * 512.0 * 2.0 * 11.0;                   // 512 steps x 2 tests
-    else                 flops = lanes * iters * 8.0 * 4.0 * 2.0 * 11.0;   // 2 tests per packed pair, 11 flop each
-    *tflops = flops / ((double)best * 1e-3) * 1e-12;
-    if (ms_out) *ms_out = best;
-    return DCRP_OK;
-}
-
-extern "C" int dcrp_flush_l2(dcrp_engine* e, void* stream)
-{
-    if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
-    CU(cudaSetDevice(e->device));
-    (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
-    DevBuf& flush = e->d_flush;
-    const size_t bytes = (size_t)256 << 20;
-    CU(flush.need(bytes));
-    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    k_fill<<<e->prop.multiProcessorCount * 8, 256, 0, st>>>(flush.as<float4>(), bytes / sizeof(float4), 1.0f);
-    ++e->launches;
-    CU(cudaGetLastError());
-    return DCRP_OK;
-}
-
+// ------------------------------------------------------------------ device queries
 extern "C" int dcrp_device_count(int* n)
 {
     if (!n) return fail(DCRP_ERR_INVALID, "dcrp_device_count: NULL argument");

@@ -11,7 +11,6 @@
 //   k_exact       every trial in fp64 (DCRP_PRECISION_FP64; the parity kernel)
 //   k_draws       Philox replay-table dump
 //   k_trajectory  full fp64 trajectories of recorded collisions (Drone::Output rows)
-//   k_peak_*      FFMA / FFMA2 / DFMA / scan-mix micro-kernels (roofline denominators)
 //
 // Reference semantics: /root/reference/Drone.cpp:66-80,107-127,164-231,253-281
 // (restated in dcrp_math.cuh).  Nothing here is translated from the reference:
@@ -1387,327 +1386,6 @@ __global__ void __launch_bounds__(64) k_trajectory(const ScenarioDev s, const Re
     }
 }
 
-// =========================================================================
-// roofline denominators: pure-pipe micro-kernels
-// =========================================================================
-// Each thread runs `iters` rounds over 8 independent accumulators; the result is
-// stored so nothing is optimised away.  flops are counted by the host.
-__global__ void __launch_bounds__(256) k_peak_ffma(float* out, int iters, float b, float c)
-{
-    float a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-          a7 = a0 + 7;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
-            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-}
-
-__global__ void __launch_bounds__(256) k_peak_ffma2(float* out, int iters, float b, float c)
-{
-    float2 a[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = make_float2(threadIdx.x + k, threadIdx.x - k);
-    const float2 bb = make_float2(b, b), cc = make_float2(c, c);
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] = ffma2(a[k], bb, cc);
-        }
-    }
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc += a[k].x + a[k].y;
-    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
-}
-
-__global__ void __launch_bounds__(256) k_peak_dfma(double* out, int iters, double b, double c)
-{
-    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-           a7 = a0 + 7;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
-            a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-}
-
-// The scan loop's own instruction mix without its shared-memory loads: per pair
-// of tests 3 FFMA2 + 3 FADD2 + 1 FMUL2 + 2 FFMA2 + 1 FMNMX3, 4 independent pairs.
-__global__ void __launch_bounds__(256) k_peak_scanmix(float* out, int iters, float s0, float a0)
-{
-    float2 B[4], S[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        B[k] = make_float2(threadIdx.x * 0.5f + k, threadIdx.x * 0.25f - k);
-        S[k] = make_float2(s0 + k, s0 - k);
-    }
-    float2 fi = make_float2(0.f, 0.f);
-    const float2 one = make_float2(1.f, 1.f), na = make_float2(a0, a0);
-    float mn = 3.0e38f;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 dx = fadd2(ffma2(fi, S[k], B[k]), na);
-                const float2 dy = fadd2(ffma2(fi, S[k], B[(k + 1) & 3]), na);
-                const float2 dz = fadd2(ffma2(fi, S[(k + 1) & 3], B[k]), na);
-                const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
-                mn = fmin3(mn, d2.x, d2.y);
-            }
-            fi = fadd2(fi, one);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = mn;
-}
-
-// Variants of the scan mix that isolate one instruction class each (profiling aid):
-//   V=4 FADD2 only   V=5 FMUL2 only   V=6 mix with LOP3 instead of FMNMX3
-//   V=7 mix with 2 x FMNMX instead of FMNMX3   V=8 FMNMX3 only   V=9 the mix unpacked (scalar)
-template <int V>
-__global__ void __launch_bounds__(256) k_peak_variant(float* out, int iters, float s0, float a0)
-{
-    float2 B[4], S[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        B[k] = make_float2(threadIdx.x * 0.5f + k, threadIdx.x * 0.25f - k);
-        S[k] = make_float2(s0 + k, s0 - k);
-    }
-    float2 fi = make_float2(0.f, 0.f);
-    const float2 one = make_float2(1.f, 1.f), na = make_float2(a0, a0);
-    float mn = 3.0e38f, mn2 = 2.0e38f;
-    uint32_t acc = 0;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (V == 4 || V == 5) {
-#pragma unroll
-                for (int r = 0; r < 9; ++r) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) B[k] = (V == 4) ? fadd2(B[k], S[k]) : fmul2(B[k], S[k]);
-                }
-            } else if (V == 8) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    B[k].x = fmin3(B[k].x, S[k].x, S[k].y);
-                    B[k].y = fmin3(B[k].y, S[k].y, B[k].x);
-                    S[k].x = fmin3(S[k].x, B[k].y, mn);
-                    S[k].y = fmin3(S[k].y, B[k].x, mn2);
-                }
-            } else if (V == 9) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float dx0 = fmaf(fi.x, S[k].x, B[k].x) + na.x, dx1 = fmaf(fi.y, S[k].y, B[k].y) + na.y;
-                    const float dy0 = fmaf(fi.x, S[k].x, B[(k + 1) & 3].x) + na.x;
-                    const float dy1 = fmaf(fi.y, S[k].y, B[(k + 1) & 3].y) + na.y;
-                    const float dz0 = fmaf(fi.x, S[(k + 1) & 3].x, B[k].x) + na.x;
-                    const float dz1 = fmaf(fi.y, S[(k + 1) & 3].y, B[k].y) + na.y;
-                    const float d0 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0));
-                    const float d1 = fmaf(dz1, dz1, fmaf(dy1, dy1, dx1 * dx1));
-                    mn = fmin3(mn, d0, d1);
-                }
-                fi = fadd2(fi, one);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 dx = fadd2(ffma2(fi, S[k], B[k]), na);
-                    const float2 dy = fadd2(ffma2(fi, S[k], B[(k + 1) & 3]), na);
-                    const float2 dz = fadd2(ffma2(fi, S[(k + 1) & 3], B[k]), na);
-                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
-                    if (V == 6) acc ^= __float_as_uint(d2.x) ^ __float_as_uint(d2.y);
-                    else { mn = fminf(mn, d2.x); mn2 = fminf(mn2, d2.y); }
-                }
-                fi = fadd2(fi, one);
-            }
-        }
-    }
-    float r = mn + mn2 + __uint_as_float(acc & 0x3fffffffu);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r += B[k].x + B[k].y + S[k].x + S[k].y;
-    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
-}
-
-// More profiling variants:
-//   V=10 Philox4x32-10 only (4 independent streams per thread)         -> reported in G calls/s
-//   V=11 the scan mix with one Philox round interleaved per 4 pair-steps (software-pipelined)
-//   V=12 incremental scan mix: P += S; D = P + (-A); all packed ops with <= 2 distinct register pairs
-template <int V>
-__global__ void __launch_bounds__(256) k_peak_variant2(float* out, int iters, float s0, float a0)
-{
-    float2 B[4], S[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        B[k] = make_float2(threadIdx.x * 0.5f + k, threadIdx.x * 0.25f - k);
-        S[k] = make_float2(s0 + k, s0 - k);
-    }
-    float2 fi = make_float2(0.f, 0.f);
-    const float2 one = make_float2(1.f, 1.f), na = make_float2(a0, a0);
-    float mn = 3.0e38f, mn2 = 2.0e38f;
-    uint32_t c0[4], c1[4], c2[4], c3[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { c0[k] = threadIdx.x + k; c1[k] = blockIdx.x; c2[k] = k; c3[k] = 7; }
-    uint32_t k0 = 0x12345u, k1 = 0x6789au;
-    for (int i = 0; i < iters; ++i) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (V == 10 || V == 11) {
-                // one Philox round on stream (u & 3)
-                const int q = u & 3;
-                const uint32_t hi0 = __umulhi(0xD2511F53u, c0[q]), lo0 = 0xD2511F53u * c0[q];
-                const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2[q]), lo1 = 0xCD9E8D57u * c2[q];
-                const uint32_t n0 = hi1 ^ c1[q] ^ k0, n2 = hi0 ^ c3[q] ^ k1;
-                c0[q] = n0; c1[q] = lo1; c2[q] = n2; c3[q] = lo0;
-                k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-            }
-            if (V == 10) {
-#pragma unroll
-                for (int q = 1; q < 4; ++q) {      // three more rounds: 4 rounds per u in total
-                    const int z = (u + q) & 3;
-                    const uint32_t hi0 = __umulhi(0xD2511F53u, c0[z]), lo0 = 0xD2511F53u * c0[z];
-                    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2[z]), lo1 = 0xCD9E8D57u * c2[z];
-                    const uint32_t n0 = hi1 ^ c1[z] ^ k0, n2 = hi0 ^ c3[z] ^ k1;
-                    c0[z] = n0; c1[z] = lo1; c2[z] = n2; c3[z] = lo0;
-                }
-            }
-            if (V == 11) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 dx = fadd2(ffma2(fi, S[k], B[k]), na);
-                    const float2 dy = fadd2(ffma2(fi, S[k], B[(k + 1) & 3]), na);
-                    const float2 dz = fadd2(ffma2(fi, S[(k + 1) & 3], B[k]), na);
-                    const float2 d2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
-                    mn = fminf(mn, d2.x); mn2 = fminf(mn2, d2.y);
-                }
-                fi = fadd2(fi, one);
-            }
-            if (V == 12) {
-                // 2 pairs x 3 coordinates of running positions live in B[0..3] / S[0..3] halves
-                float2 PX0 = B[0], PY0 = B[1], PZ0 = B[2], PX1 = B[3], PY1 = S[3], PZ1 = fi;
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    PX0 = fadd2(PX0, S[0]); PY0 = fadd2(PY0, S[1]); PZ0 = fadd2(PZ0, S[2]);
-                    PX1 = fadd2(PX1, S[0]); PY1 = fadd2(PY1, S[1]); PZ1 = fadd2(PZ1, S[2]);
-                    const float2 dx0 = fadd2(PX0, na), dy0 = fadd2(PY0, na), dz0 = fadd2(PZ0, na);
-                    const float2 dx1 = fadd2(PX1, na), dy1 = fadd2(PY1, na), dz1 = fadd2(PZ1, na);
-                    const float2 e0 = ffma2(dz0, dz0, ffma2(dy0, dy0, fmul2(dx0, dx0)));
-                    const float2 e1 = ffma2(dz1, dz1, ffma2(dy1, dy1, fmul2(dx1, dx1)));
-                    mn = fminf(mn, e0.x); mn2 = fminf(mn2, e0.y);
-                    mn = fminf(mn, e1.x); mn2 = fminf(mn2, e1.y);
-                }
-                B[0] = PX0; B[1] = PY0; B[2] = PZ0; B[3] = PX1; S[3] = PY1; fi = PZ1;
-            }
-        }
-    }
-    float r = mn + mn2;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r += B[k].x + B[k].y + S[k].x + S[k].y + __uint_as_float((c0[k] ^ c1[k] ^ c2[k] ^ c3[k]) & 0x3fffffffu);
-    out[blockIdx.x * blockDim.x + threadIdx.x] = r + fi.x;
-}
-
-__constant__ float2 c_peak_xy[512];
-
-// Scan-loop variants at the real kernel's shape (1 packed pair per thread, 2-D incremental):
-//   V=13 samples from shared memory, duplicated layout (x,x,y,y): LDS.128, plain pair operands
-//   V=14 samples from shared memory, 16 B layout: LDS.64 + scalar-broadcast operand form (production)
-//   V=15 no shared memory: loop-invariant operand (pure pipe rate of the 6-op mix)
-//   V=16 samples from __constant__ memory through the uniform datapath (LDCU + UR broadcast operand);
-//        needs CTA-uniform loop bounds, which the per-warp sorted bins of k_screen2 cannot offer
-template <int V>
-__global__ void __launch_bounds__(256) k_peak_scan2d(float* out, int iters, float s0, float a0)
-{
-    __shared__ float4 tile[512];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) tile[i] = make_float4(a0 + i, a0 + i, a0 - i, a0 - i);
-    __syncthreads();
-    f2_t PX = pk2(threadIdx.x * 0.5f, threadIdx.x * 0.25f), PY = pk2(threadIdx.x * 1.5f, -1.f * threadIdx.x);
-    const f2_t SX = pk2(s0, s0 + 1.f), SY = pk2(s0 - 1.f, s0 + 2.f);
-    const f2_t cinv = pk2(a0, a0);
-    float mn0 = 3.0e38f, mn1 = 3.0e38f;
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll 4
-        for (int k = 0; k < 512; ++k) {
-            f2_t cx, cy;
-            if (V == 13) {
-                const float4 c = tile[k];
-                cx = pk2(c.x, c.y); cy = pk2(c.z, c.w);
-            } else if (V == 14) {
-                const float2 c = *reinterpret_cast<const float2*>(&tile[k]);
-                cx = pk2(c.x, c.x); cy = pk2(c.y, c.y);
-            } else if (V == 16) {
-                const float2 c = c_peak_xy[k];
-                cx = pk2(c.x, c.x); cy = pk2(c.y, c.y);
-            } else {
-                cx = cinv; cy = cinv;
-            }
-            const f2_t dx = fadd2(PX, cx);
-            const f2_t dy = fadd2(PY, cy);
-            const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
-            mn0 = fminf(mn0, d2.x);
-            mn1 = fminf(mn1, d2.y);
-            PX = fadd2(PX, SX); PY = fadd2(PY, SY);
-        }
-    }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = mn0 + mn1;
-}
-
-// Level-1 loop shapes, parameterised: FORM 0 = Euclidean (FMUL2 + FFMA2 + min), 1 = Chebyshev (FMNMX of
-// |dx|, |dy| + predicate); SRC 0 = loop-invariant operand (registers only), 1 = one broadcast LDS.128 per
-// two indices (the production tile layout); NP packed pairs per thread.  512 indices per outer iteration.
-template <int FORM, int SRC, int NP>
-__global__ void __launch_bounds__(256) k_peak_level1(float* out, int iters, float s0, float a0, float thr1)
-{
-    __shared__ float4 tile[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) tile[i] = make_float4(a0 + i, a0 - i, a0 + i + 0.5f, a0 - i - 0.5f);
-    __syncthreads();
-    f2_t PX[NP], PY[NP], SX[NP], SY[NP];
-    float mn[2 * NP];
-    bool near[2 * NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        PX[p] = pk2(threadIdx.x * 0.5f + p, threadIdx.x * 0.25f - p); PY[p] = pk2(threadIdx.x * 1.5f, -1.f * threadIdx.x + p);
-        SX[p] = pk2(s0 + p, s0 + 1.f); SY[p] = pk2(s0 - 1.f, s0 + 2.f + p);
-        mn[2 * p] = mn[2 * p + 1] = 3.0e38f; near[2 * p] = near[2 * p + 1] = false;
-    }
-    const float4 cinv = make_float4(a0, a0 + 1.f, a0 + 2.f, a0 + 3.f);
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll 2
-        for (int k = 0; k < 256; ++k) {
-            const float4 c = SRC ? tile[k] : cinv;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float vx = h ? c.z : c.x, vy = h ? c.w : c.y;
-                const f2_t cx = pk2(vx, vx), cy = pk2(vy, vy);
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    if (FORM == 0) {
-                        const f2_t dx = fadd2(PX[p], cx), dy = fadd2(PY[p], cy);
-                        const float2 d2 = up2(ffma2(dy, dy, fmul2(dx, dx)));
-                        mn[2 * p] = fminf(mn[2 * p], d2.x); mn[2 * p + 1] = fminf(mn[2 * p + 1], d2.y);
-                    } else {
-                        const float2 dx = up2(fadd2(PX[p], cx)), dy = up2(fadd2(PY[p], cy));
-                        near[2 * p] |= fmaxf(fabsf(dx.x), fabsf(dy.x)) < thr1;
-                        near[2 * p + 1] |= fmaxf(fabsf(dx.y), fabsf(dy.y)) < thr1;
-                    }
-                    PX[p] = fadd2(PX[p], SX[p]); PY[p] = fadd2(PY[p], SY[p]);
-                }
-            }
-        }
-    }
-    float r = 0.f;
-#pragma unroll
-    for (int p = 0; p < 2 * NP; ++p) r += FORM == 0 ? mn[p] : (near[p] ? 1.f : 0.f);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) { const float2 a = up2(PX[p]), b = up2(PY[p]); r += a.x + a.y + b.x + b.y; }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
-}
-
 // Clears a run's output arena: words [0, first_off) = 0 (counters, stats, counts),
 // words [first_off, n) = INT32_MAX (first-conflict index "none").
 // ext / n_ext: a caller-owned counts buffer to clear as well (DCRP_FLAG_ZERO_COUNTS), or nullptr / 0.
@@ -1717,13 +1395,6 @@ __global__ void __launch_bounds__(256) k_run_init(uint32_t* out, uint32_t first_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (i < first_off) ? 0u : 0x7fffffffu;
     if (i < n_ext) ext[i] = 0ull;
-}
-
-__global__ void __launch_bounds__(256) k_fill(float4* p, size_t n, float v)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) p[i] = make_float4(v, v, v, v);
 }
 
 }  // namespace dcrp

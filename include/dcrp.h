@@ -297,15 +297,9 @@ int  dcrp_allreduce_counts(dcrp_engine* e, void* stream, uint64_t* d_counts);
  * [5] all-reduces done over peer memory, [6] by ncclAllReduce, [7] peer-timeout flag */
 int  dcrp_comm_info(dcrp_engine* e, int32_t info[8]);
 
-/* ---- measurement -------------------------------------------------------- */
-/* Device peak of an FFMA-only (which=0), packed FFMA2-only (1), DFMA-only (2)
- * or the scan loop's own FP instruction mix (3) micro-kernel, in TFLOP/s
- * (FMA = 2 flop): the roofline denominators MEASURED_PEAKS.json lacks.
- * which = 4..9 are profiling variants of the mix (FADD2 only, FMUL2 only, mix
- * with LOP3 / 2xFMNMX instead of FMNMX3, FMNMX3 only [Ginstr/s], unpacked mix). */
-int  dcrp_measure_peak(dcrp_engine* e, int which, double* tflops, float* ms);
-/* Writes `bytes` of a scratch buffer (L2 flush between timed iterations). */
-int  dcrp_flush_l2(dcrp_engine* e, void* stream);
+/* ---- device queries ------------------------------------------------------ */
+/* (The roofline micro-benchmarks and the L2 flush of bench.py live in libdcrp_bench.so, csrc/bench_kernels.cu:
+ * measurement code is not part of this library.) */
 /* Number of CUDA devices visible to the process (0 and DCRP_ERR_NO_DEVICE when there is none). */
 int  dcrp_device_count(int* n);
 /* Keeps `n_sms` SMs out of the persistent trial grids (0 = use them all, the default).  A multi-GPU caller

@@ -22,7 +22,8 @@ def built():
     """Build the native pieces once per session if they are missing."""
     import drone_collision_rp_b200 as pk
 
-    if not (os.path.exists(pk.LIBDCRP) and os.path.exists(pk.LIBDCRP_HOST) and os.path.exists(pk.MONTE_CARLO)):
+    if not (os.path.exists(pk.LIBDCRP) and os.path.exists(pk.LIBDCRP_HOST) and os.path.exists(pk.MONTE_CARLO)
+            and os.path.exists(pk.LIBDCRP_BENCH)):
         pk.build_native()
     import oracle_api as oa
 
