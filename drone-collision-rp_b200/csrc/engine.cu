@@ -777,7 +777,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     // the per-pair choice of the slab direction costs ~10 us plus 256 sample trials per pair: worth it from a few
     // 1e4 trials per pair on (Drone::Simulation's 10 000-trial calls keep the per-track default)
     if (use3 && !e->slab_ready && run->trial_count >= 20000) {
-        k_slab_axis<<<(unsigned)n_pairs, 128, 0, st>>>(s, 4.0f * s.thr_slab);   // once per scenario
+        k_slab_axis<<<(unsigned)n_pairs, S3_AXIS_BLOCK, 0, st>>>(s, 1.5f * s.thr_slab);   // once per scenario
         ++e->launches; ++e->launches_this_run;
         CU(cudaGetLastError());
         e->slab_ready = true;

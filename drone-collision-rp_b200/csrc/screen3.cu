@@ -30,8 +30,7 @@ constexpr int S3_BLOCK = 256;
 constexpr int S3_MAX_VL = 512;            // longest track the per-warp projected table holds
 constexpr int S3_MAX_T = 128;             // largest takeoff_t the per-warp kink tables hold
 constexpr int S3_REBASE = 128;            // exact re-base of the running position every so many indices
-constexpr int S3_DIRS = 8;                // candidate slab directions k*pi/8
-constexpr int S3_AXIS_TL = 8;             // sample trials per lane of the direction choice (256 per pair)
+constexpr int S3_DIRS = 16;               // candidate slab directions k*pi/16
 
 static_assert(S3_CHW <= 4096, "local trial index is packed in 12 bits");
 
@@ -43,61 +42,68 @@ __host__ __device__ inline size_t s3_warp_smem(int vl_pad, int tk_pad)
 }
 
 // Slab direction of every pair, once per scenario (k_stage1 has already filled in the per-track default:
-// the aircraft's main direction of travel): of S3_DIRS candidate directions the one whose slab passes the
-// fewest of 256 deterministic sample trials (at 4x the real threshold, to rank rare events with few
-// samples).  A heuristic only: any unit vector gives the same decisions, just more or fewer survivors.
-// One CTA of 4 warps per pair, 2 sample trials per lane.
-__global__ void __launch_bounds__(128) k_slab_axis(const ScenarioDev s, float thr_rank)
+// the aircraft's main direction of travel): of S3_DIRS candidate directions k*pi/S3_DIRS the one whose slab
+// passes the fewest of S3_AXIS_SAMPLES deterministic sample trials (at 1.5x the real threshold: enough
+// passes to rank the directions, still close to the quantity that matters).  A heuristic only: any unit
+// vector gives the same decisions, just more or fewer survivors for the 2-D re-scan.
+// One CTA of S3_AXIS_BLOCK threads per pair, S3_AXIS_TL sample trials per thread.
+constexpr int S3_AXIS_BLOCK = 512;
+constexpr int S3_AXIS_TL = 2;
+constexpr int S3_AXIS_SAMPLES = S3_AXIS_BLOCK * S3_AXIS_TL;
+
+__global__ void __launch_bounds__(S3_AXIS_BLOCK) k_slab_axis(const ScenarioDev s, float thr_rank)
 {
     __shared__ uint32_t cnt[S3_DIRS];
+    __shared__ float2 dirs[S3_DIRS];
+    __shared__ float2 trk[S3_MAX_VL];
     const int pair = (int)blockIdx.x;
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x < S3_DIRS) cnt[threadIdx.x] = 0;
-    __syncthreads();
     const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
     const TrackDev* __restrict__ tk = s.tracks + a;
     const int VL = tk->n_steps, takeoff_t = tk->takeoff_t;
+    if (threadIdx.x < S3_DIRS) {
+        cnt[threadIdx.x] = 0;
+        float sn, cs;
+        sincospif((float)threadIdx.x / (float)S3_DIRS, &sn, &cs);
+        dirs[threadIdx.x] = make_float2(cs, sn);
+    }
+    for (int i = threadIdx.x; i < VL; i += S3_AXIS_BLOCK) trk[i] = __ldg(&s.trkxy[(size_t)tk->off_xy + i]);
+    __syncthreads();
     TrackScale ts;
     ts.wx32 = tk->wx32; ts.wy32 = tk->wy32; ts.wz32 = tk->wz32; ts.z0rel = tk->z0rel;
-    const float2* __restrict__ g = s.trkxy + (size_t)tk->off_xy;
-    float cs[S3_DIRS], sn[S3_DIRS];
-#pragma unroll
-    for (int k = 0; k < S3_DIRS; ++k) sincospif((float)k / (float)S3_DIRS, &sn[k], &cs[k]);
-    float bx[2], by[2], sx[2], sy[2];
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        const U4 w = philox4x32_10((uint32_t)(m * 128 + threadIdx.x), 0u, (uint32_t)j, (uint32_t)a, 0xA511E9B3u, 0x5AB5A5E1u);
+    uint32_t bits[S3_AXIS_TL];
+#pragma unroll 1
+    for (int m = 0; m < S3_AXIS_TL; ++m) {
+        const U4 w = philox4x32_10((uint32_t)(m * S3_AXIS_BLOCK + threadIdx.x), 0u, (uint32_t)j, (uint32_t)a, 0xA511E9B3u,
+                                   0x5AB5A5E1u);
         const int t1st = draw_t1st(w.x, takeoff_t);
         const uint4 q = make_uint4(w.y, w.z, w.w, (uint32_t)t1st << 12);
         const Fast32 u = setup_fast32(s, ts, s.kink + (size_t)pair * s.t_max, s.p1f + (size_t)j * s.t_max, INT_MAX, q);
-        bx[m] = u.force ? 1e15f : u.bx; by[m] = u.force ? 1e15f : u.by;
-        sx[m] = u.force ? 0.f : u.sx; sy[m] = u.force ? 0.f : u.sy;
-    }
-    uint32_t bits0 = 0, bits1 = 0;
-    for (int i = 1; i < VL; ++i) {
-        const float2 p = __ldg(&g[i]);
-        const float fi = (float)i;
-        const float dx0 = fmaf(fi, sx[0], bx[0]) + p.x, dy0 = fmaf(fi, sy[0], by[0]) + p.y;
-        const float dx1 = fmaf(fi, sx[1], bx[1]) + p.x, dy1 = fmaf(fi, sy[1], by[1]) + p.y;
+        uint32_t b = 0;
+        if (!u.force) {
+            for (int i = 1; i < VL; ++i) {
+                const float2 p = trk[i];
+                const float fi = (float)i;
+                const float dx = fmaf(fi, u.sx, u.bx) + p.x, dy = fmaf(fi, u.sy, u.by) + p.y;
 #pragma unroll
-        for (int k = 0; k < S3_DIRS; ++k) {
-            if (fabsf(fmaf(cs[k], dx0, sn[k] * dy0)) < thr_rank) bits0 |= 1u << k;
-            if (fabsf(fmaf(cs[k], dx1, sn[k] * dy1)) < thr_rank) bits1 |= 1u << k;
+                for (int k = 0; k < S3_DIRS; ++k)
+                    if (fabsf(fmaf(dirs[k].x, dx, dirs[k].y * dy)) < thr_rank) b |= 1u << k;
+            }
         }
+        bits[m] = b;
     }
 #pragma unroll
     for (int k = 0; k < S3_DIRS; ++k) {
-        const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, (bits0 >> k) & 1u)) +
-                           (uint32_t)__popc(__ballot_sync(0xffffffffu, (bits1 >> k) & 1u));
+        uint32_t c = 0;
+#pragma unroll
+        for (int m = 0; m < S3_AXIS_TL; ++m) c += (uint32_t)__popc(__ballot_sync(0xffffffffu, (bits[m] >> k) & 1u));
         if (lane == 0 && c) atomicAdd(&cnt[k], c);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         int best = 0;
         for (int k = 1; k < S3_DIRS; ++k) if (cnt[k] < cnt[best]) best = k;
-        float bs, bc;
-        sincospif((float)best / (float)S3_DIRS, &bs, &bc);
-        s.slab_dir[pair] = make_float2(bc, bs);
+        s.slab_dir[pair] = dirs[best];
     }
 }
 
