@@ -32,8 +32,9 @@ def main():
         len(day), n_pairs, n, float(n_pairs) * n), "modes": {}}
     scn = capi.Scenario(day, ring)
     res = {}
-    for name, prec in (("fp64", capi.FP64), ("mixed", capi.MIXED), ("fp32", capi.FP32), ("mixed+reach_cull", capi.MIXED)):
-        flags = capi.FLAG_REACH_CULL if name.endswith("cull") else 0
+    for name, prec in (("fp64", capi.FP64), ("mixed", capi.MIXED), ("mixed, 2-D screen (round-1 kernel)", capi.MIXED),
+                       ("fp32", capi.FP32), ("mixed+reach_cull", capi.MIXED)):
+        flags = capi.FLAG_REACH_CULL if name.endswith("cull") else (capi.FLAG_SCREEN_2D if "2-D" in name else 0)
         eng.simulate(scn, seed=4, trial_count=64, precision=prec, flags=flags)                  # warm-up
         r = eng.simulate(scn, seed=4, trial_count=n, precision=prec, flags=flags, record_capacity=1 << 20)
         res[name] = r
@@ -42,8 +43,11 @@ def main():
                               "tests_evaluated": st["tests_evaluated"], "tests_culled": st["tests_culled"],
                               "tests_per_s": (st["tests_evaluated"] + st["tests_culled"]) / (st["ms_device_total"] * 1e-3),
                               "trials_per_s": st["trials"] / (st["ms_device_total"] * 1e-3),
-                              "candidates": st["candidates"], "level2": st["level2"]}
+                              "candidates": st["candidates"], "level2": st["level2"], "slab_survivors": st["slab_survivors"],
+                              "ms_trials": st["ms_trials"]}
     a, b, c, d = res["fp64"], res["mixed"], res["fp32"], res["mixed+reach_cull"]
+    b2 = res["mixed, 2-D screen (round-1 kernel)"]
+    assert np.array_equal(a.counts, b2.counts)
     out["mixed_equals_fp64"] = bool(np.array_equal(a.counts, b.counts) and np.array_equal(
         a.records[["track", "drone", "trial", "first_hit"]], b.records[["track", "drone", "trial", "first_hit"]]))
     out["cull_equals_fp64"] = bool(np.array_equal(a.counts, d.counts) and np.array_equal(

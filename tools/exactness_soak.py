@@ -22,7 +22,8 @@ for name, path in (("1km", pk.RING_1KM), ("5km", pk.RING_5KM)):
     for ti in range(len(tracks)):
         a = eng.simulate(tracks[ti:ti + 1], ring, seed=99, trial_count=n, precision=capi.FP64, record_capacity=1 << 19)
         rows = {}
-        for mode, flags in (("mixed", 0), ("cull", capi.FLAG_REACH_CULL), ("substep", capi.FLAG_SUBSTEP)):
+        for mode, flags in (("mixed", 0), ("mixed2d", capi.FLAG_SCREEN_2D), ("cull", capi.FLAG_REACH_CULL),
+                            ("substep", capi.FLAG_SUBSTEP)):
             ref = a if mode != "substep" else eng.simulate(tracks[ti:ti + 1], ring, seed=99, trial_count=n // 8,
                                                            precision=capi.FP64, flags=flags, record_capacity=1 << 20)
             cnt = n if mode != "substep" else n // 8
@@ -32,7 +33,8 @@ for name, path in (("1km", pk.RING_1KM), ("5km", pk.RING_5KM)):
                         np.array_equal(ref.records[["drone", "trial", "first_hit"]], b.records[["drone", "trial", "first_hit"]]) and
                         np.array_equal(ref.records["min_dist"], b.records["min_dist"]))
             rows[mode] = {"identical": same, "hits": int(ref.hits), "trials": int(b.stats["trials"]),
-                          "candidates": int(b.stats["candidates"]), "level2": int(b.stats["level2"])}
+                          "candidates": int(b.stats["candidates"]), "level2": int(b.stats["level2"]),
+                          "slab_survivors": int(b.stats["slab_survivors"]), "ms_trials": b.stats["ms_trials"]}
             assert same, (name, ti, mode)
         out["%s/track%d" % (name, ti)] = rows
         print(name, ti, rows, flush=True)
