@@ -554,31 +554,14 @@ static bool scenario_is_resident(const dcrp_engine* e, const dcrp_track* tracks,
 }
 
 // ------------------------------------------------------------------ run
-// One instantiation of the screen kernel: R rounds x 2 trials per thread per item, BLOCK threads,
-// at least MINB CTAs per SM.
-struct ScreenCfg {
-    int rounds, block, minb, np;
-    const void* kern[4];          // plain, replay table, reach culling, profiling (DCRP_DEBUG phase ablation)
-};
-template <int R, int BLOCK, int MINB, int NP>
-static ScreenCfg make_cfg()
-{
-    ScreenCfg c{R, BLOCK, MINB, NP, {(const void*)k_screen2<R, BLOCK, false, MINB, NP, false, false>,
-                                     (const void*)k_screen2<R, BLOCK, true, MINB, NP, false, false>,
-                                     (const void*)k_screen2<R, BLOCK, false, MINB, NP, true, false>,
-                                     (const void*)k_screen2<R, BLOCK, false, MINB, NP, false, true>}};
-    return c;
-}
-// [0] is the production configuration; the others exist for the tuning sweep
-// (tools/profile_target.py with DCRP_SCREEN_CFG=n) and cost nothing unless selected.
-static ScreenCfg g_cfgs[] = {make_cfg<2, 384, 2, 2>(), make_cfg<4, 512, 2, 1>()};
-static ScreenCfg& screen_cfg()
-{
-    static const int sel = std::getenv("DCRP_SCREEN_CFG") ? std::atoi(std::getenv("DCRP_SCREEN_CFG")) : 0;
-    const int n = (int)(sizeof g_cfgs / sizeof g_cfgs[0]);
-    return g_cfgs[(sel >= 0 && sel < n) ? sel : 0];
-}
-static uint64_t screen_chunk() { const ScreenCfg& c = screen_cfg(); return (uint64_t)2 * c.np * c.rounds * c.block; }
+// k_screen2's one configuration (profiles/r01_screen_cfg_sweep.txt has the sweep that chose it): R = 2 rounds,
+// 384 threads, 2 CTAs per SM, NP = 2 packed pairs per lane -> 3072-trial items.
+constexpr int S2_R = 2, S2_BLOCK = 384, S2_MINB = 2, S2_NP = 2;
+static const void* const g_screen2[3] = {                   // plain, replay table, reach culling
+    (const void*)k_screen2<S2_R, S2_BLOCK, false, S2_MINB, S2_NP, false, false>,
+    (const void*)k_screen2<S2_R, S2_BLOCK, true, S2_MINB, S2_NP, false, false>,
+    (const void*)k_screen2<S2_R, S2_BLOCK, false, S2_MINB, S2_NP, true, false>};
+static uint64_t screen_chunk() { return (uint64_t)2 * S2_NP * S2_R * S2_BLOCK; }
 
 // MaxDynamicSharedMemorySize belongs to the (function, device) pair, not to an engine: another engine on the same
 // device may have set it for a smaller scenario.  So it is always RAISED to the most the device allows (opt-in
@@ -596,31 +579,27 @@ static cudaError_t allow_max_dynamic_smem(const dcrp_engine* e, const void* kern
 static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                                   cudaStream_t st)
 {
-    ScreenCfg& c = screen_cfg();
-    static const uint32_t dbg = std::getenv("DCRP_DEBUG") ? (uint32_t)std::atoi(std::getenv("DCRP_DEBUG")) : 0u;
-    const int v = r.replay ? 1 : (r.cull ? 2 : (dbg ? 3 : 0));     // r.cull is never set together with a replay table
-    const void* kern = c.kern[v];
+    const int v = r.replay ? 1 : (r.cull ? 2 : 0);     // r.cull is never set together with a replay table
+    const void* kern = g_screen2[v];
     int tile_steps = e->sd.n_steps_max <= 128 ? 128 : 512;
     const size_t smem = (size_t)2 * tile_steps * 8 + (size_t)screen_chunk() * 16 + 80 * 4 + 16 +
                         (size_t)SCREEN_TAB * (sizeof(double2) + sizeof(float2) + sizeof(int2)) +
-                        (2 * c.np * c.rounds > 4 ? (size_t)screen_chunk() * 2 : 0);   // order[] of the K > 4 variants
+                        (2 * S2_NP * S2_R > 4 ? (size_t)screen_chunk() * 2 : 0);   // order[] of the K > 4 variants
     if (e->screen_smem[v] != smem) {
         cudaError_t ce = allow_max_dynamic_smem(e, kern);
         if (ce != cudaSuccess) return ce;
-        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], kern, c.block, smem);
+        ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->screen_occ[v], kern, S2_BLOCK, smem);
         if (ce != cudaSuccess) return ce;
         if (e->screen_occ[v] < 1) e->screen_occ[v] = 1;
         e->screen_smem[v] = smem;
     }
-    static const int cta_cap = std::getenv("DCRP_MAX_CTAS") ? std::atoi(std::getenv("DCRP_MAX_CTAS")) : 0;
-    const int occ = (cta_cap > 0 && cta_cap < e->screen_occ[v]) ? cta_cap : e->screen_occ[v];
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_items, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * occ);
-    static const uint32_t stagger_ns =
-        std::getenv("DCRP_STAGGER_NS") ? (uint32_t)std::atoi(std::getenv("DCRP_STAGGER_NS")) : 0u;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(
+        n_items, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->screen_occ[v]);
+    uint32_t stagger_ns = 0, dbg = 0;      // kernel-side profiling switches of round 1: never set in the product
     ScenarioDev sd = e->sd;
     RunDev rr = r;
-    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &tile_steps, (void*)&stagger_ns, (void*)&dbg};
-    cudaError_t ce = cudaLaunchKernel(kern, dim3(grid), dim3((unsigned)c.block), args, smem, st);
+    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &tile_steps, &stagger_ns, &dbg};
+    cudaError_t ce = cudaLaunchKernel(kern, dim3(grid), dim3((unsigned)S2_BLOCK), args, smem, st);
     ++e->launches; ++e->launches_this_run;
     return ce != cudaSuccess ? ce : cudaGetLastError();
 }
@@ -968,29 +947,18 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
 {
     NvtxRange nvtx_("dcrp_simulate");
     if (!result || !result->counts) return fail(DCRP_ERR_INVALID, "dcrp_simulate: result->counts is required");
-    static const bool timing = std::getenv("DCRP_HOST_TIMING") != nullptr;     // profiling aid (tools/e2e_breakdown.py)
-    using clk = std::chrono::steady_clock;
-    const clk::time_point t0 = clk::now();
     if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
     // Drone::Simulation calls this once per (aircraft, drone) with the same arrays, a bench once per step:
     // the scenario already in HBM (tables of stage 1 included) is reused when the inputs are unchanged.
     const bool cached = scenario_is_resident(e, tracks, n_tracks, drones, n_drones, model);
     int rc = cached ? DCRP_OK : dcrp_scenario_upload(e, tracks, n_tracks, drones, n_drones, model);
     if (rc != DCRP_OK) return rc;
-    const clk::time_point t1 = clk::now();
     rc = dcrp_run_async(e, run, nullptr, nullptr);
     if (rc != DCRP_OK) return rc;
-    const clk::time_point t2 = clk::now();
     rc = dcrp_fetch(e, result);
     if (rc != DCRP_OK) return rc;
     if (cached) result->stats.status |= DCRP_STAT_SCENARIO_CACHED;
     else        result->stats.h2d_bytes += e->h2d_scenario;
-    if (timing) {
-        const clk::time_point t3 = clk::now();
-        auto us = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-        std::fprintf(stderr, "dcrp_simulate host us: upload %.1f  run_async %.1f  fetch %.1f  total %.1f\n", us(t0, t1), us(t1, t2),
-                     us(t2, t3), us(t0, t3));
-    }
     return DCRP_OK;
 }
 
@@ -1068,7 +1036,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     ap.l2 = e->d_ap_l2.as<uint2>();
     ap.l2_count = ap.hist + (size_t)s.n_drones * run->ref_takeoff_t;      // last word of the hist buffer
     ap.l2_cap = L2_CAP;
-    static const int ap_np = (std::getenv("DCRP_AP_NP") && std::atoi(std::getenv("DCRP_AP_NP")) == 1) ? 1 : 2;
+    constexpr int ap_np = 2;               // packed pairs per lane of k_ap_scan_tracks
     const uint32_t ap_rays = (uint32_t)(2 * ap_np * AP_BLOCK);         // rays per CTA
     ap.blocks_per_drone = (uint32_t)((run->ray_count + ap_rays - 1) / ap_rays);
 
@@ -1088,7 +1056,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         CU(cudaGetLastError());
 
         const size_t smem = (size_t)AP_STAGES * AP_TILE * 8 + 2 * AP_STAGES * sizeof(uint64_t);
-        const void* kern = ap_np == 1 ? (const void*)k_ap_scan_tracks<1> : (const void*)k_ap_scan_tracks<2>;
+        const void* kern = (const void*)k_ap_scan_tracks<ap_np>;
         int& occ = e->ap_occ;
         if (occ == 0) {
             CU(allow_max_dynamic_smem(e, kern));
