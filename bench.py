@@ -670,6 +670,9 @@ def engine_arm(args):
         "peak_source": "FFMA-only micro-kernel measured on this device in this run (MEASURED_PEAKS.json has no "
                        "FP32 figure); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
         "algorithmic_flop_per_test": FLOP_PER_TEST, "tests_per_launch": tests_per_launch, "kernel_ms": k_ms,
+        "kernel_ms_is": "CUDA events on the launch stream around k_run_init + k_screen3: the screen kernel is launched "
+                        "programmatically dependent on the 2 us clearing launch and overlaps it, so no event can stand "
+                        "between the two; k_screen3 alone is ~2 us less (ncu: profiles/r02_bench_launches.csv)",
         "peaks_measured_tflops": peaks,
         "achieved_executed": achieved * exec_per_test / 11.0, "frac_executed": achieved * exec_per_test / 11.0 / peak,
         "issued_over_evaluated": stats_sum["tests_issued"] / max(1, stats_sum["tests_evaluated"]),

@@ -1392,6 +1392,7 @@ __global__ void __launch_bounds__(64) k_trajectory(const ScenarioDev s, const Re
 __global__ void __launch_bounds__(256) k_run_init(uint32_t* out, uint32_t first_off, uint32_t n,
                                                   unsigned long long* ext, uint32_t n_ext)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // a dependent k_screen3 may start its first item now
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (i < first_off) ? 0u : 0x7fffffffu;
     if (i < n_ext) ext[i] = 0ull;

@@ -222,6 +222,10 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
     }
 }
 
+// griddepcontrol.wait: returns once the grid this one was programmatically launched behind has completed and its
+// writes are visible (immediately when the launch carried no such dependency).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int MINB>
 __global__ void __launch_bounds__(S3_BLOCK, MINB)
 k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad)
@@ -246,9 +250,14 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         return n_warps + __shfl_sync(0xffffffffu, v, 0);
     };
 
+    // Programmatic dependent launch: this grid may start while the launch that clears the output arena (k_run_init) is
+    // still running.  Tables, draws and the slab scan of the first item touch nothing it writes; griddep_wait() stands
+    // before the first access to the arena (the work counter, and whatever s3_rescan publishes).
     uint32_t item = blockIdx.x * (S3_BLOCK / 32) + (uint32_t)warp;
+    uint32_t next_item = 0;
+    bool first = true;
     while (item < n_items) {
-        const uint32_t next_item = grab();        // in flight while this item is processed
+        if (!first) next_item = grab();           // in flight while this item is processed
         const int pair = (int)r.div_chunks.div(item);
         const uint32_t c = item - (uint32_t)pair * chunks_per_pair;
         const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
@@ -373,13 +382,16 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             nsurv += (uint32_t)__popc(pass);
             __syncwarp();
             while (list_n >= S3_RESCAN) {
+                griddep_wait();
                 list_n -= S3_RESCAN;
                 s3_rescan(s, r, list + list_n, S3_RESCAN, list_track, chunks_per_pair);
                 __syncwarp();
             }
         }
+        if (first) { griddep_wait(); next_item = grab(); first = false; }
         item = next_item;
     }
+    griddep_wait();
     if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair);
 
     // statistics: one set of global atomics per CTA, not per warp (they all land on the same three L2 lines, and
