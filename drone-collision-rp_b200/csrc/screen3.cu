@@ -346,7 +346,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
 #pragma unroll
             for (int p = 0; p < S3_NPL; ++p) PN[p] = ffma2(t02, SN[p], BN[p]);      // exact re-base
             const int nq = (min(VL, t0 + S3_REBASE) - t0 + 3) >> 2;
-#pragma unroll 2
+#pragma unroll 4
             for (int k = 0; k < nq; ++k) {
                 const float4 cq = t4[(t0 >> 2) + k];
 #define S3_STEP2(va, vb)                                                                      \
@@ -368,9 +368,16 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         }
 
         // ---- survivors -> this warp's queue (item, local); a full round of them goes through the 2-D scan
-        uint32_t pass = fmask;
+        // (one compare of the lane's smallest minimum first: 99 % of the lanes have nothing to queue)
+        float mall = mn[0];
 #pragma unroll
-        for (int m = 0; m < S3_TL; ++m) if (mn[m] < s.thr_slab) pass |= 1u << m;
+        for (int m = 1; m + 1 < S3_TL; m += 2) mall = fminf(fminf(mall, mn[m]), mn[m + 1]);
+        mall = fminf(mall, mn[S3_TL - 1]);
+        uint32_t pass = fmask;
+        if (mall < s.thr_slab) {
+#pragma unroll
+            for (int m = 0; m < S3_TL; ++m) if (mn[m] < s.thr_slab) pass |= 1u << m;
+        }
         if (__any_sync(0xffffffffu, pass != 0u)) {
 #pragma unroll
             for (int m = 0; m < S3_TL; ++m) {
