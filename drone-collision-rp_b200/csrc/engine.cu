@@ -128,8 +128,8 @@ struct dcrp_engine {
     DevBuf d_reach, d_alive, d_reach_tot;
     DevBuf d_slab_dir;             // k_screen3: slab direction per pair
     bool slab_ready = false;       // k_slab_axis has run for the current scenario
-    size_t s3_smem = 0;
-    int s3_occ = 0;
+    size_t s3_smem[2] = {0, 0};    // [0] k_screen3<3>, [1] k_screen3<4>
+    int s3_occ[2] = {0, 0};
     bool prepare_timed = false;
 
     // run
@@ -608,19 +608,23 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
 static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                           cudaStream_t st, bool behind_run_init)
 {
-    const void* kern = (const void*)k_screen3<3>;
+    // Two register budgets: 80 registers / 3 CTAs per SM for launches of a few items per warp (fewer, faster warps:
+    // shorter tail; 0.162 against 0.166 ms at 1.0e7 trials), 64 registers / 4 CTAs per SM (spills in the per-item
+    // code, more warps to hide them) for long launches (1.298 against 1.325 ms at 1.0e8 trials).
+    const int wide = (uint64_t)n_items >= (uint64_t)24 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
+    const void* kern = wide ? (const void*)k_screen3<4> : (const void*)k_screen3<3>;
     int vl_pad = (e->sd.n_steps_max + 3) & ~3;
     int tk_pad = (e->sd.t_max + 3) & ~3;
     const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);
-    if (e->s3_smem != smem) {
+    if (e->s3_smem[wide] != smem) {
         CU(allow_max_dynamic_smem(e, kern));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ, kern, S3_BLOCK, smem));
-        if (e->s3_occ < 1) e->s3_occ = 1;
-        e->s3_smem = smem;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&e->s3_occ[wide], kern, S3_BLOCK, smem));
+        if (e->s3_occ[wide] < 1) e->s3_occ[wide] = 1;
+        e->s3_smem[wide] = smem;
     }
     const uint64_t ctas_wanted = ((uint64_t)n_items + (S3_BLOCK / 32) - 1) / (S3_BLOCK / 32);   // one item per warp at least
     const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
-        ctas_wanted, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ));
+        ctas_wanted, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ[wide]));
     // the first launch of a run finds the counter cleared by k_run_init (word 2 of the output arena)
     if (r.slice_first != 0) CU(cudaMemsetAsync(e->d_out.as<uint32_t>() + 2, 0, 4, st));
     ScenarioDev sd = e->sd;

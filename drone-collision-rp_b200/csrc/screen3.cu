@@ -22,10 +22,12 @@
 namespace dcrp {
 
 constexpr int S3_NPL = 4;                 // packed pairs per lane in the slab phase
-constexpr int S3_TL = 2 * S3_NPL;         // trials per lane per item
-constexpr int S3_CHW = 32 * S3_TL;        // trials per warp item
+constexpr int S3_TL = 2 * S3_NPL;         // trials per lane per round
+constexpr int S3_RND = 32 * S3_TL;        // trials per warp round
+constexpr int S3_R = 2;                   // rounds per item: the pair's tables are staged once per item
+constexpr int S3_CHW = S3_RND * S3_R;     // trials per warp item
 constexpr int S3_RESCAN = 128;            // survivors per 2-D re-scan round (4 per lane = 2 packed pairs)
-constexpr int S3_LIST = S3_RESCAN + S3_CHW;
+constexpr int S3_LIST = S3_RESCAN + S3_RND;
 constexpr int S3_BLOCK = 256;
 constexpr int S3_MAX_VL = 512;            // longest track the per-warp projected table holds
 constexpr int S3_MAX_T = 128;             // largest takeoff_t the per-warp kink tables hold
@@ -292,17 +294,20 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             __syncwarp();
         }
 
-        // ---- draws + slab ray of this lane's S3_TL trials.  Branch-free: the slots past a ragged last item
-        // compute a (harmless) trial beyond the range and are masked afterwards.
-        float bn[S3_TL], sn[S3_TL];
-        uint32_t fmask = 0, t1s = 0;               // item-local: the run-long accumulators are touched once per item
+        uint32_t t1s = 0;                          // item-local: the run-long accumulators are touched once per item
         const uint64_t trial0 = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + (uint32_t)lane;
         const uint32_t t0lo = (uint32_t)trial0, t0hi = (uint32_t)(trial0 >> 32);
         const uint32_t pj = r.drone_base + (uint32_t)j, pa = r.track_base + (uint32_t)a;
+#pragma unroll 1
+        for (uint32_t rbase = 0; rbase < n_valid; rbase += S3_RND) {
+        // ---- draws + slab ray of this lane's S3_TL trials of the round.  Branch-free: the slots past a ragged last
+        // item compute a (harmless) trial beyond the range and are masked afterwards.
+        float bn[S3_TL], sn[S3_TL];
+        uint32_t fmask = 0;
 #pragma unroll
         for (int m = 0; m < S3_TL; ++m) {
-            const bool valid = (uint32_t)(m * 32 + lane) < n_valid;
-            const uint32_t c0 = t0lo + (uint32_t)(m * 32);
+            const bool valid = rbase + (uint32_t)(m * 32 + lane) < n_valid;
+            const uint32_t c0 = t0lo + rbase + (uint32_t)(m * 32);
             const U4 w = philox4x32_10_rk(c0, t0hi + (c0 < t0lo ? 1u : 0u), pj, pa, r.rk);
             const int t1st = draw_t1st(w.x, takeoff_t);
             const int last = t1st - 1;
@@ -322,14 +327,6 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             t1s += valid ? (uint32_t)t1st : 0u;
             bn[m] = valid ? b : 1e15f;
             sn[m] = valid ? sv : 0.f;
-        }
-        const uint32_t nv = n_valid > (uint32_t)lane ? (n_valid - (uint32_t)lane + 31u) >> 5 : 0u;   // this lane's valid slots
-        acc_t1 += t1s;
-        acc_is += nv * (uint32_t)VL;                 // slab lane-steps of this lane's trials
-        if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {      // rare: keep the 32-bit partial sums exact
-            atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
-            atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
-            acc_t1 = acc_is = 0;
         }
 
         // ---- LEVEL 1a, the slab: min over the indices of |n . D(i)|, D(i) = P(i) - A(i), P(i) = B + i*S
@@ -383,7 +380,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             for (int m = 0; m < S3_TL; ++m) {
                 const bool on = (pass >> m) & 1u;
                 const uint32_t bal = __ballot_sync(0xffffffffu, on);
-                if (on) list[list_n + __popc(bal & ((1u << lane) - 1u))] = make_uint2(item, (uint32_t)(m * 32 + lane));
+                if (on) list[list_n + __popc(bal & ((1u << lane) - 1u))] = make_uint2(item, rbase + (uint32_t)(m * 32 + lane));
                 list_n += __popc(bal);
             }
             nsurv += (uint32_t)__popc(pass);
@@ -396,6 +393,15 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             }
         }
         if (first) { griddep_wait(); next_item = grab(); first = false; }
+        }   // rounds
+        const uint32_t nv = n_valid > (uint32_t)lane ? (n_valid - (uint32_t)lane + 31u) >> 5 : 0u;   // this lane's valid slots
+        acc_t1 += t1s;
+        acc_is += nv * (uint32_t)VL;                 // slab lane-steps of this lane's trials
+        if (acc_t1 > 0x40000000u || acc_is > 0x40000000u) {      // rare: keep the 32-bit partial sums exact
+            atomicAdd(&r.stats[ST_SHARED], (unsigned long long)acc_t1);
+            atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
+            acc_t1 = acc_is = 0;
+        }
         item = next_item;
     }
     griddep_wait();
