@@ -159,6 +159,7 @@ struct dcrp_engine {
     int reserve_sms = 0;           // SMs kept free for the caller's communication kernels
     bool run_cull = false;         // the last run used DCRP_FLAG_REACH_CULL
     bool run_screen3 = false;      // the last run went through k_screen3
+    bool has_confirm = false;      // the last run launched a separate confirm / resolve kernel (ev_trials recorded)
     bool k0_is_begin = false;      // ... launched programmatically behind k_run_init: no event between the two
     bool reach_ready = false;      // k_reach has run for the current scenario
     uint64_t ap_rays = 0;
@@ -810,14 +811,15 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
             }
         }
     }
-    CU(cudaEventRecord(e->ev_trials, st));
-    if (run->precision == DCRP_PRECISION_MIXED && run->trial_count && !use3) {    // k_screen3 confirms in-kernel
+    e->has_confirm = run->precision == DCRP_PRECISION_MIXED && run->trial_count && !use3;    // k_screen3 confirms in-kernel
+    if (e->has_confirm) {
+        CU(cudaEventRecord(e->ev_trials, st));
         // grid-stride over the candidate list whose length lives on the device
         k_confirm_all<<<e->prop.multiProcessorCount * 4, 128, 0, st>>>(s, r);
         ++e->launches; ++e->launches_this_run;
         CU(cudaGetLastError());
     }
-    CU(cudaEventRecord(e->ev_end, st));
+    CU(cudaEventRecord(e->ev_end, st));      // (without a confirm kernel this is also the end of the trial kernels)
     e->run_event_valid = true;
     e->has_run = true;
     return DCRP_OK;
@@ -952,9 +954,12 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     }
     o.ms_prepare = e->ms_prepare;
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, e->k0_is_begin ? e->ev_begin : e->ev_k0, e->ev_trials)); o.ms_trials = ms;
-    CU(cudaEventElapsedTime(&ms, e->ev_trials, e->ev_end));   o.ms_confirm = ms;
+    // as few event queries as the run needs (each is a driver call; a 1e7-trial run is 170 us)
+    cudaEvent_t trials_end = e->has_confirm ? e->ev_trials : e->ev_end;
     CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));    o.ms_device_total = ms;
+    if (e->k0_is_begin && !e->has_confirm) o.ms_trials = ms;
+    else { CU(cudaEventElapsedTime(&ms, e->k0_is_begin ? e->ev_begin : e->ev_k0, trials_end)); o.ms_trials = ms; }
+    if (e->has_confirm) { CU(cudaEventElapsedTime(&ms, e->ev_trials, e->ev_end)); o.ms_confirm = ms; }
     o.h2d_bytes = e->h2d_run;
     o.d2h_bytes = d2h;
     return DCRP_OK;
@@ -1100,6 +1105,8 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(e->ev_trials, st));
+    e->has_confirm = true;
+    e->k0_is_begin = false;
     if (n_rays) {
         k_ap_resolve<<<e->prop.multiProcessorCount * 4, 128, 0, st>>>(s, r, ap);
         ++e->launches; ++e->launches_this_run;
