@@ -6,15 +6,16 @@
 // per two tests instead of six packed ops, and with a well-chosen n it clears 90-99 % of the trials
 // (5 km ring: 99 %); the survivors queue up per warp and are re-scanned 128 at a time by the 2-D
 // level-1 scan of kernels.cu (scan_tile_xy), then level 2 (3-D fp32) and level 3 (the fp64 decision in the
-// reference's order of operations, one warp per candidate) -- all inside this one kernel.
+// reference's order of operations, by the lane that holds the candidate) -- all inside this one kernel.
 // Decisions are those of the all-fp64 kernel by construction: every level is conservative and the last
 // one is exact (tests/test_gpu_parity.py, test_gpu_fuzz.py).
 //
 // No sort: the slab test of an index before the trial's kink (i < t1st) evaluates the stage-2 ray
 // extrapolated backwards, which can only ADD survivors, so all lanes scan the whole track from index 0
 // with warp-uniform bounds and nothing is staged in shared memory per trial.  Warps are independent
-// (no CTA barrier in steady state): each pulls 256-trial items from a device-side counter, keeps its
-// pair's projected track and kink tables in its own shared-memory slice, and keeps its own survivor queue.
+// (no CTA barrier in steady state): each pulls 512-trial items (two rounds of 8 trials per lane) from a
+// device-side counter, keeps its pair's projected track and kink tables in its own shared-memory slice,
+// and keeps its own survivor queue.
 //
 // Reference semantics: /root/reference/Drone.cpp:107-127,164-231,253-265 (restated in dcrp_math.cuh).
 #include "dcrp_device.cuh"
