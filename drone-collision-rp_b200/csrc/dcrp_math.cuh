@@ -312,4 +312,33 @@ DCRP_HD Ray32 stage2_ray32(float dls, float dbs, float da,
     return r;
 }
 
+// ---------------------------------------------------------------- 1-D slab level (screen3.cu)
+// The stage-2 ray projected on a unit vector n, relative to the scenario origin: n . position(i) = b + i * s for the
+// absolute index i.  (dls, dbs) = target - kink and ada = |target altitude - start altitude|, each formed in fp64
+// and rounded once; pln = n . (kink - origin); lastf = float(t1st - 1).  Same speed law as stage2_ray32
+// (Drone.cpp:216-220), one MUFU.RSQ on the device.
+struct Slab32 {
+    float b, s;
+    bool  degenerate;    // target (numerically) on top of the kink: the trial must be confirmed
+};
+
+DCRP_HD Slab32 slab_ray32(float dls, float dbs, float ada, float pln, float lastf, float nx, float ny,
+                          float v_straight, float coef)
+{
+    Slab32 o;
+    const float m2 = fmaf(dls, dls, dbs * dbs);
+    o.degenerate = !(m2 > 1e-12f);
+#if defined(__CUDA_ARCH__)
+    float inv_m;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_m) : "f"(m2));
+#else
+    const float inv_m = 1.0f / sqrtf(m2);
+#endif
+    const float pitch = atan_nonneg(ada * inv_m);                 // Drone.cpp:218
+    const float k = inv_m * fmaf(-coef, pitch, v_straight);       // vf / m, Drone.cpp:220
+    o.s = fmaf(dls, nx, dbs * ny) * k;                            // n . step
+    o.b = fmaf(-lastf, o.s, pln);                                 // n . position(0)
+    return o;
+}
+
 }  // namespace dcrp

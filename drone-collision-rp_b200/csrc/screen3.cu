@@ -316,14 +316,9 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             const float dls = (float)fma((double)w.y, ts.wx32, kk.x);     // target - kink, rounded once
             const float dbs = (float)fma((double)w.z, ts.wy32, kk.y);
             const float ada = fabsf(fmaf((float)w.w, ts.wz32, ts.z0rel));
-            const float m2 = fmaf(dls, dls, dbs * dbs);
-            float inv_m;
-            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_m) : "f"(m2));
-            const float pitch = atan_nonneg(ada * inv_m);                 // Drone.cpp:218
-            const float k = inv_m * fmaf(-s.coef_f, pitch, s.v_straight_f);   // vf / m, Drone.cpp:220
-            const float sv = fmaf(dls, nd.x, dbs * nd.y) * k;             // n . step
-            const float b = fmaf(-(float)last, sv, tabpn[last]);          // n . position(0)
-            const bool force = !(m2 > 1e-12f) || s1_first <= last;        // degenerate ray / stage-1 conflict
+            const Slab32 u = slab_ray32(dls, dbs, ada, tabpn[last], (float)last, nd.x, nd.y, s.v_straight_f, s.coef_f);
+            const float sv = u.s, b = u.b;
+            const bool force = u.degenerate || s1_first <= last;          // degenerate ray / stage-1 conflict
             fmask |= (valid && force) ? (1u << m) : 0u;
             t1s += valid ? (uint32_t)t1st : 0u;
             bn[m] = valid ? b : 1e15f;

@@ -143,4 +143,41 @@ void hs_screen(const double* ax, const double* ay, const double* az, int n_steps
     }
 }
 
+// Level 1a of k_screen3 for n draws of one (track, drone) along the unit vector (nx, ny): the scalar form of the packed
+// sequence -- projected track table T_i = n . (-A_i) (index 0 never passes), projected kink table, slab_ray32, scan of
+// ALL indices from 0 (the ray extrapolated backwards before the kink), D = P + T_i, P += S, exact re-base every 128.
+// Returns min over i >= 1 of |n . D(i)| per draw (0 for a degenerate ray).
+void hs_slab(const double* ax, const double* ay, int n_steps, int takeoff_t, double x0, double y0, double heading0,
+             double start_alt, double v_straight, double v_ascend, double ox, double oy, double nx, double ny,
+             const Draw* draws, long n, float* min_abs_out)
+{
+    const double s1x = std::sin(heading0) * v_straight, s1y = std::cos(heading0) * v_straight;
+    std::vector<double> p1x(takeoff_t), p1y(takeoff_t);
+    std::vector<float> pln(takeoff_t), T(n_steps);
+    const float fnx = (float)nx, fny = (float)ny;
+    double x = x0, y = y0;
+    for (int i = 0; i < takeoff_t; ++i) {
+        if (i > 0) { x = DADD(x, s1x); y = DADD(y, s1y); }
+        p1x[i] = x; p1y[i] = y;
+        pln[i] = fmaf(fnx, (float)DSUB(x, ox), fny * (float)DSUB(y, oy));
+    }
+    for (int i = 0; i < n_steps; ++i)
+        T[i] = i == 0 ? 1e15f : fmaf(fnx, -(float)(ax[i] - ox), fny * -(float)(ay[i] - oy));
+    const float coef = (float)(2.0 * (v_straight - v_ascend) / DCRP_PI);
+    for (long r = 0; r < n; ++r) {
+        const Draw& d = draws[r];
+        const int last = d.t1st - 1;
+        const Slab32 u = slab_ray32((float)DSUB(d.tx, p1x[last]), (float)DSUB(d.ty, p1y[last]),
+                                    fabsf((float)DSUB(d.tz, start_alt)), pln[last], (float)last, fnx, fny,
+                                    (float)v_straight, coef);
+        float mn = 3.0e38f;
+        for (int t0 = 0; t0 < n_steps; t0 += 128) {
+            float p = fmaf((float)t0, u.s, u.b);
+            const int hi = t0 + 128 < n_steps ? t0 + 128 : n_steps;
+            for (int i = t0; i < hi; ++i) { mn = fminf(mn, fabsf(p + T[i])); p += u.s; }
+        }
+        min_abs_out[r] = u.degenerate ? 0.f : mn;
+    }
+}
+
 }  // extern "C"

@@ -222,6 +222,7 @@ class HostSim:
                                                                                    C.c_void_p, C.c_void_p]
         L.hs_screen.argtypes = [dp, dp, dp, C.c_int, C.c_int] + [C.c_double] * 9 + [C.c_void_p, C.c_long, C.c_void_p,
                                                                                     C.c_void_p]
+        L.hs_slab.argtypes = [dp, dp, C.c_int, C.c_int] + [C.c_double] * 10 + [C.c_void_p, C.c_long, C.c_void_p]
         self.L = L
 
     def philox(self, ctr, key):
@@ -230,6 +231,16 @@ class HostSim:
         o = (C.c_uint32 * 4)()
         self.L.hs_philox(c, k, o)
         return list(o)
+
+    def slab(self, trk, drone, draws, origin, direction, start_alt=100.0, v_straight=19.0, v_ascend=8.0):
+        """min over i >= 1 of |n . D(i)| in the fp32 arithmetic of k_screen3's level 1a."""
+        x, y = (np.ascontiguousarray(trk[k], dtype=np.float64) for k in "xy")
+        draws = np.ascontiguousarray(draws, dtype=DRAW_DTYPE)
+        out = np.zeros(len(draws), np.float32)
+        self.L.hs_slab(_d(x), _d(y), len(x), int(trk["takeoff_t"]), float(drone[0]), float(drone[1]), float(drone[2]),
+                       start_alt, v_straight, v_ascend, float(origin[0]), float(origin[1]), float(direction[0]),
+                       float(direction[1]), draws.ctypes.data, len(draws), out.ctypes.data)
+        return out
 
     def draws(self, seed, trial_begin, n, drone, track, takeoff_t, box):
         out = np.zeros(n, dtype=DRAW_DTYPE)

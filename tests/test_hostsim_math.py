@@ -91,3 +91,43 @@ def test_fp32_screen_levels_are_conservative_and_accurate(hostsim, golden, track
     print("worst level-2 error %.2e m; level 1 passes %d of %d golden (near-miss-enriched) trials" % (
         worst3, passed1, total))
     assert worst3 < 5e-3
+
+
+def test_slab_level_is_conservative_and_within_its_margin(hostsim, golden, tracks, ring1):
+    """Level 1a of k_screen3 (drone-collision-rp_b200/csrc/screen3.cu), the statements of dcrp_math.cuh::slab_ray32 and
+    the incremental projected scan, on the golden (near-miss-enriched) trials and 16 directions:
+      * exactness: |n . D(i)| <= |D_xy(i)|, so the slab minimum never exceeds the 2-D level-1 minimum (same trials,
+        a superset of the indices) -- beyond fp32 rounding;
+      * every trial the reference counts as a stage-2 hit is flagged with room to spare;
+      * accuracy: against the fp64 value of min_i |n . D(i)| the fp32 scan is within the margin the engine adds to the
+        radius (engine.cu: 0.02 + 76 ulp32(sqrt2 * extent) + n_steps * vmax * 2^-20 ~ 0.10 m at 8 km extent)."""
+    origin = (np.floor(0.5 * (671819.02 + 678600.0)), np.floor(0.5 * (5704300.0 + 5706300.0)), 250.0)
+    worst = 0.0
+    for p, (a, j) in enumerate(golden["pairs"]):
+        t = tracks[a]
+        draws = golden["pair%d_draws" % p][:4000]
+        first = golden["pair%d_first_hit" % p][:4000]
+        s2, _ = hostsim.screen(t, ring1[j], draws, origin)
+        s2 = np.sqrt(s2.astype(np.float64))
+        # fp64 restatement of the projected separation at every index >= 1 (ray extrapolated backwards before the kink)
+        x0, y0, h = ring1[j]
+        last = draws["t1st"].astype(np.int64) - 1
+        kx = x0 + np.cumsum(np.r_[0.0, np.full(t["takeoff_t"] - 1, np.sin(h) * 19.0)])[last]
+        ky = y0 + np.cumsum(np.r_[0.0, np.full(t["takeoff_t"] - 1, np.cos(h) * 19.0)])[last]
+        dl, db = draws["tx"] - kx, draws["ty"] - ky
+        m = np.hypot(dl, db)
+        vf = 19.0 - (2.0 * (19.0 - 8.0) / np.pi) * np.arctan(np.abs(draws["tz"] - 100.0) / m)
+        idx = np.arange(1, t["n_steps"])
+        rel = idx[None, :] - last[:, None]
+        dx = kx[:, None] + rel * (dl / m * vf)[:, None] - t["x"][None, 1:]
+        dy = ky[:, None] + rel * (db / m * vf)[:, None] - t["y"][None, 1:]
+        hit2 = first >= draws["t1st"]
+        for k in range(16):
+            n = (np.cos(np.pi * k / 16), np.sin(np.pi * k / 16))
+            got = hostsim.slab(t, ring1[j], draws, origin, n).astype(np.float64)
+            want = np.abs(n[0] * dx + n[1] * dy).min(axis=1)
+            worst = max(worst, np.abs(got - want).max())
+            assert (got <= s2 + 2e-2).all(), (p, k)                    # never above the 2-D level
+            assert (got[hit2] < 3.69 + 2e-2).all(), (p, k)             # reference hits are always flagged
+    print("worst |fp32 slab - fp64| = %.2e m" % worst)
+    assert worst < 0.08
