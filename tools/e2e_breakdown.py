@@ -27,3 +27,20 @@ for flags, name in ((0, "plain"), (capi.FLAG_REACH_CULL, "cull")):
             name, n, 1e6 * walls[len(walls) // 2], 1e6 * walls[0], 1e3 * st["ms_prepare"], 1e3 * st["ms_trials"],
             1e3 * st["ms_confirm"], 1e3 * st["ms_device_total"]))
 eng.close()
+
+# the same split into its two halves (Python-side clocks around the ctypes calls; scenario resident)
+import statistics
+eng = capi.Engine(0)
+eng.upload(tracks, ring)
+for n in (1, 101011):
+    ta, tf = [], []
+    for k in range(40):
+        t0 = time.perf_counter()
+        run = eng.run_async(seed=1, trial_begin=k * n, trial_count=n, precision=capi.MIXED)
+        t1 = time.perf_counter()
+        r = eng.fetch(run)
+        t2 = time.perf_counter()
+        ta.append(t1 - t0); tf.append(t2 - t1)
+    print("split n=%-7d run_async median %.1f us   fetch (wait + copy + unpack) median %.1f us   device_total %.1f us" % (
+        n, 1e6 * statistics.median(ta[5:]), 1e6 * statistics.median(tf[5:]), 1e3 * r.stats["ms_device_total"]))
+eng.close()
