@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(256) k_comm_push(const CommPeers peers, int ra
 {
     int dst = (int)blockIdx.x;
     if (dst >= rank) ++dst;
+    DCRP_ASSERT(dst < nranks && n <= COMM_MAX_PAIRS && peers.p[dst] != nullptr);
     unsigned long long* mb = peers.p[dst];
     unsigned long long* slot = mb + comm_slot_off(parity, nranks, rank);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) slot[i] = counts[i];

@@ -23,6 +23,22 @@
 #include <cuda_runtime.h>
 #include "dcrp_math.cuh"
 
+// Bounds checks of our own (compute-sanitizer is closed on the GPU pool): `make EXTRA=-DDCRP_BOUNDS` turns every
+// DCRP_ASSERT on an index into a printf + trap, and the GPU test tier is run once against that build
+// (profiles/r02_bounds_build_pytest.log).  Nothing in the release build.
+#if defined(DCRP_BOUNDS) && defined(__CUDA_ARCH__)
+#include <stdio.h>
+#define DCRP_ASSERT(cond)                                                                   \
+    do {                                                                                    \
+        if (!(cond)) {                                                                      \
+            printf("DCRP_BOUNDS violated: %s  (%s:%d)\n", #cond, __FILE__, __LINE__);       \
+            __trap();                                                                       \
+        }                                                                                   \
+    } while (0)
+#else
+#define DCRP_ASSERT(cond) ((void)0)
+#endif
+
 namespace dcrp {
 
 struct TrackDev {

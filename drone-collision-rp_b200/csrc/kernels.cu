@@ -364,6 +364,7 @@ __device__ __forceinline__ TrialOut exact_trial(const ScenarioDev& s, int pair, 
     o.first = (s1 <= last) ? s1 : -1;
     o.min_d2 = s.s1_prefmin[(size_t)pair * s.t_max + last];
     double x = r.x, y = r.y, z = r.z;
+    DCRP_ASSERT(d.t1st >= 1 && last < s.t_max);
     for (int i = d.t1st; i < n_steps; ++i) {                // Drone.cpp:224-230
         x = DADD(x, r.sx); y = DADD(y, r.sy); z = DADD(z, r.sz);
         const double d2 = sep2(x, y, z, ax[i], ay[i], az[i]);
@@ -425,6 +426,7 @@ __device__ __forceinline__ void publish_hit(const ScenarioDev& s, const RunDev& 
     atomicAdd(&r.counts[pair], 1ull);
     atomicMin(&r.first_conflict[pair], o.first);
     const uint32_t slot = warp_claim_slot(r.rec_count);
+    DCRP_ASSERT(pair >= 0 && pair < s.n_tracks * s.n_drones && o.first >= 0);
     if (slot < r.rec_cap) {
         Record rec;
         rec.track = (uint32_t)a; rec.drone = (uint32_t)j; rec.trial = trial;
@@ -734,6 +736,7 @@ __device__ __forceinline__ Fast32 setup_fast32(const ScenarioDev& s, const Track
     Fast32 o;
     o.t1st = (int32_t)(q.w >> 12);
     const int last = o.t1st - 1;
+    DCRP_ASSERT(last >= 0 && last < s.t_max);
     const double2 kk = kk_tab[last];
     const float2 pl = pl_tab[last];
     // target - kink: one fp64 FMA per coordinate, rounded once to fp32
@@ -890,6 +893,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
                         w1[mm] = w.y; w2[mm] = w.z; w3[mm] = w.w;
                     }
                     bucket = (uint32_t)(t1st - 1) >> s.bucket_shift;
+                    DCRP_ASSERT(t1st >= 1 && t1st <= takeoff_t && bucket < 64u);
                     meta[mm] = local | ((uint32_t)t1st << 12);
                 }
                 if (IND) stage[local] = make_uint4(w1[0], w2[0], w3[0], meta[0]);
@@ -915,6 +919,7 @@ k_screen2(const ScenarioDev s, const RunDev r, uint32_t chunks_per_pair, uint32_
 #pragma unroll
             for (int m = 0; m < K; ++m) {
                 const uint32_t slot = hist[rank[m] >> 16] + (rank[m] & 0xffffu);
+                DCRP_ASSERT(slot < (uint32_t)CH);
                 if (IND) order[slot] = (uint16_t)(m * BLOCK + tid);
                 else     stage[slot] = make_uint4(w1[IND ? 0 : m], w2[IND ? 0 : m], w3[IND ? 0 : m], meta[IND ? 0 : m]);
             }

@@ -132,8 +132,10 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
         const int idx = m * 32 + lane;
         float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
         if (idx < n) {
+            DCRP_ASSERT(n <= S3_RESCAN);
             const uint2 e = list[idx];
             const int pair = (int)r.div_chunks.div(e.x);
+            DCRP_ASSERT(pair >= a * s.n_drones && pair < (a + 1) * s.n_drones && e.y < (uint32_t)S3_CHW);
             const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
             const int j = pair - a * s.n_drones;
             const uint64_t trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
@@ -285,9 +287,11 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             for (int i = lane; i < vlr; i += 32) {
                 float v = 1e15f;
                 if (i >= 1 && i < VL) { const float2 p = __ldg(&g[i]); v = fmaf(nd.x, p.x, nd.y * p.y); }
+                DCRP_ASSERT(i < vl_pad);
                 tabT[i] = v;
             }
             for (int t = lane; t < takeoff_t; t += 32) {
+                DCRP_ASSERT(t < tk_pad && pair < s.n_tracks * s.n_drones && takeoff_t <= s.t_max);
                 tabk[t] = __ldg(&s.kink[(size_t)pair * s.t_max + t]);
                 const float2 pl = __ldg(&s.p1f[(size_t)j * s.t_max + t]);
                 tabpn[t] = fmaf(nd.x, pl.x, nd.y * pl.y);
@@ -312,6 +316,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             const U4 w = philox4x32_10_rk(c0, t0hi + (c0 < t0lo ? 1u : 0u), pj, pa, r.rk);
             const int t1st = draw_t1st(w.x, takeoff_t);
             const int last = t1st - 1;
+            DCRP_ASSERT(last >= 0 && last < takeoff_t && last < tk_pad);
             const double2 kk = tabk[last];
             const float dls = (float)fma((double)w.y, ts.wx32, kk.x);     // target - kink, rounded once
             const float dbs = (float)fma((double)w.z, ts.wy32, kk.y);
@@ -341,6 +346,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             const int nq = (min(VL, t0 + S3_REBASE) - t0 + 3) >> 2;
 #pragma unroll 4
             for (int k = 0; k < nq; ++k) {
+                DCRP_ASSERT(((t0 >> 2) + k) * 4 + 3 < vl_pad);
                 const float4 cq = t4[(t0 >> 2) + k];
 #define S3_STEP2(va, vb)                                                                      \
                 {                                                                             \
@@ -376,6 +382,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             for (int m = 0; m < S3_TL; ++m) {
                 const bool on = (pass >> m) & 1u;
                 const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                DCRP_ASSERT(list_n + __popc(bal) <= S3_LIST);
                 if (on) list[list_n + __popc(bal & ((1u << lane) - 1u))] = make_uint2(item, rbase + (uint32_t)(m * 32 + lane));
                 list_n += __popc(bal);
             }

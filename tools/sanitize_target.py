@@ -18,6 +18,19 @@ ring = scenario.load_ring(pk.RING_1KM)[40:52]
 for prec in (capi.FP64, capi.MIXED, capi.FP32):
     r = eng.simulate(tracks, ring, seed=1, trial_count=3000, precision=prec)
     print("prec", prec, "hits", r.hits, flush=True)
+# the slab-first screen with everything it can do in one launch: ragged items, a full survivor queue (re-scan rounds),
+# level 2, the in-kernel fp64 decision and the warp-aggregated record append (a 60 m "aircraft": many hits), the
+# direction choice (second run of >= 20 000 trials per pair on the scenario), and the 2-D screen / culled variants
+m = capi.default_model()
+m.aircraft_radius = 60.0
+for flags in (0, 0, capi.FLAG_SCREEN_2D, capi.FLAG_REACH_CULL):
+    r = eng.simulate(tracks[:2], ring[:3], seed=5, trial_count=20011, precision=capi.MIXED, flags=flags, model=m,
+                     record_capacity=1 << 16)
+    print("dense flags", flags, "hits", r.hits, "survivors", r.stats["slab_survivors"], "records", len(r.records), flush=True)
+uid = capi.Engine.comm_unique_id()
+eng.attach_comm(uid, 0, 1)
+eng.allreduce_counts()
+eng.detach_comm()
 eng.upload(tracks[:1], ring[:2])
 draws = eng.dump_draws(0, 1, 1, 0, 2500)
 rep = np.concatenate([eng.dump_draws(0, 0, 1, 0, 2500), draws])
