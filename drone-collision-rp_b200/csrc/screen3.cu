@@ -39,8 +39,9 @@ static_assert(S3_CHW <= 4096, "local trial index is packed in 12 bits");
 
 __host__ __device__ inline size_t s3_warp_smem(int vl_pad, int tk_pad)
 {
-    // [tabk: tk_pad double2][tabT: vl_pad float][list: S3_LIST uint2][tabpn: tk_pad float], 16-B multiple
-    size_t b = (size_t)tk_pad * 16 + (size_t)vl_pad * 4 + (size_t)S3_LIST * 8 + (size_t)tk_pad * 4;
+    // [tile: vl_pad float2 (the track's (x, y) samples, one TMA bulk copy per track change)][tabk: tk_pad double2]
+    // [tabT: vl_pad float][list: S3_LIST uint2][tabpn: tk_pad float][mbarrier + its phase: 16 B], 16-B multiple
+    size_t b = (size_t)vl_pad * 8 + (size_t)tk_pad * 16 + (size_t)vl_pad * 4 + (size_t)S3_LIST * 8 + (size_t)tk_pad * 4 + 16;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -238,10 +239,14 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wb = smem_raw + (size_t)warp * s3_warp_smem(vl_pad, tk_pad);
-    double2* tabk  = reinterpret_cast<double2*>(wb);
-    float*   tabT  = reinterpret_cast<float*>(wb + (size_t)tk_pad * 16);
-    uint2*   list  = reinterpret_cast<uint2*>(wb + (size_t)tk_pad * 16 + (size_t)vl_pad * 4);
-    float*   tabpn = reinterpret_cast<float*>(wb + (size_t)tk_pad * 16 + (size_t)vl_pad * 4 + (size_t)S3_LIST * 8);
+    float2*  tile  = reinterpret_cast<float2*>(wb);                                   // the warp's current track, (-x', -y')
+    double2* tabk  = reinterpret_cast<double2*>(wb + (size_t)vl_pad * 8);
+    float*   tabT  = reinterpret_cast<float*>(wb + (size_t)vl_pad * 8 + (size_t)tk_pad * 16);
+    uint2*   list  = reinterpret_cast<uint2*>(wb + (size_t)vl_pad * 12 + (size_t)tk_pad * 16);
+    float*   tabpn = reinterpret_cast<float*>(wb + (size_t)vl_pad * 12 + (size_t)tk_pad * 16 + (size_t)S3_LIST * 8);
+    uint64_t* bar  = reinterpret_cast<uint64_t*>(wb + (size_t)vl_pad * 12 + (size_t)tk_pad * 20 + (size_t)S3_LIST * 8);
+    if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); bar[1] = 0ull; }     // bar[1]: the barrier's phase bit
+    __syncwarp();
 
     uint32_t acc_t1 = 0, acc_is = 0, nsurv = 0;       // per-lane partial sums
     int list_n = 0, list_track = -1;       // warp-uniform
@@ -266,12 +271,27 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         const int pair = (int)r.div_chunks.div(item);
         const uint32_t c = item - (uint32_t)pair * chunks_per_pair;
         const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
-        if (a != list_track) {                    // queued survivors share one track: drain before it changes
-            if (list_n) { s3_rescan(s, r, list, list_n, list_track, chunks_per_pair); list_n = 0; }
-            list_track = a;
-        }
         const TrackDev* __restrict__ tk = s.tracks + a;
         const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
+        if (a != list_track) {                    // (once per run for a one-track scenario)
+            // queued survivors share one track: drain them before it changes
+            if (list_n) { s3_rescan(s, r, list, list_n, list_track, chunks_per_pair); list_n = 0; }
+            list_track = a;
+            // the track's samples come in by ONE 1-D TMA bulk copy; the per-item projection on the pair's direction
+            // then reads shared memory, not L2
+            __syncwarp();
+            const uint32_t phase = (uint32_t)bar[1];
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)((VL + 1) & ~1) * 8u;              // tracks are padded to an even length
+                DCRP_ASSERT(bytes <= (uint32_t)vl_pad * 8u);
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, bytes);
+                tma_bulk_g2s(tile, s.trkxy + (size_t)__ldg(&tk->off_xy), bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            __syncwarp();
+            if (lane == 0) bar[1] = phase ^ 1u;
+        }
         const uint32_t n_valid = (uint32_t)min((uint64_t)S3_CHW, r.slice_count - (uint64_t)c * S3_CHW);
         const int s1_first = __ldg(&s.s1_first_hit[pair]);
         const float2 nd = __ldg(&s.slab_dir[pair]);
@@ -281,12 +301,11 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         // ---- this pair's tables: projected track T_i = n . (-A_i) (index 0 and the padding never pass),
         // kink tables (target-box corner minus kink in fp64; kink projected on n)
         {
-            const float2* __restrict__ g = s.trkxy + (size_t)__ldg(&tk->off_xy);
             const int vlr = (VL + 3) & ~3;
             __syncwarp();
             for (int i = lane; i < vlr; i += 32) {
                 float v = 1e15f;
-                if (i >= 1 && i < VL) { const float2 p = __ldg(&g[i]); v = fmaf(nd.x, p.x, nd.y * p.y); }
+                if (i >= 1 && i < VL) { const float2 p = tile[i]; v = fmaf(nd.x, p.x, nd.y * p.y); }
                 DCRP_ASSERT(i < vl_pad);
                 tabT[i] = v;
             }
