@@ -14,8 +14,9 @@
 // extrapolated backwards, which can only ADD survivors, so all lanes scan the whole track from index 0
 // with warp-uniform bounds and nothing is staged in shared memory per trial.  Warps are independent
 // (no CTA barrier in steady state): each pulls 512-trial items (two rounds of 8 trials per lane) from a
-// device-side counter, keeps its pair's projected track and kink tables in its own shared-memory slice,
-// and keeps its own survivor queue.
+// device-side counter, keeps the track (one 1-D TMA bulk copy per track change, its own mbarrier), its pair's
+// projected track and kink tables in its own shared-memory slice, and keeps its own survivor queue.  The grid is
+// launched programmatically dependent on the launch that clears the output arena (griddep_wait below).
 //
 // Reference semantics: /root/reference/Drone.cpp:107-127,164-231,253-265 (restated in dcrp_math.cuh).
 #include "dcrp_device.cuh"
