@@ -113,10 +113,10 @@ __global__ void __launch_bounds__(S3_AXIS_BLOCK) k_slab_axis(const ScenarioDev s
 }
 
 // 2-D level-1 re-scan of n <= S3_RESCAN queued survivors of track a (4 per lane as two packed pairs);
-// the draws are regenerated from the trial id (nothing but (item, local) was kept), the track is read
-// through L1 with warp-uniform addresses.
+// the draws are regenerated from the trial id (nothing but (item, local) was kept), the track is the warp's
+// own shared-memory tile (the queue is drained before the tile is reloaded for another track).
 __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
-                                       uint32_t chunks_per_pair)
+                                       uint32_t chunks_per_pair, const float2* __restrict__ tile)
 {
     const int lane = (int)lane_id();
     uint32_t acc_is = 0, npass = 0, ncand = 0;
@@ -124,7 +124,6 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
     const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
     TrackScale ts;
     ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
-    const float2* __restrict__ gtrk = s.trkxy + (size_t)__ldg(&tk->off_xy);
     constexpr int TR = 4, NP = 2;
     float bxs[TR], bys[TR], sxs[TR], sys[TR];
     uint32_t fmask = 0;
@@ -172,7 +171,7 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
             f2_t PX[NP], PY[NP];
 #pragma unroll
             for (int p = 0; p < NP; ++p) { PX[p] = ffma2(lo2, SX[p], BX[p]); PY[p] = ffma2(lo2, SY[p], BY[p]); }
-            scan_tile_xy<NP>(gtrk + t0, t0, lo, hi, PX, PY, SX, SY, mn);
+            scan_tile_xy<NP>(tile + t0, t0, lo, hi, PX, PY, SX, SY, mn);
         }
     }
 #pragma unroll
@@ -276,7 +275,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
         if (a != list_track) {                    // (once per run for a one-track scenario)
             // queued survivors share one track: drain them before it changes
-            if (list_n) { s3_rescan(s, r, list, list_n, list_track, chunks_per_pair); list_n = 0; }
+            if (list_n) { s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile); list_n = 0; }
             list_track = a;
             // the track's samples come in by ONE 1-D TMA bulk copy; the per-item projection on the pair's direction
             // then reads shared memory, not L2
@@ -411,7 +410,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             while (list_n >= S3_RESCAN) {
                 griddep_wait();
                 list_n -= S3_RESCAN;
-                s3_rescan(s, r, list + list_n, S3_RESCAN, list_track, chunks_per_pair);
+                s3_rescan(s, r, list + list_n, S3_RESCAN, list_track, chunks_per_pair, tile);
                 __syncwarp();
             }
         }
@@ -428,7 +427,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         item = next_item;
     }
     griddep_wait();
-    if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair);
+    if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile);
 
     // statistics: one set of global atomics per CTA, not per warp (they all land on the same three L2 lines, and
     // the warps of a launch finish within microseconds of each other)
