@@ -614,7 +614,7 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
     // Two register budgets: 80 registers / 3 CTAs per SM for launches of a few items per warp (fewer, faster warps:
     // shorter tail; 0.162 against 0.166 ms at 1.0e7 trials), 64 registers / 4 CTAs per SM (spills in the per-item
     // code, more warps to hide them) for long launches (1.298 against 1.325 ms at 1.0e8 trials).
-    const int wide = (uint64_t)n_items >= (uint64_t)24 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
+    const int wide = (uint64_t)n_items >= (uint64_t)48 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
     const void* kern = wide ? (const void*)k_screen3<4> : (const void*)k_screen3<3>;
     int vl_pad = (e->sd.n_steps_max + 3) & ~3;
     int tk_pad = (e->sd.t_max + 3) & ~3;
@@ -625,15 +625,23 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
         if (e->s3_occ[wide] < 1) e->s3_occ[wide] = 1;
         e->s3_smem[wide] = smem;
     }
-    const uint64_t ctas_wanted = ((uint64_t)n_items + (S3_BLOCK / 32) - 1) / (S3_BLOCK / 32);   // one item per warp at least
-    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(
-        ctas_wanted, (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ[wide]));
+    const uint64_t ctas_max = (uint64_t)(e->prop.multiProcessorCount - e->reserve_sms) * e->s3_occ[wide];
+    // Every warp starts on a static block of consecutive items.  A launch of up to four items per warp of a full grid
+    // is latency-bound (its duration is the longest chain of items any warp runs): it is dealt out statically, as few
+    // warps as give every warp the same number of items, one staging of the pair's tables per block.  Longer launches
+    // start on two items per warp and take the rest from the work counter in guided blocks (screen3.cu).
+    const uint64_t warps_max = ctas_max * (S3_BLOCK / 32);
+    uint32_t first_block = (uint64_t)n_items <= 4 * warps_max
+        ? (uint32_t)std::max<uint64_t>(1, ((uint64_t)n_items + warps_max - 1) / warps_max) : 2u;
+    const uint64_t per_cta = (uint64_t)first_block * (S3_BLOCK / 32);
+    const uint64_t ctas_wanted = ((uint64_t)n_items + per_cta - 1) / per_cta;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(ctas_wanted, ctas_max));
     // the first launch of a run finds the counter cleared by k_run_init (word 2 of the output arena)
     if (r.slice_first != 0) CU(cudaMemsetAsync(e->d_out.as<uint32_t>() + 2, 0, 4, st));
     ScenarioDev sd = e->sd;
     RunDev rr = r;
     rr.work_counter = e->d_out.as<uint32_t>() + 2;
-    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad};
+    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad, &first_block};
     // Directly behind k_run_init the grid is launched programmatically dependent: its first items overlap the clearing
     // launch and the launch latency (the kernel waits before it first touches the arena, screen3.cu).
     cudaLaunchConfig_t cfg{};
@@ -829,6 +837,17 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     ++e->runs_on_scenario;
     return DCRP_OK;
 }
+
+#ifdef DCRP_TIMELINE
+// instrumented build only (screen3.cu): the per-warp time stamps of the last k_screen3 launch
+extern "C" int dcrp_debug_timeline(unsigned long long* out, int n_words)
+{
+    if (!out || n_words <= 0) return fail(DCRP_ERR_INVALID, "dcrp_debug_timeline: bad arguments");
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out, dcrp::g_timeline, sizeof(unsigned long long) * (size_t)std::min(n_words, TL_WARPS * TL_SLOTS)));
+    return DCRP_OK;
+}
+#endif
 
 extern "C" int dcrp_last_run_ms(dcrp_engine* e, float* ms)
 {

@@ -26,8 +26,9 @@ namespace dcrp {
 constexpr int S3_NPL = 4;                 // packed pairs per lane in the slab phase
 constexpr int S3_TL = 2 * S3_NPL;         // trials per lane per round
 constexpr int S3_RND = 32 * S3_TL;        // trials per warp round
-constexpr int S3_R = 2;                   // rounds per item: the pair's tables are staged once per item
+constexpr int S3_R = 1;                   // rounds per item
 constexpr int S3_CHW = S3_RND * S3_R;     // trials per warp item
+constexpr uint32_t S3_GMAX = 32;          // most items one grab of the work counter takes (contiguous: same pair, same track)
 constexpr int S3_RESCAN = 128;            // survivors per 2-D re-scan round (4 per lane = 2 packed pairs)
 constexpr int S3_LIST = S3_RESCAN + S3_RND;
 constexpr int S3_BLOCK = 256;
@@ -232,9 +233,36 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
 // writes are visible (immediately when the launch carried no such dependency).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+#ifdef DCRP_TIMELINE
+// Opt-in instrumentation (make EXTRA=-DDCRP_TIMELINE, tools/warp_timeline.py): %globaltimer of every warp at entry,
+// after its first staging, after its first item, when it leaves the item loop and at its end, plus its item count.
+constexpr int TL_WARPS = 8192, TL_SLOTS = 6;
+__device__ unsigned long long g_timeline[TL_WARPS * TL_SLOTS];
+__device__ __forceinline__ unsigned long long tl_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TL_MARK(slot)                                                                             \
+    do {                                                                                          \
+        const uint32_t gw_ = blockIdx.x * (S3_BLOCK / 32) + (threadIdx.x >> 5);                   \
+        if ((threadIdx.x & 31) == 0 && gw_ < (uint32_t)TL_WARPS) g_timeline[gw_ * TL_SLOTS + (slot)] = tl_now(); \
+    } while (0)
+#define TL_COUNT(n)                                                                               \
+    do {                                                                                          \
+        const uint32_t gw_ = blockIdx.x * (S3_BLOCK / 32) + (threadIdx.x >> 5);                   \
+        if ((threadIdx.x & 31) == 0 && gw_ < (uint32_t)TL_WARPS) g_timeline[gw_ * TL_SLOTS + 5] = (n); \
+    } while (0)
+#else
+#define TL_MARK(slot) do {} while (0)
+#define TL_COUNT(n) do {} while (0)
+#endif
+
 template <int MINB>
 __global__ void __launch_bounds__(S3_BLOCK, MINB)
-k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad)
+k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad,
+          uint32_t first_block)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -245,29 +273,51 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     uint2*   list  = reinterpret_cast<uint2*>(wb + (size_t)vl_pad * 12 + (size_t)tk_pad * 16);
     float*   tabpn = reinterpret_cast<float*>(wb + (size_t)vl_pad * 12 + (size_t)tk_pad * 16 + (size_t)S3_LIST * 8);
     uint64_t* bar  = reinterpret_cast<uint64_t*>(wb + (size_t)vl_pad * 12 + (size_t)tk_pad * 20 + (size_t)S3_LIST * 8);
+    TL_MARK(0);
     if (lane == 0) { mbar_init(bar, 1); mbar_fence_init(); bar[1] = 0ull; }     // bar[1]: the barrier's phase bit
     __syncwarp();
 
     uint32_t acc_t1 = 0, acc_is = 0, nsurv = 0;       // per-lane partial sums
     int list_n = 0, list_track = -1;       // warp-uniform
 
-    // Work items: the first one of every warp is its global warp index (no round trip to the one L2 line all
-    // 3552 warps would queue on at launch: ~10 us for the last of them), the later ones come from the counter.
+    // Work items are S3_CHW consecutive trials of one pair, numbered pair-major.  A warp takes them in BLOCKS of
+    // consecutive items (same pair, same track: tables and track are staged only when they change, and the survivor
+    // queue fills up across the items of a block before it is drained).  The first block of every warp is static --
+    // items [w * first_block, (w + 1) * first_block), no round trip to the one L2 line all warps would queue on at
+    // launch -- the later ones come from the device counter, guided: a grab takes 1/(2 n_warps) of what the counter
+    // had left when this warp last looked, at most S3_GMAX items, at least one (big blocks while there is plenty,
+    // single items at the end of the launch, where the finish times of the warps decide the tail).
     const uint32_t n_warps = gridDim.x * (S3_BLOCK / 32);
-    auto grab = [&]() -> uint32_t {
-        uint32_t v = 0;
-        if (lane == 0) v = atomicAdd(r.work_counter, 1u);
-        return n_warps + __shfl_sync(0xffffffffu, v, 0);
+    const uint32_t n_static = n_warps * first_block;
+    const uint32_t n_dyn = n_items > n_static ? n_items - n_static : 0u;
+    uint32_t seen = 0;                     // counter value after this warp's last grab (progress of the launch)
+    uint32_t pend_v = 0, pend_g = 0;       // the grab in flight: lane 0 holds the counter's answer until the block is needed
+    auto grab_issue = [&]() {
+        if (n_dyn == 0u) return;           // a launch dealt out statically: grab_take answers "nothing left"
+        const uint32_t left = n_dyn > seen ? n_dyn - seen : 0u;
+        pend_g = min(max(left / (2u * n_warps), 1u), S3_GMAX);
+        if (lane == 0) pend_v = atomicAdd(r.work_counter, pend_g);
+    };
+    auto grab_take = [&](uint32_t& b, uint32_t& e) {
+        const uint32_t v = __shfl_sync(0xffffffffu, pend_v, 0);
+        seen = v + pend_g;
+        b = n_static + min(v, n_dyn);      // (== n_items once the counter has run out)
+        e = n_static + min(v + pend_g, n_dyn);
     };
 
     // Programmatic dependent launch: this grid may start while the launch that clears the output arena (k_run_init) is
     // still running.  Tables, draws and the slab scan of the first item touch nothing it writes; griddep_wait() stands
     // before the first access to the arena (the work counter, and whatever s3_rescan publishes).
-    uint32_t item = blockIdx.x * (S3_BLOCK / 32) + (uint32_t)warp;
-    uint32_t next_item = 0;
-    bool first = true;
+    uint32_t item = (blockIdx.x * (S3_BLOCK / 32) + (uint32_t)warp) * first_block;
+    uint32_t blk_end = min(item + first_block, n_items);
+    bool waited = false;
+    int cur_pair = -1;
+#ifdef DCRP_TIMELINE
+    unsigned long long tl_items = 0;
+#endif
     while (item < n_items) {
-        if (!first) next_item = grab();           // in flight while this item is processed
+        const bool last_of_block = item + 1 == blk_end;
+        if (last_of_block && waited) grab_issue();                  // in flight while this item is processed
         const int pair = (int)r.div_chunks.div(item);
         const uint32_t c = item - (uint32_t)pair * chunks_per_pair;
         const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
@@ -275,9 +325,9 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
         if (a != list_track) {                    // (once per run for a one-track scenario)
             // queued survivors share one track: drain them before it changes
-            if (list_n) { s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile); list_n = 0; }
+            if (list_n) { griddep_wait(); s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile); list_n = 0; }
             list_track = a;
-            // the track's samples come in by ONE 1-D TMA bulk copy; the per-item projection on the pair's direction
+            // the track's samples come in by ONE 1-D TMA bulk copy; the per-pair projection on the pair's direction
             // then reads shared memory, not L2
             __syncwarp();
             const uint32_t phase = (uint32_t)bar[1];
@@ -299,8 +349,9 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
 
         // ---- this pair's tables: projected track T_i = n . (-A_i) (index 0 and the padding never pass),
-        // kink tables (target-box corner minus kink in fp64; kink projected on n)
-        {
+        // kink tables (target-box corner minus kink in fp64; kink projected on n).  The items of a block share them.
+        if (pair != cur_pair) {
+            cur_pair = pair;
             const int vlr = (VL + 3) & ~3;
             __syncwarp();
             for (int i = lane; i < vlr; i += 32) {
@@ -318,6 +369,10 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             __syncwarp();
         }
 
+#ifdef DCRP_TIMELINE
+        if (!waited) TL_MARK(1);
+        ++tl_items;
+#endif
         uint32_t t1s = 0;                          // item-local: the run-long accumulators are touched once per item
         const uint64_t trial0 = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + (uint32_t)lane;
         const uint32_t t0lo = (uint32_t)trial0, t0hi = (uint32_t)(trial0 >> 32);
@@ -414,8 +469,8 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
                 __syncwarp();
             }
         }
-        if (first) { griddep_wait(); next_item = grab(); first = false; }
         }   // rounds
+        if (!waited) { TL_MARK(2); griddep_wait(); waited = true; if (last_of_block) grab_issue(); }
         const uint32_t nv = n_valid > (uint32_t)lane ? (n_valid - (uint32_t)lane + 31u) >> 5 : 0u;   // this lane's valid slots
         acc_t1 += t1s;
         acc_is += nv * (uint32_t)VL;                 // slab lane-steps of this lane's trials
@@ -424,10 +479,13 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
             acc_t1 = acc_is = 0;
         }
-        item = next_item;
+        if (++item == blk_end) grab_take(item, blk_end);        // (every block issues exactly one grab, at its last item)
     }
+    TL_MARK(3);
     griddep_wait();
     if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile);
+    TL_MARK(4);
+    TL_COUNT(tl_items);
 
     // statistics: one set of global atomics per CTA, not per warp (they all land on the same three L2 lines, and
     // the warps of a launch finish within microseconds of each other)
