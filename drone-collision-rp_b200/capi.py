@@ -100,6 +100,7 @@ DCRP_SYMBOLS = [
     "dcrp_run_async", "dcrp_fetch", "dcrp_last_run_ms", "dcrp_allpairs", "dcrp_dump_draws", "dcrp_trajectories",
     "dcrp_comm_unique_id", "dcrp_engine_attach_comm", "dcrp_engine_detach_comm", "dcrp_allreduce_counts", "dcrp_comm_info",
     "dcrp_device_count", "dcrp_engine_reserve_sms", "dcrp_launch_count", "dcrp_device_info",
+    "dcrp_debug_block_schedule",
 ]
 DCRP_HOST_SYMBOLS = [
     "dcrph_last_error", "dcrph_reference_aircraft_csv", "dcrph_synth_day_write", "dcrph_synth_day_write_mixed",

@@ -608,6 +608,47 @@ static cudaError_t launch_screen2(dcrp_engine* e, const RunDev& r, uint32_t chun
     return ce != cudaSuccess ? ce : cudaGetLastError();
 }
 
+// The block schedule of a k_screen3 launch (screen3.cu S3Sched): `n_static` items are dealt out statically, the
+// rest in blocks numbered by the work counter.  A block size 2^lg is used while at least twice a full round of it
+// (2 * n_warps * 2^lg items) is left, then the size halves; the last 4 * n_warps items go one by one.
+static S3Sched s3_schedule(uint32_t n_items, uint32_t n_warps, uint32_t n_static)
+{
+    S3Sched sc{};
+    uint64_t pos = n_static, blk = 0, left = n_items > n_static ? n_items - n_static : 0;
+    for (int lg = S3_LG_GMAX; lg >= 0 && left > 0; --lg) {
+        const uint64_t size = 1ull << lg, keep = 2ull * n_warps * size;
+        uint64_t nb;
+        if (lg > 0) {
+            if (left < keep) continue;
+            nb = (left - keep) / size + 1;
+        } else nb = left;
+        sc.item0[sc.n_ph] = (uint32_t)pos; sc.blk0[sc.n_ph] = (uint32_t)blk; sc.lg[sc.n_ph] = (uint32_t)lg;
+        ++sc.n_ph;
+        pos += nb * size; blk += nb; left -= nb * size;
+    }
+    sc.item0[sc.n_ph] = n_items; sc.blk0[sc.n_ph] = (uint32_t)blk;
+    return sc;
+}
+
+// The schedule as the kernel reads it (screen3.cu grab_take), block by block: for the CPU test tier.
+extern "C" int64_t dcrp_debug_block_schedule(uint32_t n_items, uint32_t n_warps, uint32_t n_static,
+                                             uint32_t* begin, uint32_t* end, int64_t cap)
+{
+    if (n_warps == 0 || (cap > 0 && (!begin || !end))) return fail(DCRP_ERR_INVALID, "dcrp_debug_block_schedule: bad arguments");
+    const S3Sched sc = s3_schedule(n_items, n_warps, n_static);
+    const int64_t n_blocks = sc.blk0[sc.n_ph];
+    for (int64_t k = 0; k < n_blocks && k < cap; ++k) {
+        uint32_t b = n_items, e = n_items;
+        for (int p = 0; p < S3_MAX_PH; ++p)
+            if ((uint32_t)p < sc.n_ph && (uint32_t)k >= sc.blk0[p] && (uint32_t)k < sc.blk0[p + 1]) {
+                b = sc.item0[p] + (((uint32_t)k - sc.blk0[p]) << sc.lg[p]);
+                e = std::min(b + (1u << sc.lg[p]), sc.item0[p + 1]);
+            }
+        begin[k] = b; end[k] = e;
+    }
+    return n_blocks;
+}
+
 static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                           cudaStream_t st, bool behind_run_init)
 {
@@ -641,7 +682,8 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
     ScenarioDev sd = e->sd;
     RunDev rr = r;
     rr.work_counter = e->d_out.as<uint32_t>() + 2;
-    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad, &first_block};
+    S3Sched sch = s3_schedule(n_items, grid * (S3_BLOCK / 32), grid * (S3_BLOCK / 32) * first_block);
+    void* args[] = {&sd, &rr, &chunks_per_pair, &n_items, &vl_pad, &tk_pad, &first_block, &sch};
     // Directly behind k_run_init the grid is launched programmatically dependent: its first items overlap the clearing
     // launch and the launch latency (the kernel waits before it first touches the arena, screen3.cu).
     cudaLaunchConfig_t cfg{};

@@ -28,7 +28,7 @@ constexpr int S3_TL = 2 * S3_NPL;         // trials per lane per round
 constexpr int S3_RND = 32 * S3_TL;        // trials per warp round
 constexpr int S3_R = 1;                   // rounds per item
 constexpr int S3_CHW = S3_RND * S3_R;     // trials per warp item
-constexpr uint32_t S3_GMAX = 32;          // most items one grab of the work counter takes (contiguous: same pair, same track)
+constexpr int S3_LG_GMAX = 5;             // largest block of the work counter: 32 consecutive items (same pair, same track)
 constexpr int S3_RESCAN = 128;            // survivors per 2-D re-scan round (4 per lane = 2 packed pairs)
 constexpr int S3_LIST = S3_RESCAN + S3_RND;
 constexpr int S3_BLOCK = 256;
@@ -38,6 +38,18 @@ constexpr int S3_REBASE = 128;            // exact re-base of the running positi
 constexpr int S3_DIRS = 16;               // candidate slab directions k*pi/16
 
 static_assert(S3_CHW <= 4096, "local trial index is packed in 12 bits");
+
+// How the work counter deals out the items behind the static first blocks (host-built, engine.cu s3_schedule):
+// block k of the launch is items [item0[p] + ((k - blk0[p]) << lg[p]), + 2^lg[p]) of the phase p that holds k.
+// Block sizes taper 32, 16, ... 1 items ("factoring": a size is used while twice a full round of it is left), as a
+// function of the block NUMBER, so a warp that has not looked at the counter for a long block cannot overdraw.
+constexpr int S3_MAX_PH = 6;
+struct S3Sched {
+    uint32_t n_ph;
+    uint32_t item0[S3_MAX_PH + 1];          // first item of phase p; [n_ph] = n_items
+    uint32_t blk0[S3_MAX_PH + 1];           // first block number of phase p; [n_ph] = number of blocks
+    uint32_t lg[S3_MAX_PH];                 // log2 of the phase's block size
+};
 
 __host__ __device__ inline size_t s3_warp_smem(int vl_pad, int tk_pad)
 {
@@ -116,8 +128,12 @@ __global__ void __launch_bounds__(S3_AXIS_BLOCK) k_slab_axis(const ScenarioDev s
 // 2-D level-1 re-scan of n <= S3_RESCAN queued survivors of track a (4 per lane as two packed pairs);
 // the draws are regenerated from the trial id (nothing but (item, local) was kept), the track is the warp's
 // own shared-memory tile (the queue is drained before the tile is reloaded for another track).
-__device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
-                                       uint32_t chunks_per_pair, const float2* __restrict__ tile)
+// NP packed pairs per lane: 2 for a full round of S3_RESCAN survivors, 1 for the up to 64 left over when a warp
+// changes track or ends (on the 5 km ring a warp queues a dozen survivors per launch: that one call is its whole
+// re-scan work, and it stands at the very end of the launch).
+template <int NP>
+__device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
+                                          uint32_t chunks_per_pair, const float2* __restrict__ tile)
 {
     const int lane = (int)lane_id();
     uint32_t acc_is = 0, npass = 0, ncand = 0;
@@ -125,7 +141,7 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
     const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
     TrackScale ts;
     ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
-    constexpr int TR = 4, NP = 2;
+    constexpr int TR = 2 * NP;
     float bxs[TR], bys[TR], sxs[TR], sys[TR];
     uint32_t fmask = 0;
     int tmin = INT_MAX;
@@ -134,7 +150,7 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
         const int idx = m * 32 + lane;
         float bx = 1e15f, by = 1e15f, sx = 0.f, sy = 0.f;
         if (idx < n) {
-            DCRP_ASSERT(n <= S3_RESCAN);
+            DCRP_ASSERT(n <= 32 * TR);
             const uint2 e = list[idx];
             const int pair = (int)r.div_chunks.div(e.x);
             DCRP_ASSERT(pair >= a * s.n_drones && pair < (a + 1) * s.n_drones && e.y < (uint32_t)S3_CHW);
@@ -177,43 +193,42 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
     }
 #pragma unroll
     for (int m = 0; m < TR; ++m) if (mn[m] < s.thr2_screen) fmask |= 1u << m;
-    // ---- rare: LEVEL 2 (3-D fp32, fused form) of the flagged trials, then LEVEL 3 (fp64) of what survives
+    // ---- rare: LEVEL 2 (3-D fp32, fused form) of the flagged trials, then LEVEL 3 (fp64) of what survives -- one
+    // trial at a time by the WHOLE warp (every lane re-derives the trial from its queue entry, the indices are dealt
+    // out over the lanes: min3d_fp32_warp, exact_any_warp).  Same decisions and bits as one lane per trial; what
+    // changes is the latency: this code also runs when a warp empties its queue at the very end of a launch, where
+    // a lane alone on a 96-index fp32 scan (2.5 us) or an fp64 trial (20 us) was the tail of the whole kernel.
+    // Candidates are ~3e-7 of the trials: deciding them here saves the candidate list, a kernel launch and its
+    // ~10 us of latency per run.
     uint32_t hits = 0;
     if (__any_sync(0xffffffffu, fmask != 0u)) {
+        const TrackDev t = *tk;
 #pragma unroll 1
         for (int m = 0; m < TR; ++m) {
-            const int idx = m * 32 + lane;
-            bool cand = false;
-            int pair = 0;
-            uint64_t trial = 0;
-            if (((fmask >> m) & 1u) && idx < n) {
-                const uint2 e = list[idx];
-                pair = (int)r.div_chunks.div(e.x);
+            uint32_t todo = __ballot_sync(0xffffffffu, ((fmask >> m) & 1u) && m * 32 + lane < n);
+            while (todo) {
+                const int src = __ffs((int)todo) - 1;
+                todo &= todo - 1u;
+                const uint2 e = list[m * 32 + src];                       // the same entry for every lane
+                const int pair = (int)r.div_chunks.div(e.x);
                 const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
                 const int j = pair - a * s.n_drones;
-                trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
+                const uint64_t trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
                 const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
                                               r.track_base + (uint32_t)a, r.rk);
                 const int t1st = draw_t1st(w.x, takeoff_t);
                 const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
-                ++npass;
-                const Setup32 u = setup_trial32(s, r, *tk, pair, j, __ldg(&s.s1_first_hit[pair]), 0, q);
-                cand = u.force || min3d_fp32(s, *tk, u) < s.thr2_screen;
-                ncand += cand ? 1u : 0u;
-            }
-            // LEVEL 3 inside the screen kernel: the fp64 decision in the reference's order of operations, by the
-            // lane that holds the candidate (all candidate lanes of the warp at once).  Candidates are ~3e-7 of
-            // the trials, so deciding them where they are found costs nothing measurable and saves the candidate
-            // list, a kernel launch and its ~10 us of latency per run.
-            if (cand) {
-                const int j = pair - a * s.n_drones;
-                const TrackDev t = *tk;
-                const Draw d = make_draw(r.seed, trial, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a,
-                                         t.takeoff_t, t.box);
-                const TrialOut o = exact_trial(s, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d);
-                if (o.first >= 0) {
-                    ++hits;
-                    publish_hit(s, r, pair, a, j, trial, d, o);
+                const Setup32 u = setup_trial32(s, r, t, pair, j, __ldg(&s.s1_first_hit[pair]), 0, q);
+                const bool cand = u.force || min3d_fp32_warp(s, t, u, lane) < s.thr2_screen;
+                if (lane == 0) { ++npass; ncand += cand ? 1u : 0u; }
+                if (cand) {
+                    const Draw d = make_draw(r.seed, trial, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a,
+                                             t.takeoff_t, t.box);
+                    const TrialOut o = exact_any_warp(s, r, pair, j, t.n_steps, s.ax + t.off, s.ay + t.off, s.az + t.off, d, lane);
+                    if (o.first >= 0 && lane == 0) {
+                        ++hits;
+                        publish_hit(s, r, pair, a, j, trial, d, o);
+                    }
                 }
             }
         }
@@ -229,14 +244,22 @@ __device__ __noinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, co
     }
 }
 
+__device__ __forceinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
+                                          uint32_t chunks_per_pair, const float2* __restrict__ tile)
+{
+    if (n <= 64) s3_rescan_np<1>(s, r, list, n, a, chunks_per_pair, tile);
+    else         s3_rescan_np<2>(s, r, list, n, a, chunks_per_pair, tile);
+}
+
 // griddepcontrol.wait: returns once the grid this one was programmatically launched behind has completed and its
 // writes are visible (immediately when the launch carried no such dependency).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 #ifdef DCRP_TIMELINE
 // Opt-in instrumentation (make EXTRA=-DDCRP_TIMELINE, tools/warp_timeline.py): %globaltimer of every warp at entry,
-// after its first staging, after its first item, when it leaves the item loop and at its end, plus its item count.
-constexpr int TL_WARPS = 8192, TL_SLOTS = 6;
+// after its first staging, after its first item, when it leaves the item loop and at its end, plus its item count,
+// its SM and the start of its last item.
+constexpr int TL_WARPS = 8192, TL_SLOTS = 8;
 __device__ unsigned long long g_timeline[TL_WARPS * TL_SLOTS];
 __device__ __forceinline__ unsigned long long tl_now()
 {
@@ -262,7 +285,7 @@ __device__ __forceinline__ unsigned long long tl_now()
 template <int MINB>
 __global__ void __launch_bounds__(S3_BLOCK, MINB)
 k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad,
-          uint32_t first_block)
+          uint32_t first_block, const __grid_constant__ S3Sched sch)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -284,25 +307,22 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     // consecutive items (same pair, same track: tables and track are staged only when they change, and the survivor
     // queue fills up across the items of a block before it is drained).  The first block of every warp is static --
     // items [w * first_block, (w + 1) * first_block), no round trip to the one L2 line all warps would queue on at
-    // launch -- the later ones come from the device counter, guided: a grab takes 1/(2 n_warps) of what the counter
-    // had left when this warp last looked, at most S3_GMAX items, at least one (big blocks while there is plenty,
-    // single items at the end of the launch, where the finish times of the warps decide the tail).
-    const uint32_t n_warps = gridDim.x * (S3_BLOCK / 32);
-    const uint32_t n_static = n_warps * first_block;
-    const uint32_t n_dyn = n_items > n_static ? n_items - n_static : 0u;
-    uint32_t seen = 0;                     // counter value after this warp's last grab (progress of the launch)
-    uint32_t pend_v = 0, pend_g = 0;       // the grab in flight: lane 0 holds the counter's answer until the block is needed
+    // launch -- the later ones are numbered by the device counter and sized by the schedule `sch` (big blocks while
+    // there is plenty, single items at the end of the launch, where the finish times of the warps decide the tail).
+    uint32_t pend_v = 0;                   // the grab in flight: lane 0 holds the counter's answer until the block is needed
     auto grab_issue = [&]() {
-        if (n_dyn == 0u) return;           // a launch dealt out statically: grab_take answers "nothing left"
-        const uint32_t left = n_dyn > seen ? n_dyn - seen : 0u;
-        pend_g = min(max(left / (2u * n_warps), 1u), S3_GMAX);
-        if (lane == 0) pend_v = atomicAdd(r.work_counter, pend_g);
+        if (sch.n_ph == 0u) return;        // a launch dealt out statically: grab_take answers "nothing left"
+        if (lane == 0) pend_v = atomicAdd(r.work_counter, 1u);
     };
     auto grab_take = [&](uint32_t& b, uint32_t& e) {
-        const uint32_t v = __shfl_sync(0xffffffffu, pend_v, 0);
-        seen = v + pend_g;
-        b = n_static + min(v, n_dyn);      // (== n_items once the counter has run out)
-        e = n_static + min(v + pend_g, n_dyn);
+        const uint32_t k = __shfl_sync(0xffffffffu, pend_v, 0);
+        b = e = n_items;                   // (the counter has run out)
+#pragma unroll
+        for (int p = 0; p < S3_MAX_PH; ++p)
+            if ((uint32_t)p < sch.n_ph && k >= sch.blk0[p] && k < sch.blk0[p + 1]) {
+                b = sch.item0[p] + ((k - sch.blk0[p]) << sch.lg[p]);
+                e = min(b + (1u << sch.lg[p]), sch.item0[p + 1]);
+            }
     };
 
     // Programmatic dependent launch: this grid may start while the launch that clears the output arena (k_run_init) is
@@ -310,27 +330,32 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     // before the first access to the arena (the work counter, and whatever s3_rescan publishes).
     uint32_t item = (blockIdx.x * (S3_BLOCK / 32) + (uint32_t)warp) * first_block;
     uint32_t blk_end = min(item + first_block, n_items);
-    bool waited = false;
+    bool waited = false, prefetch = true;
     int cur_pair = -1;
 #ifdef DCRP_TIMELINE
     unsigned long long tl_items = 0;
 #endif
     while (item < n_items) {
         const bool last_of_block = item + 1 == blk_end;
-        if (last_of_block && waited) grab_issue();                  // in flight while this item is processed
+        // the next block is asked for while the last item of a BIG block is processed; towards the end of the launch
+        // (blocks of one or two items) only when the warp is ready for it, so that no warp sits on unstarted work
+        // that a warp with nothing left to do could have taken
+        if (last_of_block && waited && prefetch) grab_issue();
         const int pair = (int)r.div_chunks.div(item);
         const uint32_t c = item - (uint32_t)pair * chunks_per_pair;
         const int a = (int)s.div_drones.div((uint32_t)pair), j = pair - a * s.n_drones;
         const TrackDev* __restrict__ tk = s.tracks + a;
         const int VL = __ldg(&tk->n_steps), takeoff_t = __ldg(&tk->takeoff_t);
+        bool tile_wait = false;
+        uint32_t phase = 0;
         if (a != list_track) {                    // (once per run for a one-track scenario)
             // queued survivors share one track: drain them before it changes
             if (list_n) { griddep_wait(); s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile); list_n = 0; }
             list_track = a;
-            // the track's samples come in by ONE 1-D TMA bulk copy; the per-pair projection on the pair's direction
-            // then reads shared memory, not L2
+            // the track's samples come in by ONE 1-D TMA bulk copy (waited for below, behind the loads that do not
+            // need them); the per-pair projection on the pair's direction then reads shared memory, not L2
             __syncwarp();
-            const uint32_t phase = (uint32_t)bar[1];
+            phase = (uint32_t)bar[1];
             if (lane == 0) {
                 const uint32_t bytes = (uint32_t)((VL + 1) & ~1) * 8u;              // tracks are padded to an even length
                 DCRP_ASSERT(bytes <= (uint32_t)vl_pad * 8u);
@@ -338,9 +363,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
                 mbar_arrive_expect_tx(bar, bytes);
                 tma_bulk_g2s(tile, s.trkxy + (size_t)__ldg(&tk->off_xy), bytes, bar);
             }
-            mbar_wait(bar, phase);
-            __syncwarp();
-            if (lane == 0) bar[1] = phase ^ 1u;
+            tile_wait = true;
         }
         const uint32_t n_valid = (uint32_t)min((uint64_t)S3_CHW, r.slice_count - (uint64_t)c * S3_CHW);
         const int s1_first = __ldg(&s.s1_first_hit[pair]);
@@ -348,29 +371,39 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         TrackScale ts;
         ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
 
-        // ---- this pair's tables: projected track T_i = n . (-A_i) (index 0 and the padding never pass),
-        // kink tables (target-box corner minus kink in fp64; kink projected on n).  The items of a block share them.
-        if (pair != cur_pair) {
-            cur_pair = pair;
-            const int vlr = (VL + 3) & ~3;
+        // ---- this pair's tables, shared by the items of a block: kink tables (target-box corner minus kink in fp64;
+        // kink projected on n) first -- they do not need the track -- then the projected track T_i = n . (-A_i)
+        // (index 0 and the padding never pass)
+        const bool new_pair = pair != cur_pair;
+        if (new_pair) {
             __syncwarp();
-            for (int i = lane; i < vlr; i += 32) {
-                float v = 1e15f;
-                if (i >= 1 && i < VL) { const float2 p = tile[i]; v = fmaf(nd.x, p.x, nd.y * p.y); }
-                DCRP_ASSERT(i < vl_pad);
-                tabT[i] = v;
-            }
             for (int t = lane; t < takeoff_t; t += 32) {
                 DCRP_ASSERT(t < tk_pad && pair < s.n_tracks * s.n_drones && takeoff_t <= s.t_max);
                 tabk[t] = __ldg(&s.kink[(size_t)pair * s.t_max + t]);
                 const float2 pl = __ldg(&s.p1f[(size_t)j * s.t_max + t]);
                 tabpn[t] = fmaf(nd.x, pl.x, nd.y * pl.y);
             }
+        }
+        if (tile_wait) {
+            mbar_wait(bar, phase);
+            __syncwarp();
+            if (lane == 0) bar[1] = phase ^ 1u;
+        }
+        if (new_pair) {
+            cur_pair = pair;
+            const int vlr = (VL + 3) & ~3;
+            for (int i = lane; i < vlr; i += 32) {
+                float v = 1e15f;
+                if (i >= 1 && i < VL) { const float2 p = tile[i]; v = fmaf(nd.x, p.x, nd.y * p.y); }
+                DCRP_ASSERT(i < vl_pad);
+                tabT[i] = v;
+            }
             __syncwarp();
         }
 
 #ifdef DCRP_TIMELINE
         if (!waited) TL_MARK(1);
+        TL_MARK(7);
         ++tl_items;
 #endif
         uint32_t t1s = 0;                          // item-local: the run-long accumulators are touched once per item
@@ -471,6 +504,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         }
         }   // rounds
         if (!waited) { TL_MARK(2); griddep_wait(); waited = true; if (last_of_block) grab_issue(); }
+        else if (last_of_block && !prefetch) grab_issue();
         const uint32_t nv = n_valid > (uint32_t)lane ? (n_valid - (uint32_t)lane + 31u) >> 5 : 0u;   // this lane's valid slots
         acc_t1 += t1s;
         acc_is += nv * (uint32_t)VL;                 // slab lane-steps of this lane's trials
@@ -479,13 +513,24 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             atomicAdd(&r.stats[ST_ISSUED], (unsigned long long)acc_is);
             acc_t1 = acc_is = 0;
         }
-        if (++item == blk_end) grab_take(item, blk_end);        // (every block issues exactly one grab, at its last item)
+        if (++item == blk_end) {                                // (every block issues exactly one grab, at its last item)
+            grab_take(item, blk_end);
+            prefetch = blk_end - item >= 4u;
+        }
     }
     TL_MARK(3);
     griddep_wait();
     if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile);
     TL_MARK(4);
     TL_COUNT(tl_items);
+#ifdef DCRP_TIMELINE
+    {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        const uint32_t gw_ = blockIdx.x * (S3_BLOCK / 32) + (threadIdx.x >> 5);
+        if (lane == 0 && gw_ < (uint32_t)TL_WARPS) g_timeline[gw_ * TL_SLOTS + 6] = smid;
+    }
+#endif
 
     // statistics: one set of global atomics per CTA, not per warp (they all land on the same three L2 lines, and
     // the warps of a launch finish within microseconds of each other)

@@ -313,6 +313,16 @@ int  dcrp_launch_count(dcrp_engine* e, uint64_t* n);
 int  dcrp_device_info(dcrp_engine* e, char* name, int name_cap, int* sm_count,
                       int* cc_major, int* cc_minor, int* clock_khz);
 
+
+/* ---- diagnostics ----------------------------------------------------------- */
+/* How a slab-screen launch of `n_items` 256-trial work items deals them out to `n_warps` warps after the first
+ * `n_static` items (which go to the warps statically): block k of the device work counter covers the items
+ * [begin[k], end[k]).  Host arithmetic only (no device needed); fills at most `cap` blocks and returns the number
+ * of blocks of the schedule (negative = error).  The CPU test tier checks with it that every item is dealt out
+ * exactly once for launch sizes the GPU tests do not reach. */
+int64_t dcrp_debug_block_schedule(uint32_t n_items, uint32_t n_warps, uint32_t n_static,
+                                  uint32_t* begin, uint32_t* end, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -164,6 +164,44 @@ def test_partition_trials_is_disjoint_and_exhaustive():
         assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
 
 
+def test_slab_screen_block_schedule_deals_every_item_exactly_once():
+    """k_screen3's work counter numbers BLOCKS of consecutive items whose size tapers 32, 16, ... 1 with the block
+    number (csrc/engine.cu s3_schedule, read by screen3.cu grab_take).  For launch sizes from empty to 2^30 items:
+    the blocks tile [n_static, n_items) in order with no gap and no overlap, sizes never grow, full-size blocks are
+    powers of two, and the last 4 * n_warps items (at least) are dealt out one by one."""
+    L = capi.lib()
+    L.dcrp_debug_block_schedule.restype = C.c_int64
+    L.dcrp_debug_block_schedule.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64]
+    rng = np.random.default_rng(5)
+    cases = [(0, 8, 0), (1, 8, 8), (7, 8, 8), (9, 8, 8), (39105, 3552, 7104), (390654, 4736, 9472), (3920400, 4736, 9472),
+             (2**20 + 3, 3552, 7104), (5000, 8, 16), (100000, 8, 16)]
+    for _ in range(60):
+        w = int(rng.integers(1, 600)) * 8
+        fb = int(rng.integers(1, 3))
+        cases.append((int(rng.integers(0, 3_000_000)), w, w * fb))
+    cap = 3_200_000
+    b = np.zeros(cap, dtype=np.uint32)
+    e = np.zeros(cap, dtype=np.uint32)
+    for n_items, n_warps, n_static in cases:
+        nb = L.dcrp_debug_block_schedule(n_items, n_warps, n_static, b.ctypes.data, e.ctypes.data, cap)
+        assert 0 <= nb <= cap, (n_items, n_warps, n_static, nb)
+        if n_items <= n_static:
+            assert nb == 0
+            continue
+        bb, ee = b[:nb].astype(np.int64), e[:nb].astype(np.int64)
+        assert bb[0] == n_static and ee[-1] == n_items
+        assert np.array_equal(bb[1:], ee[:-1])                       # contiguous, in order: every item exactly once
+        size = ee - bb
+        assert size.min() >= 1 and size.max() <= 32
+        assert np.all(np.diff(size[:-1]) <= 0) or nb < 3             # sizes taper (the very last block may be cut short)
+        full = size[:-1] if nb > 1 else size
+        assert np.all((full & (full - 1)) == 0)                      # powers of two
+        tail = min(n_items - n_static, 4 * n_warps - 1)
+        assert np.all(size[bb >= n_items - tail] == 1)               # the end of the launch goes item by item
+    # the whole 2^30-item launch limit: block count and coverage by the phase arithmetic alone (no arrays)
+    assert L.dcrp_debug_block_schedule(2**30, 4736, 9472, None, None, 0) > 0
+
+
 def test_committed_workload_csv_is_what_the_generator_writes(tmp_path):
     """bench.py (both arms) reads data/synthetic_day_1_20170630.csv; it must stay byte for byte what
     host/synth_day.cpp writes for one flight with the default seed."""

@@ -28,7 +28,7 @@ ring = scenario.load_ring(pk.RING_5KM)
 eng.upload(tracks, ring)
 L = capi.lib()
 L.dcrp_debug_timeline.argtypes = [C.c_void_p, C.c_int]
-SLOTS, WARPS = 6, 8192
+SLOTS, WARPS = 8, 8192
 buf = np.zeros(WARPS * SLOTS, dtype=np.uint64)
 
 
@@ -61,6 +61,17 @@ for flush in (False, True):
     lost_tail = float(np.sum(end - t[:, 4])) * 1e-3 / w
     lost_ramp = float(np.sum(t[:, 1] - t0)) * 1e-3 / w
     print("mean warp-time idle at the tail %.2f us, before the first Philox %.2f us (of %.1f)" % (lost_tail, lost_ramp, dur))
+    # per SM sub-partition (warp slot mod 4 of a CTA's 8 warps -> its 4 schedulers): how evenly the tail ends
+    gw = np.nonzero(buf.reshape(WARPS, SLOTS)[:, 0] > 0)[0]
+    smsp = t[:, 6] * 4 + (gw % 8) % 4
+    ends, items, lastlen = [], [], []
+    for q in np.unique(smsp):
+        m = smsp == q
+        ends.append(us(t[m, 4].max()))
+        items.append(t[m, 5].sum())
+    print("per SM sub-partition : last warp ends at", pct(np.array(ends), (0, 10, 50, 90, 100)), "| items", pct(np.array(items), (0, 10, 50, 90, 100)))
+    print("last item of a warp  : duration", pct((t[:, 3] - t[:, 7]) * 1e-3, (0, 10, 50, 90, 100)), "| started", pct(us(t[:, 7]), (0, 10, 50, 90, 100)))
+    print("final re-scan        : duration", pct((t[:, 4] - t[:, 3]) * 1e-3, (0, 10, 50, 90, 100)))
     d = np.diff(np.unique(t[:, :5].ravel()))
     print("globaltimer: smallest step between distinct stamps %d ns" % (d[d > 0].min() if len(d) else -1))
 eng.close()
