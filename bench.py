@@ -655,7 +655,7 @@ def engine_arm(args):
     rescan_steps = max(0.0, stats_sum["tests_issued"] - slab_steps)
     exec_per_test = (2.0 * slab_steps + 7.0 * rescan_steps) / max(1.0, stats_sum["tests_evaluated"])
     roofline = {
-        "bound": "fp32", "kernel": "k_screen3<MINB=3> (256 threads; slab level + queued 2-D re-scan + level 2 + fp64 decision)",
+        "bound": "fp32", "kernel": "k_screen3<MINB=2> (256 threads, 128 registers, 2 CTAs per SM; slab level + queued 2-D re-scan + level 2 + fp64 decision)",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": traffic,
         "traffic_note": "DRAM bytes per launch from one ncu --set full capture (profiles/r02_traffic.json); the "

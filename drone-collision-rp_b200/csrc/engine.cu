@@ -129,7 +129,7 @@ struct dcrp_engine {
     DevBuf d_slab_dir;             // k_screen3: slab direction per pair
     bool slab_ready = false;       // k_slab_axis has run for the current scenario
     uint32_t runs_on_scenario = 0; // dcrp_run_async calls since the last upload
-    size_t s3_smem[2] = {0, 0};    // [0] k_screen3<3>, [1] k_screen3<4>
+    size_t s3_smem[2] = {0, 0};    // [0] k_screen3<2>, [1] k_screen3<4>
     int s3_occ[2] = {0, 0};
     bool prepare_timed = false;
 
@@ -652,11 +652,16 @@ extern "C" int64_t dcrp_debug_block_schedule(uint32_t n_items, uint32_t n_warps,
 static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_pair, uint32_t n_items,
                           cudaStream_t st, bool behind_run_init)
 {
-    // Two register budgets: 80 registers / 3 CTAs per SM for launches of a few items per warp (fewer, faster warps:
-    // shorter tail; 0.162 against 0.166 ms at 1.0e7 trials), 64 registers / 4 CTAs per SM (spills in the per-item
-    // code, more warps to hide them) for long launches (1.298 against 1.325 ms at 1.0e8 trials).
-    const int wide = (uint64_t)n_items >= (uint64_t)48 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
-    const void* kern = wide ? (const void*)k_screen3<4> : (const void*)k_screen3<3>;
+    // Two builds.  k_screen3<2>: 128 registers, 2 CTAs = 4 warps per SM sub-partition -- the slab loop and Philox carry
+    // 8 independent trials per lane, so four warps fill the dispatch port, the only spills left are the 232 B around
+    // the out-of-line re-scan call, and fewer, faster warps leave a shorter ramp and tail: faster than 3 CTAs x 80 registers and 4 CTAs x 64 registers at
+    // every launch size on both rings (1.0e7 trials on the 5 km ring 0.148 against 0.152 / 0.159 ms, 1.0e8 trials 1.232
+    // against 1.267 / 1.272 ms; one CTA of 172 registers 0.163 / 1.310).  k_screen3<4>: 64 registers, 8 warps per
+    // sub-partition, for long launches over MANY tracks (the 600-flight day on the 1 km ring: a tenth of the trials
+    // go through the re-scan and its latency-bound rare path; 20.3 against 21.1 ms).
+    const int wide = e->sd.n_tracks > 1 &&
+                     (uint64_t)n_items >= (uint64_t)48 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
+    const void* kern = wide ? (const void*)k_screen3<4> : (const void*)k_screen3<2>;
     int vl_pad = (e->sd.n_steps_max + 3) & ~3;
     int tk_pad = (e->sd.t_max + 3) & ~3;
     const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);

@@ -10,10 +10,10 @@ from drone_collision_rp_b200 import capi, scenario
 flags = capi.FLAG_SCREEN_2D if "--2d" in sys.argv else 0
 eng = capi.Engine(0)
 tracks = [scenario.load_flight(os.path.join(pk.DATA_DIR, "synthetic_day_1_20170630.csv"), 0)]
-ring = scenario.load_ring(pk.RING_5KM)
+ring = scenario.load_ring(pk.RING_1KM if "--ring1" in sys.argv else pk.RING_5KM)
 eng.upload(tracks, ring)
 eng.fetch(eng.run_async(seed=1, trial_count=101011, precision=capi.MIXED, flags=flags))
-for n in (1, 256, 2560, 10000, 25600, 50000, 101011, 202022, 404044, 1010110):
+for n in ((101011, 1010110) if "--short" in sys.argv else (1, 256, 2560, 10000, 25600, 50000, 101011, 202022, 404044, 1010110)):
     best, tot = 1e9, 1e9
     for k in range(7):
         r = eng.fetch(eng.run_async(seed=1, trial_begin=k * n, trial_count=n, precision=capi.MIXED, flags=flags))
