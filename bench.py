@@ -514,7 +514,7 @@ def engine_arm(args):
         run = eng.run_async(seed=SEED, trial_begin=10**12 + (k * world + rank) * SUSTAIN_TRIALS_PER_DRONE,
                             trial_count=SUSTAIN_TRIALS_PER_DRONE, precision=capi.MIXED, stream=sh)
         res_s = eng.fetch(run)
-        sus_ms += res_s.stats["ms_trials"]
+        sus_ms += eng.last_run_ms()        # CUDA events around the launch on its stream (dcrp_last_run_ms)
         for q in sus:
             sus[q] += res_s.stats[q]
     t_load1 = time.time()
@@ -553,7 +553,8 @@ def engine_arm(args):
     # ---- end to end through the public C-ABI call with HOST buffers (dcrp_simulate: scenario check / upload,
     # kernels, download per step), on every rank at once; aggregate = all ranks' tests / slowest rank's wall time
     scn = capi.Scenario(tracks, ring)            # ctypes marshalling of the caller's arrays, done once
-    call = eng.prepared_simulate(scn, precision=capi.MIXED, record_capacity=4096, seed=SEED)
+    # (DCRP_FLAG_NO_TIMING: the caller reads no dcrp_stats.ms_*, as the reference-facing Drone::Simulation does not)
+    call = eng.prepared_simulate(scn, precision=capi.MIXED, record_capacity=4096, seed=SEED, flags=capi.FLAG_NO_TIMING)
     e2e_secs, e2e_tests, h2d, d2h, cached_steps = 0.0, 0, 0, 0, 0
     first_call = None
     for s in range(args.warmup + args.steps):
@@ -703,7 +704,7 @@ def engine_arm(args):
         "back_to_back": back_to_back,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "call": "dcrp_simulate (host buffers in/out)",
+                "call": "dcrp_simulate (host buffers in/out; DCRP_FLAG_NO_TIMING, as host/Drone.cpp calls it)",
                 "ms_per_step": 1e3 * e2e_secs / args.steps,
                 "scenario_cache": "%d of %d timed calls found the scenario resident (bit-for-bit comparison with the pinned "
                                   "mirror of the last upload): h2d_bytes_per_step = 0 is the truth for them; the first call "

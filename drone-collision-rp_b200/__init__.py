@@ -12,7 +12,7 @@ import subprocess as _sp
 PKG_DIR = _os.path.dirname(_os.path.abspath(__file__))
 REPO_ROOT = _os.path.dirname(PKG_DIR)
 DATA_DIR = _os.path.join(REPO_ROOT, "data")
-LIBDCRP = _os.path.join(PKG_DIR, "libdcrp.so")
+LIBDCRP = _os.environ.get("DCRP_LIBDCRP") or _os.path.join(PKG_DIR, "libdcrp.so")    # (override: A/B runs of two builds, tools/)
 LIBDCRP_HOST = _os.path.join(PKG_DIR, "libdcrp_host.so")
 LIBDCRP_BENCH = _os.path.join(PKG_DIR, "libdcrp_bench.so")    # measurement only (bench.py, tools/)
 MONTE_CARLO = _os.path.join(PKG_DIR, "Monte_Carlo")

@@ -19,6 +19,7 @@ FLAG_SUBSTEP = 2
 FLAG_REACH_CULL = 4
 FLAG_SCREEN_2D = 8
 FLAG_ZERO_COUNTS = 16
+FLAG_NO_TIMING = 32
 STAT_SCENARIO_CACHED, STAT_FP64_FALLBACK, STAT_CULL_IGNORED = 1, 2, 4
 INT32_MAX = 2**31 - 1
 

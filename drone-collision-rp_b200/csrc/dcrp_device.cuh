@@ -159,7 +159,7 @@ struct RunDev {
     uint32_t  rk[20];                    // Philox round keys of `seed` (philox_round_keys)
     FastDiv   div_chunks;                // item / chunks_per_pair of the launch
     int32_t   cull;                      // 1 = DCRP_FLAG_REACH_CULL
-    uint32_t* work_counter;              // k_screen3: next unclaimed work item of the launch
+    uint32_t* work_counter;              // k_screen3: next unclaimed block of the launch
 };
 
 }  // namespace dcrp

@@ -8,6 +8,7 @@
 #include "dcrp_device.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -59,6 +60,20 @@ struct NvtxRange {
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
+#ifdef DCRP_TIMELINE
+// instrumented build only: host-side time stamps (ns) of the last dcrp_simulate call, tools/e2e_breakdown.py
+static double g_host_ns[16];
+static std::chrono::steady_clock::time_point g_host_t0;
+#define HOST_MARK(i) (g_host_ns[i] = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - g_host_t0).count())
+extern "C" int dcrp_debug_host_times(double* out, int n)
+{
+    for (int i = 0; i < n && i < 16; ++i) out[i] = g_host_ns[i];
+    return DCRP_OK;
+}
+#else
+#define HOST_MARK(i) do {} while (0)
+#endif
+
 // ------------------------------------------------------------------ buffers
 struct DevBuf {            // grow-only device buffer
     void*  p = nullptr;
@@ -86,7 +101,7 @@ struct PinnedBuf {         // grow-only pinned host buffer (async copies need pa
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = (bytes + 4095) & ~size_t(4095);
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);      // kernels may write it (published runs)
         if (e == cudaSuccess) cap = want;
         return e;
     }
@@ -146,6 +161,19 @@ struct dcrp_engine {
     DevBuf d_out;
     PinnedBuf h_out;
     size_t out_counts_off = 0, out_first_off = 0, out_bytes = 0;     // out_bytes: the part before the records
+    // Published runs: a plain MIXED run of one k_screen3 launch with engine-owned counts is read back by a kernel of
+    // its own, k_publish, queued right behind the trial kernel: one CTA stores the arena and the first records into
+    // h_out through its device mapping and raises a flag; dcrp_fetch polls the flag instead of queueing a D2H copy
+    // behind the run and waiting for the stream (measured from the host: ~13 us from the end of the trial kernel to
+    // knowing it, against ~3).  Without a communicator (whose all-reduce may still want the counts on the device)
+    // k_publish also leaves the arena cleared, and the next such run needs no k_run_init in front of it: the trial
+    // kernel is the first thing queued.  e2e per 1.0e7-trial call: 0.174 -> 0.159 ms.
+    bool published = false;        // the last run publishes
+    bool run_timed = true;         // the last run recorded its timing events (no DCRP_FLAG_NO_TIMING)
+    uint32_t pub_seq = 0;          // flag value of the last published run
+    bool arena_clean = false;      // the last run leaves (d_out, out_bytes) cleared
+    void* clean_ptr = nullptr;
+    size_t clean_bytes = 0;
     uint32_t run_status = 0;       // DCRP_STAT_* bits of the current run (reported in dcrp_stats.status)
     Comm* comm = nullptr;          // dcrp_engine_attach_comm
     bool run_event_valid = false;  // ev_end marks the end of the last run on its stream: later calls on OTHER streams wait for it
@@ -180,8 +208,10 @@ static cudaError_t size_out_arena(dcrp_engine* e, size_t n_pairs)
     e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
     cudaError_t ce = e->d_out.need(e->out_bytes + sizeof(Record) * (size_t)e->rec_cap);
     if (ce != cudaSuccess) return ce;
-    return e->h_out.need(e->out_bytes + sizeof(Record) * (size_t)std::min(e->rec_cap, INLINE_RECORDS));
+    // the mirror: the arena, INLINE_RECORDS records, and the flag line of a published run
+    return e->h_out.need(e->out_bytes + sizeof(Record) * (size_t)INLINE_RECORDS + 64);
 }
+static size_t pub_flag_off(const dcrp_engine* e) { return e->out_bytes + sizeof(Record) * (size_t)INLINE_RECORDS; }
 static Record* out_records(dcrp_engine* e) { return reinterpret_cast<Record*>(e->d_out.as<unsigned char>() + e->out_bytes); }
 
 static uint32_t* small_rec_count(dcrp_engine* e) { return e->d_out.as<uint32_t>(); }
@@ -697,7 +727,8 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr; cfg.numAttrs = behind_run_init ? 1 : 0;
-    const cudaError_t ce = cudaLaunchKernelExC(&cfg, kern, args);
+    const cudaError_t ce = behind_run_init ? cudaLaunchKernelExC(&cfg, kern, args)
+                                           : cudaLaunchKernel(kern, dim3(grid), dim3(S3_BLOCK), args, smem, st);
     ++e->launches; ++e->launches_this_run;
     if (ce != cudaSuccess)
         return fail(DCRP_ERR_CUDA, "k_screen3 launch (grid %u, %zu B shared memory, device %d): %s", grid, smem, e->device,
@@ -805,18 +836,6 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         r.trial_min = e->d_trial_min.as<double>();
     }
 
-    CU(cudaEventRecord(e->ev_begin, st));
-    // one launch clears the whole output arena (counters, stats, counts) and sets first_conflict = INT32_MAX
-    {
-        const bool zero_ext = d_counts && (run->flags & DCRP_FLAG_ZERO_COUNTS);
-        const size_t words = std::max(e->out_bytes / 4, zero_ext ? n_pairs : (size_t)0);
-        k_run_init<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(
-            e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4),
-            zero_ext ? reinterpret_cast<unsigned long long*>(d_counts) : nullptr, zero_ext ? (uint32_t)n_pairs : 0u);
-    }
-    ++e->launches; ++e->launches_this_run;
-    CU(cudaGetLastError());
-
     // slices keep the item count of one launch below 2^30
     const bool exact = (run->precision == DCRP_PRECISION_FP64);
     // the slab-first screen serves plain MIXED runs on tracks its per-warp tables hold; everything else
@@ -824,29 +843,59 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     const bool use3 = run->precision == DCRP_PRECISION_MIXED && !r.replay && !r.cull && !r.substep &&
                       !(run->flags & DCRP_FLAG_SCREEN_2D) && s.n_steps_max <= S3_MAX_VL && s.t_max <= S3_MAX_T;
     e->run_screen3 = use3;
-    // The per-pair choice of the slab direction costs ~50 us (1024 sample trials per pair) and saves ~10 % of a kernel:
-    // it pays off for one big run (>= 3e5 trials per pair) or once a scenario is run AGAIN with >= 2e4 trials per pair
-    // (a bench loop, a study streaming trial ranges).  A one-off dcrp_simulate on a new scenario, Drone::Simulation's
-    // 10 000-trial calls and the 600-flight day keep the per-track default.
-    bool axis_now = false;
-    if (use3 && !e->slab_ready && run->trial_count >= 20000 && (run->trial_count >= 300000 || e->runs_on_scenario >= 1)) {
-        axis_now = true;
-        k_slab_axis<<<(unsigned)n_pairs, S3_AXIS_BLOCK, 0, st>>>(s, 1.5f * s.thr_slab);   // once per scenario
-        ++e->launches; ++e->launches_this_run;
-        CU(cudaGetLastError());
-        e->slab_ready = true;
-    }
-    // ms_trials starts here: the trial kernel(s) alone.  (Not for a k_screen3 launched programmatically behind
-    // k_run_init: an event between the two would serialise them; ms_trials then includes the 2 us it overlaps.)
-    const bool pdl = use3 && !axis_now;
-    if (!pdl) CU(cudaEventRecord(e->ev_k0, st));
-    e->k0_is_begin = pdl;
     const uint64_t per_item = exact ? (uint64_t)EXB : (use3 ? (uint64_t)S3_CHW : screen_chunk());
     // DCRP_MAX_ITEMS: test aid, forces the slicing below at small sizes (tests/test_gpu_parity.py)
     static const uint64_t max_items = std::getenv("DCRP_MAX_ITEMS")
         ? std::max<uint64_t>(1, std::strtoull(std::getenv("DCRP_MAX_ITEMS"), nullptr, 10)) : MAX_ITEMS_PER_LAUNCH;
     const uint64_t max_chunks = std::max<uint64_t>(1, max_items / n_pairs);
     const uint64_t slice_max = max_chunks * per_item;
+
+    // Published run (dcrp_engine::published): one k_screen3 launch with engine-owned counts.  Without a communicator
+    // (whose all-reduce may still want the counts on the device) the kernel also leaves the arena cleared, and a run
+    // that finds it so needs no clearing launch in front of it.
+    e->published = use3 && run->trial_count > 0 && run->trial_count <= slice_max && !d_counts;
+    const bool self_clean = e->published && !e->comm;
+    const bool arena_is_clean = e->arena_clean && e->clean_ptr == e->d_out.p && e->clean_bytes == e->out_bytes;
+    const bool need_init = !(e->published && arena_is_clean);
+    if (e->published && ++e->pub_seq == 0) ++e->pub_seq;
+
+    // DCRP_FLAG_NO_TIMING: no timing events around the kernels (each is a microsecond of host time in front of the
+    // trial kernel, and one between k_screen3 and k_publish keeps the two from being queued back to back)
+    const bool timed = !(run->flags & DCRP_FLAG_NO_TIMING);
+    e->run_timed = timed;
+    HOST_MARK(2);
+    if (timed) CU(cudaEventRecord(e->ev_begin, st));
+    HOST_MARK(3);
+    // The per-pair choice of the slab direction costs ~50 us (1024 sample trials per pair) and saves ~10 % of a kernel:
+    // it pays off for one big run (>= 3e5 trials per pair) or once a scenario is run AGAIN with >= 2e4 trials per pair
+    // (a bench loop, a study streaming trial ranges).  A one-off dcrp_simulate on a new scenario, Drone::Simulation's
+    // 10 000-trial calls and the 600-flight day keep the per-track default.
+    if (use3 && !e->slab_ready && run->trial_count >= 20000 && (run->trial_count >= 300000 || e->runs_on_scenario >= 1)) {
+        k_slab_axis<<<(unsigned)n_pairs, S3_AXIS_BLOCK, 0, st>>>(s, 1.5f * s.thr_slab);   // once per scenario
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+        e->slab_ready = true;
+    }
+    // one launch clears the whole output arena (counters, stats, counts) and sets first_conflict = INT32_MAX
+    if (need_init) {
+        const bool zero_ext = d_counts && (run->flags & DCRP_FLAG_ZERO_COUNTS);
+        const size_t words = std::max(e->out_bytes / 4, zero_ext ? n_pairs : (size_t)0);
+        k_run_init<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(
+            e->d_out.as<uint32_t>(), (uint32_t)(e->out_first_off / 4), (uint32_t)(e->out_bytes / 4),
+            zero_ext ? reinterpret_cast<unsigned long long*>(d_counts) : nullptr, zero_ext ? (uint32_t)n_pairs : 0u);
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+    }
+    // whatever runs next finds the arena as this run leaves it
+    e->arena_clean = self_clean;
+    e->clean_ptr = e->d_out.p;
+    e->clean_bytes = e->out_bytes;
+    HOST_MARK(4);
+    // ms_trials starts here: the trial kernel(s) alone.  (Not for k_screen3: launched programmatically behind
+    // k_run_init an event between the two would serialise them, and ms_trials includes the 2 us it overlaps.)
+    const bool pdl = use3 && need_init;
+    if (!use3 && timed) CU(cudaEventRecord(e->ev_k0, st));
+    e->k0_is_begin = use3;
     for (uint64_t first = 0; first < run->trial_count; first += slice_max) {
         r.slice_first = first;
         r.slice_count = std::min<uint64_t>(slice_max, run->trial_count - first);
@@ -872,13 +921,32 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     }
     e->has_confirm = run->precision == DCRP_PRECISION_MIXED && run->trial_count && !use3;    // k_screen3 confirms in-kernel
     if (e->has_confirm) {
-        CU(cudaEventRecord(e->ev_trials, st));
+        if (timed) CU(cudaEventRecord(e->ev_trials, st));
         // grid-stride over the candidate list whose length lives on the device
         k_confirm_all<<<e->prop.multiProcessorCount * 4, 128, 0, st>>>(s, r);
         ++e->launches; ++e->launches_this_run;
         CU(cudaGetLastError());
     }
+    if (e->published) {
+        if (timed) CU(cudaEventRecord(e->ev_trials, st));       // the end of the trial kernel
+        PublishArgs pa{};
+        CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&pa.host), e->h_out.p, 0));
+        pa.arena = e->d_out.as<uint32_t>();
+        pa.records = reinterpret_cast<const uint32_t*>(out_records(e));
+        pa.words = (uint32_t)(e->out_bytes / 4);
+        pa.first_word = (uint32_t)(e->out_first_off / 4);
+        pa.rec_cap = e->rec_cap;
+        pa.inline_recs = std::min(e->rec_cap, INLINE_RECORDS);
+        pa.flag_word = (uint32_t)(pub_flag_off(e) / 4);
+        pa.seq = e->pub_seq;
+        pa.clean = self_clean ? 1 : 0;
+        k_publish<<<1, 256, 0, st>>>(pa);
+        ++e->launches; ++e->launches_this_run;
+        CU(cudaGetLastError());
+    }
+    HOST_MARK(5);
     CU(cudaEventRecord(e->ev_end, st));      // (without a confirm kernel this is also the end of the trial kernels)
+    HOST_MARK(6);
     e->run_event_valid = true;
     e->has_run = true;
     ++e->runs_on_scenario;
@@ -900,6 +968,7 @@ extern "C" int dcrp_last_run_ms(dcrp_engine* e, float* ms)
 {
     if (!e || !ms) return fail(DCRP_ERR_INVALID, "dcrp_last_run_ms: NULL argument");
     if (!e->has_run) return fail(DCRP_ERR_STATE, "no run to time");
+    if (!e->run_timed) return fail(DCRP_ERR_STATE, "the last run was not timed (DCRP_FLAG_NO_TIMING)");
     CU(cudaSetDevice(e->device));
     (void)cudaGetLastError();      // a stale error left in this thread by other CUDA users (torch, NCCL) is not ours to report
     CU(cudaEventSynchronize(e->ev_end));
@@ -919,7 +988,24 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
     // one D2H copy of the output arena and the first few records into the pinned mirror
     const uint32_t inl = res->records ? std::min(e->rec_cap, INLINE_RECORDS) : 0u;
+    HOST_MARK(7);
+    bool have = false;              // the kernel has delivered the results itself
+    if (e->published) {
+        // poll the flag behind the mirror (short runs), then fall back to waiting for the stream (long runs; a run
+        // that failed never raises the flag and the error surfaces here)
+        volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(e->h_out.as<unsigned char>() + pub_flag_off(e));
+        const auto t0 = std::chrono::steady_clock::now();
+        while (!(have = (*flag == e->pub_seq)) && std::chrono::steady_clock::now() - t0 < std::chrono::milliseconds(2)) {}
+        if (!have) {
+            const cudaError_t q = cudaStreamSynchronize(st);
+            if (q != cudaSuccess) return fail(DCRP_ERR_CUDA, "waiting for the run failed: %s", cudaGetErrorString(q));
+            have = (*flag == e->pub_seq);
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
+    if (!have) {
     CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, e->out_bytes + sizeof(Record) * (size_t)inl, cudaMemcpyDeviceToHost, st));
+    HOST_MARK(8);
     {   // short runs: poll (a blocking sync wakes up 10-20 us late, a tenth of a 1e7-trial run); long runs: block
         const auto t0 = std::chrono::steady_clock::now();
         cudaError_t q;
@@ -928,6 +1014,8 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
         if (q == cudaErrorNotReady) q = cudaStreamSynchronize(st);
         if (q != cudaSuccess) return fail(DCRP_ERR_CUDA, "waiting for the run failed: %s", cudaGetErrorString(q));
     }
+    }
+    HOST_MARK(9);
     if (e->comm && e->comm->h_err && *e->comm->h_err)
         return fail(DCRP_ERR_COMM, "count exchange: a peer rank did not deliver its counts within 10 s");
     const unsigned char* small = e->h_out.as<unsigned char>();
@@ -937,6 +1025,8 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     std::memcpy(&cand_count, small + 4, 4);
     std::memcpy(stats, small + 16, sizeof stats);
     uint64_t d2h = e->out_bytes + sizeof(Record) * (size_t)inl;
+    if (have)       // what k_publish stored into the mirror: the arena, the records there are, the flag
+        d2h = e->out_bytes + sizeof(Record) * (size_t)std::min(std::min(rec_count, e->rec_cap), INLINE_RECORDS) + 4;
 
     if (e->run.precision == DCRP_PRECISION_MIXED && cand_count > CAND_CAP) {
         // More candidates than the list holds (absurd hit rates, e.g. a huge radius):
@@ -1025,12 +1115,23 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     }
     o.ms_prepare = e->ms_prepare;
     float ms = 0.f;
-    // as few event queries as the run needs (each is a driver call; a 1e7-trial run is 170 us)
+    if (e->run.flags & DCRP_FLAG_NO_TIMING) {
+        // the caller does not read them (the end-of-run event of a published run completes a few microseconds after
+        // the flag: not waited for)
+    } else if (have) {
+        cudaError_t q;
+        while ((q = cudaEventQuery(e->ev_end)) == cudaErrorNotReady) {}
+        if (q != cudaSuccess) return fail(DCRP_ERR_CUDA, "waiting for the run failed: %s", cudaGetErrorString(q));
+        CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_trials));    o.ms_trials = ms;
+        CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));       o.ms_device_total = ms;
+    } else {
+    // as few event queries as the run needs (each is a driver call; a 1e7-trial run is 150 us)
     cudaEvent_t trials_end = e->has_confirm ? e->ev_trials : e->ev_end;
     CU(cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end));    o.ms_device_total = ms;
     if (e->k0_is_begin && !e->has_confirm) o.ms_trials = ms;
     else { CU(cudaEventElapsedTime(&ms, e->k0_is_begin ? e->ev_begin : e->ev_k0, trials_end)); o.ms_trials = ms; }
     if (e->has_confirm) { CU(cudaEventElapsedTime(&ms, e->ev_trials, e->ev_end)); o.ms_confirm = ms; }
+    }
     o.h2d_bytes = e->h2d_run;
     o.d2h_bytes = d2h;
     return DCRP_OK;
@@ -1045,12 +1146,18 @@ extern "C" int dcrp_simulate(dcrp_engine* e, const dcrp_track* tracks, int32_t n
     if (!e) return fail(DCRP_ERR_INVALID, "engine is NULL");
     // Drone::Simulation calls this once per (aircraft, drone) with the same arrays, a bench once per step:
     // the scenario already in HBM (tables of stage 1 included) is reused when the inputs are unchanged.
+#ifdef DCRP_TIMELINE
+    g_host_t0 = std::chrono::steady_clock::now();
+#endif
+    HOST_MARK(0);
     const bool cached = scenario_is_resident(e, tracks, n_tracks, drones, n_drones, model);
+    HOST_MARK(1);
     int rc = cached ? DCRP_OK : dcrp_scenario_upload(e, tracks, n_tracks, drones, n_drones, model);
     if (rc != DCRP_OK) return rc;
     rc = dcrp_run_async(e, run, nullptr, nullptr);
     if (rc != DCRP_OK) return rc;
     rc = dcrp_fetch(e, result);
+    HOST_MARK(10);
     if (rc != DCRP_OK) return rc;
     if (cached) result->stats.status |= DCRP_STAT_SCENARIO_CACHED;
     else        result->stats.h2d_bytes += e->h2d_scenario;
@@ -1083,6 +1190,8 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     as_run.precision = DCRP_PRECISION_MIXED; as_run.record_capacity = run->record_capacity;
     e->run = as_run;
     e->allpairs_run = true;
+    e->published = false;
+    e->arena_clean = false;
     e->ap_rays = n_rays;
     e->run_stream = st;
     e->launches_this_run = 0;
@@ -1376,6 +1485,7 @@ extern "C" int dcrp_allreduce_counts(dcrp_engine* e, void* stream, uint64_t* d_c
     unsigned long long* counts = d_counts ? reinterpret_cast<unsigned long long*>(d_counts)
         : reinterpret_cast<unsigned long long*>(e->d_out.as<unsigned char>() + e->out_counts_off);
     if (c->nranks == 1) return DCRP_OK;
+    if (!d_counts) e->published = false;     // the arena's counts change behind the run: dcrp_fetch copies them from the device
     if (c->p2p && n_pairs <= COMM_MAX_PAIRS) {
         ++c->seq;
         const int parity = (int)(c->seq & 1ull);

@@ -545,6 +545,39 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         if (cta_acc[1]) atomicAdd(&r.stats[ST_ISSUED], cta_acc[1]);
         if (cta_acc[2]) atomicAdd(&r.stats[ST_SLAB_SURVIVORS], cta_acc[2]);
     }
+
+}
+
+// Published run (engine.cu): launched right behind k_screen3 on the same stream, one CTA.  Copies the output arena
+// (counters, statistics, counts, first-conflict indices) and the first records into the host's pinned mirror through
+// its device mapping, fences at system scope and raises the flag the host polls; then -- clean -- clears the arena,
+// which is what k_run_init would do in front of the next run.  A kernel of its own rather than the last CTA of
+// k_screen3: code added to that kernel, even a time stamp at its entry, cost 1-3 % of it (A/B on one box).
+struct PublishArgs {
+    uint32_t* host;                  // the mirror as the device sees it
+    uint32_t* arena;                 // the output arena (word 0 = record count)
+    const uint32_t* records;
+    uint32_t  words;                 // arena words in front of the records
+    uint32_t  first_word;            // first word of first_conflict[] (cleared to INT32_MAX, everything before it to 0)
+    uint32_t  rec_cap, inline_recs;  // records that travel with the mirror (right behind the arena words)
+    uint32_t  flag_word;             // mirror word of the flag
+    uint32_t  seq;                   // what the flag reads once the mirror is complete
+    int32_t   clean;
+};
+
+__global__ void __launch_bounds__(256) k_publish(const PublishArgs a)
+{
+    for (uint32_t i = threadIdx.x; i < a.words; i += 256) a.host[i] = a.arena[i];
+    const uint32_t nrec = min(min(a.arena[0], a.rec_cap), a.inline_recs);
+    for (uint32_t i = threadIdx.x; i < nrec * (uint32_t)(sizeof(Record) / 4); i += 256) a.host[a.words + i] = a.records[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile uint32_t*>(a.host + a.flag_word) = a.seq;
+        __threadfence_system();
+    }
+    if (a.clean)
+        for (uint32_t i = threadIdx.x; i < a.words; i += 256) a.arena[i] = i < a.first_word ? 0u : 0x7fffffffu;
 }
 
 }  // namespace dcrp

@@ -169,7 +169,7 @@ void Drone::Simulation64(uint64_t number_runs, double* total_collisions)
     run.trial_begin = consumed;
     run.trial_count = number_runs;
     run.precision = precision_;
-    run.flags = run_flags_;
+    run.flags = run_flags_ | DCRP_FLAG_NO_TIMING;                 // (the reference's interface has no timings to fill)
     run.record_capacity = 1u << 16;
     // one-pair scenario: the Philox counter still carries the real indices, so this
     // call draws exactly what a whole-day batch draws for (aircraft, drone)

@@ -71,6 +71,12 @@ extern "C" {
 
 #define DCRP_FLAG_ZERO_COUNTS 16u  /* dcrp_run_async with a caller-owned d_counts: clear it first (in the launch that
                                      clears the engine's own accumulators), instead of adding to what is there   */
+#define DCRP_FLAG_NO_TIMING   32u  /* leave dcrp_stats.ms_* at 0 and record no timing events (dcrp_last_run_ms then
+                                      returns DCRP_ERR_STATE).  For callers that do not read the times: a plain MIXED
+                                      run of one launch with engine-owned counts is read back by a small kernel queued
+                                      behind the trial kernel (it stores the results into the host's pinned mirror and
+                                      raises a flag: no D2H copy, no wait for the stream), and the host learns of a
+                                      completed CUDA event ~13 us later than of that flag                            */
 
 typedef struct dcrp_engine dcrp_engine;
 
@@ -169,9 +175,10 @@ typedef struct dcrp_stats {
     float    ms_prepare;       /* stage-1 / per-pair tables                                           */
     float    ms_trials;        /* trial kernel(s): screen or exact                                    */
     float    ms_confirm;       /* fp64 confirm of candidates                                          */
-    float    ms_device_total;  /* first to last kernel, CUDA events on the engine stream              */
+    float    ms_device_total;  /* first to last kernel, CUDA events on the run's stream (0 with
+                                  DCRP_FLAG_NO_TIMING)                                                    */
     uint64_t h2d_bytes;
-    uint64_t d2h_bytes;
+    uint64_t d2h_bytes;        /* bytes brought to the host: by the copy engine, or by the kernel's stores    */
     /* DCRP_FLAG_REACH_CULL only (0 otherwise) */
     uint64_t trials_culled;    /* trials of (track, drone) pairs the reach bound cleared as a whole: no
                                   draws made, nothing in tests_shared                                     */

@@ -52,6 +52,25 @@ def test_own_counts_equal_caller_counts_and_fp64(engine, tracks, ring1):
         assert pub.stats["d2h_bytes"] > 0 and pub.stats["ms_device_total"] > 0
 
 
+def test_no_timing_flag_changes_nothing_but_the_times(engine, tracks, ring5):
+    """DCRP_FLAG_NO_TIMING: dcrp_stats.ms_* stay 0 (a run read back by k_publish then returns without waiting for its
+    end-of-run event), everything else is the run's; without the flag the times are CUDA-event times."""
+    kw = dict(seed=SEED, trial_begin=123, trial_count=20000, precision=capi.MIXED, record_capacity=4096)
+    timed = engine.simulate(tracks[:1], ring5, **kw)
+    quiet = engine.simulate(tracks[:1], ring5, flags=capi.FLAG_NO_TIMING, **kw)
+    _same(timed, quiet, "no-timing")
+    for key in ("trials", "tests_evaluated", "tests_shared", "drone_steps", "hits"):     # (survivor counts depend on the slab
+        assert timed.stats[key] == quiet.stats[key], key                                 #  directions, refined at the second run)
+    assert 0 < timed.stats["ms_trials"] <= timed.stats["ms_device_total"] < 50
+    assert quiet.stats["ms_trials"] == 0 and quiet.stats["ms_device_total"] == 0 and quiet.stats["ms_confirm"] == 0
+    with pytest.raises(capi.DcrpError):
+        engine.last_run_ms()                                                     # the last run recorded no events
+    f64 = engine.simulate(tracks[:1], ring5, seed=SEED, trial_begin=123, trial_count=20000, precision=capi.FP64,
+                          record_capacity=4096, flags=capi.FLAG_NO_TIMING)
+    _same(f64, quiet, "fp64 no-timing")
+    assert f64.stats["ms_device_total"] == 0
+
+
 def test_runs_back_to_back(engine, tracks, ring5):
     """40 runs on one engine, no other call between: every result is the run's own (counts of disjoint trial ranges
     add up to the count of the whole range, ids partition)."""

@@ -9,6 +9,37 @@ sys.path.insert(0, ROOT)
 import drone_collision_rp_b200 as pk
 from drone_collision_rp_b200 import capi, scenario
 
+# host-side stamps inside one dcrp_simulate call (instrumented build only: libdcrp_timeline.so, make EXTRA=-DDCRP_TIMELINE)
+import ctypes as C
+import numpy as np
+tl = os.path.join(pk.PKG_DIR, "libdcrp_timeline.so")
+if "--host" in sys.argv and os.path.exists(tl):
+    capi.LIBDCRP = tl          # (the ONLY engine library of this process: its extern "C" calls bind to the first one loaded)
+    tracks, _ = scenario.synthetic_tracks(tempfile.mkdtemp(), 1)
+    ring = scenario.load_ring(pk.RING_5KM)
+    scn = capi.Scenario(tracks, ring)
+    eng = capi.Engine(0)
+    L = capi.lib()
+    L.dcrp_debug_host_times.argtypes = [C.c_void_p, C.c_int]
+    call = eng.prepared_simulate(scn, precision=capi.MIXED, record_capacity=4096, seed=1)
+    names = ["entry", "resident check done", "run_async: before ev_begin", "ev_begin recorded", "k_run_init launched",
+             "k_screen3 launched", "ev_end recorded", "fetch: before copy", "copy queued", "stream done", "fetch done"]
+    for n in (1, 101011):
+        rows, walls, dev = [], [], []
+        for k in range(60):
+            t0 = time.perf_counter()
+            _, _, st = call(k * n, n)
+            walls.append(time.perf_counter() - t0)
+            buf = np.zeros(16)
+            L.dcrp_debug_host_times(buf.ctypes.data_as(C.c_void_p), 16)
+            rows.append(buf[:11].copy()); dev.append(st.ms_device_total)
+        med = np.median(np.array(rows[10:]), axis=0) * 1e-3
+        print("host stamps n=%d (us, medians; wall %.1f, device_total %.1f):" % (n, 1e6 * np.median(walls[10:]), 1e3 * np.median(dev[10:])))
+        for nm, v in zip(names, med):
+            print("   %-28s %8.2f" % (nm, v))
+    eng.close()
+    sys.exit(0)
+
 eng = capi.Engine(0)
 tracks, _ = scenario.synthetic_tracks(tempfile.mkdtemp(), 1)
 ring = scenario.load_ring(pk.RING_5KM)
