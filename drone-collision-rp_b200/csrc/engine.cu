@@ -198,6 +198,8 @@ struct dcrp_engine {
 
 // Records kept in the first D2H copy of a fetch (one copy, one sync for the usual handful of hits).
 constexpr uint32_t INLINE_RECORDS = 32;
+// Largest output arena k_publish delivers (dcrp_engine::published); larger ones go through the copy engine.
+constexpr size_t PUBLISH_MAX_BYTES = 64 * 1024;
 
 // Sizes the per-run output arena: [rec_count, cand_count, work_counter, pad | stats | counts | first_conflict]
 // (cleared by k_run_init) followed by rec_cap records.
@@ -853,7 +855,9 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     // Published run (dcrp_engine::published): one k_screen3 launch with engine-owned counts.  Without a communicator
     // (whose all-reduce may still want the counts on the device) the kernel also leaves the arena cleared, and a run
     // that finds it so needs no clearing launch in front of it.
-    e->published = use3 && run->trial_count > 0 && run->trial_count <= slice_max && !d_counts;
+    // (one CTA storing over PCIe: for the scenarios Drone::Simulation and the benchmark run -- up to a few thousand
+    // pairs; the 713 KB arena of the 600-flight day takes it 0.24 ms, the copy engine 0.03)
+    e->published = use3 && run->trial_count > 0 && run->trial_count <= slice_max && !d_counts && e->out_bytes <= PUBLISH_MAX_BYTES;
     const bool self_clean = e->published && !e->comm;
     const bool arena_is_clean = e->arena_clean && e->clean_ptr == e->d_out.p && e->clean_bytes == e->out_bytes;
     const bool need_init = !(e->published && arena_is_clean);

@@ -6,17 +6,20 @@
 // per two tests instead of six packed ops, and with a well-chosen n it clears 90-99 % of the trials
 // (5 km ring: 99 %); the survivors queue up per warp and are re-scanned 128 at a time by the 2-D
 // level-1 scan of kernels.cu (scan_tile_xy), then level 2 (3-D fp32) and level 3 (the fp64 decision in the
-// reference's order of operations, by the lane that holds the candidate) -- all inside this one kernel.
+// reference's order of operations), one flagged trial at a time by the whole warp -- all inside this one kernel.
 // Decisions are those of the all-fp64 kernel by construction: every level is conservative and the last
 // one is exact (tests/test_gpu_parity.py, test_gpu_fuzz.py).
 //
 // No sort: the slab test of an index before the trial's kink (i < t1st) evaluates the stage-2 ray
 // extrapolated backwards, which can only ADD survivors, so all lanes scan the whole track from index 0
 // with warp-uniform bounds and nothing is staged in shared memory per trial.  Warps are independent
-// (no CTA barrier in steady state): each pulls 512-trial items (two rounds of 8 trials per lane) from a
-// device-side counter, keeps the track (one 1-D TMA bulk copy per track change, its own mbarrier), its pair's
-// projected track and kink tables in its own shared-memory slice, and keeps its own survivor queue.  The grid is
-// launched programmatically dependent on the launch that clears the output arena (griddep_wait below).
+// (no CTA barrier in steady state): each runs 256-trial items (8 trials per lane), taken in blocks of
+// consecutive items -- a static first block, then blocks numbered by a device-side counter whose size tapers
+// from 32 items to 1 towards the end of the launch (S3Sched) -- keeps the track (one 1-D TMA bulk copy per
+// track change, its own mbarrier), its pair's projected track and kink tables in its own shared-memory slice
+// (re-staged only when the pair changes) and keeps its own survivor queue.  The grid is launched
+// programmatically dependent on the launch that clears the output arena (griddep_wait below), or alone when
+// the previous run left the arena cleared (k_publish, at the end of this file).
 //
 // Reference semantics: /root/reference/Drone.cpp:107-127,164-231,253-265 (restated in dcrp_math.cuh).
 #include "dcrp_device.cuh"
@@ -572,10 +575,7 @@ __global__ void __launch_bounds__(256) k_publish(const PublishArgs a)
     for (uint32_t i = threadIdx.x; i < nrec * (uint32_t)(sizeof(Record) / 4); i += 256) a.host[a.words + i] = a.records[i];
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) {
-        *reinterpret_cast<volatile uint32_t*>(a.host + a.flag_word) = a.seq;
-        __threadfence_system();
-    }
+    if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(a.host + a.flag_word) = a.seq;
     if (a.clean)
         for (uint32_t i = threadIdx.x; i < a.words; i += 256) a.arena[i] = i < a.first_word ? 0u : 0x7fffffffu;
 }
