@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DCRP_ABI_VERSION 4
+#define DCRP_ABI_VERSION 5
 
 /* status codes */
 #define DCRP_OK               0

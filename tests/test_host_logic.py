@@ -35,7 +35,7 @@ def test_libraries_export_every_declared_symbol():
         nm = subprocess.run(["nm", "-D", "--defined-only", libpath], capture_output=True, text=True, check=True).stdout
         exported = set(re.findall(r" T (dcrph?_[a-z0-9_]+)", nm))
         assert declared <= exported, declared - exported
-    assert capi.lib().dcrp_abi_version() == 4
+    assert capi.lib().dcrp_abi_version() == 5
 
 
 def test_abi_struct_sizes_match_header():
