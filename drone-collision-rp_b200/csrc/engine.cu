@@ -102,7 +102,7 @@ struct PinnedBuf {         // grow-only pinned host buffer (async copies need pa
         p = nullptr; cap = 0;
         size_t want = (bytes + 4095) & ~size_t(4095);
         cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocMapped);      // kernels may write it (published runs)
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) { cap = want; std::memset(p, 0, want); }     // (the flag word of a published run must not start on garbage)
         return e;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
@@ -208,7 +208,9 @@ static cudaError_t size_out_arena(dcrp_engine* e, size_t n_pairs)
     e->out_counts_off = align256(16 + sizeof(unsigned long long) * ST_COUNT);
     e->out_first_off = align256(e->out_counts_off + sizeof(uint64_t) * n_pairs);
     e->out_bytes = align256(e->out_first_off + sizeof(int32_t) * n_pairs);
+    const size_t cap_before = e->d_out.cap;
     cudaError_t ce = e->d_out.need(e->out_bytes + sizeof(Record) * (size_t)e->rec_cap);
+    if (e->d_out.cap != cap_before) e->arena_clean = false;     // a new allocation (even at the old address) is not a cleared arena
     if (ce != cudaSuccess) return ce;
     // the mirror: the arena, INLINE_RECORDS records, and the flag line of a published run
     return e->h_out.need(e->out_bytes + sizeof(Record) * (size_t)INLINE_RECORDS + 64);
@@ -760,6 +762,7 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
     const ScenarioDev& s = e->sd;
     const size_t n_pairs = (size_t)s.n_tracks * (size_t)s.n_drones;
 
+    e->has_run = false;            // until every launch below is queued: a run that failed half-way cannot be fetched
     e->run = *run;
     e->allpairs_run = false;
     e->run_stream_prev = e->run_stream;
@@ -942,6 +945,9 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
         pa.rec_cap = e->rec_cap;
         pa.inline_recs = std::min(e->rec_cap, INLINE_RECORDS);
         pa.flag_word = (uint32_t)(pub_flag_off(e) / 4);
+        // The flag's place in the mirror moves with the scenario's size: whatever an earlier run left there (a count,
+        // a first-conflict index -- small integers, like sequence numbers) must not read as "delivered".
+        *reinterpret_cast<volatile uint32_t*>(e->h_out.as<unsigned char>() + pub_flag_off(e)) = 0u;
         pa.seq = e->pub_seq;
         pa.clean = self_clean ? 1 : 0;
         k_publish<<<1, 256, 0, st>>>(pa);
@@ -1192,11 +1198,17 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     dcrp_run as_run{};                      // what dcrp_fetch reports against
     as_run.seed = run->seed; as_run.trial_begin = run->ray_begin; as_run.trial_count = run->ray_count;
     as_run.precision = DCRP_PRECISION_MIXED; as_run.record_capacity = run->record_capacity;
+    e->has_run = false;
     e->run = as_run;
     e->allpairs_run = true;
     e->published = false;
     e->arena_clean = false;
+    e->run_timed = true;
+    e->run_cull = false;
+    e->run_screen3 = false;
+    e->run_status = 0;
     e->ap_rays = n_rays;
+    e->run_stream_prev = e->run_stream;
     e->run_stream = st;
     e->launches_this_run = 0;
     e->h2d_run = 0;
@@ -1204,6 +1216,7 @@ extern "C" int dcrp_allpairs(dcrp_engine* e, const dcrp_allpairs_run* run, dcrp_
     e->rec_cap = run->record_capacity ? run->record_capacity : DEFAULT_RECORD_CAP;
 
     CU(size_out_arena(e, n_pairs));
+    if (e->run_event_valid && st != e->run_stream_prev) CU(cudaStreamWaitEvent(st, e->ev_end, 0));   // the arenas are shared between runs
     constexpr uint32_t L2_CAP = 1u << 22;
     const size_t hist_bytes = sizeof(uint32_t) * ((size_t)s.n_drones * run->ref_takeoff_t + 1);
     CU(e->d_ap_hist.need(hist_bytes));

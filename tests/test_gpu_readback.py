@@ -133,3 +133,49 @@ print("sliced ok", a.stats["kernel_launches"], int(a.counts.sum()))
     env = dict(os.environ, DCRP_MAX_ITEMS="1000")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "sliced ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_published_runs_across_scenario_sizes(engine, tracks, ring1):
+    """The flag k_publish raises sits behind the output arena in the host's pinned mirror, so its place moves with the
+    number of pairs -- onto words an earlier, larger run filled with counts and first-conflict indices: small
+    integers, like the flag's sequence numbers.  On a fresh engine (sequence numbers from 1) a hit-dense 396-pair
+    scenario and a one-pair scenario alternate; every result must be the run's own (dcrp_run_async clears the flag's
+    word before it queues k_publish).  Both parities of the sequence number meet the stale words."""
+    m = capi.default_model()
+    m.aircraft_radius = 300.0
+    big, small = (tracks[:4], ring1), (tracks[:1], ring1[47:48])
+    kw = dict(seed=11, precision=capi.MIXED, model=m, record_capacity=1 << 15, flags=capi.FLAG_NO_TIMING)
+    want_big = engine.simulate(*big, seed=11, trial_count=96, precision=capi.FP64, model=m, record_capacity=1 << 15)
+    assert want_big.hits > 3000 and 2 < np.median(want_big.counts) < 96
+    fresh = capi.Engine(0)
+    try:
+        for k in range(70):
+            a = fresh.simulate(*big, trial_count=96, **kw)
+            _same(a, want_big, ("big", k))
+            for rep in range(2 if k == 35 else 1):          # (one extra run flips the parity of the small runs' numbers)
+                n0 = 1000 * k + 500 * rep
+                b = fresh.simulate(*small, trial_begin=n0, trial_count=700, **kw)
+                want = engine.simulate(*small, seed=11, trial_begin=n0, trial_count=700, precision=capi.FP64, model=m,
+                                       record_capacity=1 << 15)
+                _same(b, want, ("small", k, rep))
+                assert b.stats["trials"] == 700 and b.stats["hits"] == want.stats["hits"]
+    finally:
+        fresh.close()
+
+
+def test_a_failed_run_cannot_be_fetched(engine, tracks, ring1):
+    """dcrp_run_async that fails (here: a replay row of another track) leaves nothing to fetch -- not the previous
+    run's arena read against the failed run's parameters."""
+    engine.upload(tracks[:1], ring1[:4])
+    ok = engine.fetch(engine.run_async(seed=5, trial_count=300, precision=capi.MIXED))
+    assert ok.stats["trials"] == 1200
+    bad = np.zeros(4 * 50, dtype=capi.DRAW_DTYPE)
+    bad["t1st"] = tracks[0]["takeoff_t"] + 1
+    with pytest.raises(capi.DcrpError) as e:
+        engine.run_async(seed=5, trial_count=50, precision=capi.FP64, flags=capi.FLAG_PER_TRIAL, replay=bad)
+    assert e.value.status == capi.ERR_INVALID
+    with pytest.raises(capi.DcrpError) as e:
+        engine.fetch(capi.Engine._run_struct(5, 0, 50, capi.FP64))
+    assert e.value.status == capi.ERR_STATE
+    again = engine.fetch(engine.run_async(seed=5, trial_count=300, precision=capi.MIXED))
+    assert np.array_equal(again.counts, ok.counts)
