@@ -82,6 +82,7 @@ class Drone {
     int last_status_ = 0;
     std::string last_error_;
     std::vector<double> last_traj_;
+    std::vector<dcrp_record> records_;                 // record buffer of Simulation, allocated once
 
     bool load_cells(const std::string& path);
     void fail(int status, const std::string& what);
