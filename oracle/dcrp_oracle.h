@@ -100,7 +100,12 @@ int64_t orc_run_philox(const double* ax, const double* ay, const double* az, int
  * the GPU implements the same definition.  Drone and aircraft move linearly
  * between consecutive samples; on segment i the relative position is
  * D(t) = D_i + t (D_{i+1} - D_i); a conflict is min_t |D(t)|^2 < R^2.
- * n trials of one (track, drone); trajectories come from orc_trial. */
+ * n trials of one (track, drone); trajectories come from orc_trial.
+ * What IS anchored (tests/test_oracle_pinning.py::test_substep_extension_anchored_on_reference_trajectories):
+ * the trajectories it interpolates are the reference's bit for bit; at the samples it reduces to the
+ * reference (every reference hit is a sub-step hit in the adjacent segment, min distance <= the reference's);
+ * and an independent numpy evaluation (closed form in long double + brute force on 4097 points per
+ * segment) of trajectories written by the unmodified Drone.cpp gives the same minimum and conflict time. */
 int64_t orc_run_trials_substep(const double* ax, const double* ay, const double* az, int32_t n_steps,
                                double x0, double y0, double heading0,
                                const orc_draw* draws, int64_t n, const orc_model* model,

@@ -188,3 +188,87 @@ def test_target_box_matches_reference(oracle, ref):
     rc, _ = oracle.target_box(5705500.0, 0.0)          # between the runways: reference leaves stale values
     assert rc == -1
     assert np.isnan(ref.cubed_volume(5705500.0, 0.0)[:4]).all()
+
+
+def _substep_independent(traj, trk, radius):
+    """Interpolated separation of one trial, written independently of oracle/dcrp_oracle.c: positions of drone and
+    aircraft interpolated linearly between samples; per segment the closest approach in closed form (numpy longdouble)
+    and by brute force on 4097 points.  Returns (min distance, first conflict time in index units or -1,
+    brute-force min distance, longest relative step)."""
+    ld = np.longdouble
+    D = np.stack([traj[0].astype(ld) - trk["x"].astype(ld), traj[1].astype(ld) - trk["y"].astype(ld),
+                  traj[2].astype(ld) - trk["z"].astype(ld)], axis=1)            # relative position per sample
+    D0, E = D[:-1], D[1:] - D[:-1]
+    a = (E * E).sum(1)
+    b = (D0 * E).sum(1)
+    t = np.where(a > 0, np.clip(-b / np.where(a > 0, a, 1), 0, 1), 0)
+    closest = np.sqrt(((D0 + t[:, None] * E) ** 2).sum(1))
+    ts = np.linspace(0.0, 1.0, 4097).astype(ld)
+    dist = np.sqrt(((D0[:, None, :] + ts[None, :, None] * E[:, None, :]) ** 2).sum(2))      # [segment, sample]
+    first_time = -1.0
+    inside = dist < ld(radius)
+    if inside.any():
+        seg = int(np.argmax(inside.any(1)))
+        k = int(np.argmax(inside[seg]))
+        if k == 0:
+            first_time = float(seg)
+        else:                                   # entry between two brute-force points: bisect the exact distance
+            lo, hi = ts[k - 1], ts[k]
+            for _ in range(60):
+                mid = (lo + hi) / 2
+                if np.sqrt(((D0[seg] + mid * E[seg]) ** 2).sum()) < ld(radius):
+                    hi = mid
+                else:
+                    lo = mid
+            first_time = float(seg + hi)
+    return float(closest.min()), first_time, float(dist.min()), float(np.sqrt(a.max()))
+
+
+def test_substep_extension_anchored_on_reference_trajectories(oracle, golden, tracks, ring1):
+    """The sub-step mode is an EXTENSION: the reference compares sample i with sample i only (Drone.cpp:254-259), so no
+    reference output can pin it and oracle/dcrp_oracle.h says so.  What can be anchored on the reference is:
+      (1) at the samples it reduces to the reference -- on the reference's own replayed draws every reference hit is a
+          sub-step hit, found in the segment that ends or starts at the reference's first-hit index, and the continuous
+          minimum distance never exceeds the reference's per-trial minimum;
+      (2) on trajectories WRITTEN BY THE UNMODIFIED Drone.cpp (golden pair*_traj) and on oracle trajectories (bit-equal
+          to the reference's, test above) an independent numpy evaluation of "both tracks interpolated linearly" --
+          closed form in longdouble, and brute force on 4097 points per segment -- gives the oracle's minimum distance
+          and first-conflict time, for the reference's radius and for one that makes most trials conflicts."""
+    om = type(oracle.model)()
+    oracle.L.orc_default_model(om)
+    wide = type(oracle.model)()
+    oracle.L.orc_default_model(wide)
+    wide.aircraft_radius = 60.0
+    n_conf = n_traj = 0
+    for p, (a, j) in enumerate(golden["pairs"]):
+        t = tracks[a]
+        draws = golden["pair%d_draws" % p]
+        hit_s, first_s, ftime, mind_s = oracle.run_trials_substep(t, ring1[j], draws)
+        ref_hit, ref_first, ref_min = golden["pair%d_hit" % p] == 1, golden["pair%d_first_hit" % p], golden["pair%d_min_dist" % p]
+        # (1) reduces to the reference at the samples
+        assert hit_s[ref_hit].all()
+        assert (mind_s <= ref_min * (1 + 1e-12) + 1e-9).all()
+        assert ((first_s[ref_hit] == ref_first[ref_hit]) | (first_s[ref_hit] == ref_first[ref_hit] - 1)).all()
+        assert (ftime[ref_hit] <= ref_first[ref_hit]).all() and (ftime[ref_hit] >= first_s[ref_hit]).all()
+        assert (first_s[hit_s == 0] == -1).all() and (ftime[hit_s == 0] == -1).all()
+        # (2a) the reference's own trajectories
+        pos = {int(tr): i for i, tr in enumerate(golden["pair%d_trial" % p])}
+        cases = [(golden["pair%d_traj" % p][s], draws[pos[int(tr)]]) for s, tr in enumerate(golden["pair%d_traj_trial" % p])]
+        # (2b) more geometry: oracle trajectories of the first 25 draws
+        cases += [(np.stack(oracle.trajectory(t, ring1[j], d)), d) for d in draws[:25]]
+        for traj, d in cases:
+            one = np.array([d], dtype=draws.dtype)
+            for model in (om, wide):
+                radius = model.aircraft_radius + model.drone_radius
+                h, f, ft, md = oracle.run_trials_substep(t, ring1[j], one, model=model)
+                want_min, want_time, brute_min, step = _substep_independent(traj, t, radius)
+                assert abs(md[0] - want_min) <= 1e-9 * max(1.0, want_min)
+                assert want_min - 1e-9 <= brute_min <= want_min + step / 4096
+                knife = abs(want_min - radius) < 1e-6
+                if not knife:
+                    assert bool(h[0]) == (want_min < radius)
+                    if h[0]:
+                        assert abs(ft[0] - want_time) <= 1e-6 and f[0] == int(np.floor(ft[0] if ft[0] < len(t["x"]) - 1 else ft[0] - 1e-12))
+                        n_conf += 1
+                n_traj += 1
+    assert n_traj > 500 and n_conf > 100
