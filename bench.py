@@ -628,6 +628,25 @@ def engine_arm(args):
         "trials_in_cleared_pairs_fraction": rc_culled_trials / max(1.0, rc_trials),
         "e2e": {"value": rc_e2e_tests / rc_e2e_secs, "ms_per_step": 1e3 * rc_e2e_secs / args.steps},
     }
+    # ---- the same workload in the sub-step mode (DCRP_FLAG_SUBSTEP, the interpolated-separation extension of SURVEY
+    # 8(f3): a test is then one (trial, segment) closest approach); slab-first screen and, for comparison, the 2-D screen
+    sub = {}
+    for name, fl in (("slab_first", capi.FLAG_SUBSTEP), ("screen_2d", capi.FLAG_SUBSTEP | capi.FLAG_SCREEN_2D)):
+        ms, tests_s, hits_s, surv = 0.0, 0, 0, 0
+        for s in range(args.warmup + args.steps):
+            r = eng.fetch(eng.run_async(seed=SEED, trial_begin=(s * world + rank) * n, trial_count=n, precision=capi.MIXED,
+                                        flags=fl, stream=sh))
+            if s >= args.warmup:
+                ms += r.stats["ms_device_total"]; tests_s += r.stats["tests_evaluated"]; hits_s += r.stats["hits"]
+                surv += r.stats["slab_survivors"]
+            capi.flush_l2(local, sh)
+        ms = allmax([ms])[0]
+        tests_s, hits_s, surv = allsum([float(tests_s), float(hits_s), float(surv)])
+        sub[name] = {"ms_per_step": ms / args.steps, "tests_per_s": tests_s / (ms * 1e-3), "hits": int(hits_s),
+                     "slab_survivors_fraction": surv / (world * args.steps * 99.0 * n)}
+    assert sub["slab_first"]["hits"] == sub["screen_2d"]["hits"]
+    substep = {"flag": "DCRP_FLAG_SUBSTEP (extension: drone and aircraft interpolated between samples; results equal the "
+                       "fp64 kernel's, tests/test_gpu_substep.py)", **sub}
     if comm_info is not None:
         comm_info = eng.comm_info()
 
@@ -716,6 +735,7 @@ def engine_arm(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "reach_cull": reach_cull,
+        "substep": substep,
         "strong_scaling": strong,
         "collective": comm_info,
         "device": info,

@@ -54,6 +54,7 @@ struct TrackDev {
     float    thr2_l1_sub;// sub-step mode, level-1 threshold: (R + margin + (max |dA_xy| + v_straight)/2)^2
     float    thr2_l2_sub;// sub-step mode, level-2 threshold: (R + margin)^2 + the fp32 error of the segment closest approach
     float    dir0x, dir0y;// default slab direction of this track's pairs: the aircraft's main direction of travel (unit)
+    float    thr_slab_sub;// sub-step mode, slab threshold (NOT squared): R + slab margin + (max |dA_xy| + vmax)/2
 };
 
 struct ScenarioDev {

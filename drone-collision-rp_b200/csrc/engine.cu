@@ -143,9 +143,10 @@ struct dcrp_engine {
     DevBuf d_reach, d_alive, d_reach_tot;
     DevBuf d_slab_dir;             // k_screen3: slab direction per pair
     bool slab_ready = false;       // k_slab_axis has run for the current scenario
+    double sub_survivors = -1.0;   // slab survivors per trial of the last sub-step run through k_screen3 on this scenario (-1: none yet)
     uint32_t runs_on_scenario = 0; // dcrp_run_async calls since the last upload
-    size_t s3_smem[2] = {0, 0};    // [0] k_screen3<2>, [1] k_screen3<4>
-    int s3_occ[2] = {0, 0};
+    size_t s3_smem[4] = {0, 0, 0, 0};    // [0] k_screen3<2>, [1] k_screen3<4>, [2], [3] their sub-step builds
+    int s3_occ[4] = {0, 0, 0, 0};
     bool prepare_timed = false;
 
     // run
@@ -436,6 +437,11 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     const double margin = 0.02 + 1.7321 * (0.5 * screen_tile + 4.0) * ulp +
                           (double)vl_max * vmax * std::ldexp(1.0, -21);
     s.thr2_screen = std::nextafterf((float)((s.radius + margin) * (s.radius + margin)), INFINITY);
+    // 1-D slab level (screen3.cu): the same error sources, on coordinates projected on a unit vector
+    // (magnitudes up to sqrt(2) x extent, three more roundings for the projections), re-based every 128
+    const double ulp_p = (double)ulp32_of(1.4143 * extent);
+    const double margin_slab = 0.02 + (0.5 * 128.0 + 12.0) * ulp_p + (double)vl_max * vmax * std::ldexp(1.0, -20);
+    s.thr_slab = std::nextafterf((float)(s.radius + margin_slab), INFINITY);
     for (int a = 0; a < n_tracks; ++a) {          // sub-step mode: per-track level-1 radius
         const dcrp_track& t = tracks[a];
         double amax = 0.0, amax3 = 0.0;
@@ -449,6 +455,9 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         const double rr = s.radius + margin + 0.5 * (amax + vmax) * (1.0 + 1e-6);
         TrackDev& d = e->h_tracks[(size_t)a];
         d.thr2_l1_sub = std::nextafterf((float)(rr * rr), INFINITY);
+        // the slab level likewise: |n . D| at one END of a segment in conflict is below R + half the projected
+        // relative step, and a projection is no longer than the step
+        d.thr_slab_sub = std::nextafterf((float)(s.radius + margin_slab + 0.5 * (amax + vmax) * (1.0 + 1e-6)), INFINITY);
         // level 2 evaluates c + t(2b + ta) in fp32 with |c|, |b|, |a| up to (R + E)^2, E the 3-D relative step
         // (<= aircraft step + sqrt(2) vmax): ~10 roundings of 2^-24 each, bounded by 4e-6 (R + E)^2.  Nothing for
         // real tracks (E ~ 100 m: 0.05 m^2), decisive for sparse or teleporting ones.
@@ -457,12 +466,6 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
                                                 4e-6 * (s.radius + E) * (s.radius + E)), INFINITY);
     }
     s.thr2_fp32 = (float)(s.radius * s.radius);
-    {   // 1-D slab level (screen3.cu): the same error sources, on coordinates projected on a unit vector
-        // (magnitudes up to sqrt(2) x extent, three more roundings for the projections), re-based every 128
-        const double ulp_p = (double)ulp32_of(1.4143 * extent);
-        const double margin_slab = 0.02 + (0.5 * 128.0 + 12.0) * ulp_p + (double)vl_max * vmax * std::ldexp(1.0, -20);
-        s.thr_slab = std::nextafterf((float)(s.radius + margin_slab), INFINITY);
-    }
     s.v_straight_f = (float)model->v_straight;
     s.coef_f = (float)(2.0 * (model->v_straight - model->v_ascend) / DCRP_PI);
     s.bucket_shift = 0;
@@ -554,6 +557,7 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
     CU(cudaGetLastError());
     e->reach_ready = false;        // the reach table is built by the first run that asks for it
     e->slab_ready = false;         // likewise the slab directions of k_screen3
+    e->sub_survivors = -1.0;
     e->runs_on_scenario = 0;
     CU(cudaEventRecord(e->ev_b, st));   // no host sync here: runs queue behind it on the same stream
     e->prepare_timed = false;
@@ -693,9 +697,13 @@ static int launch_screen3(dcrp_engine* e, const RunDev& r, uint32_t chunks_per_p
     // against 1.267 / 1.272 ms; one CTA of 172 registers 0.163 / 1.310).  k_screen3<4>: 64 registers, 8 warps per
     // sub-partition, for long launches over MANY tracks (the 600-flight day on the 1 km ring: a tenth of the trials
     // go through the re-scan and its latency-bound rare path; 20.3 against 21.1 ms).
-    const int wide = e->sd.n_tracks > 1 &&
-                     (uint64_t)n_items >= (uint64_t)48 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
-    const void* kern = wide ? (const void*)k_screen3<4> : (const void*)k_screen3<2>;
+    const int wide0 = e->sd.n_tracks > 1 &&
+                      (uint64_t)n_items >= (uint64_t)48 * e->prop.multiProcessorCount * 4 * (S3_BLOCK / 32) ? 1 : 0;
+    // (the sub-step builds: same kernel, thresholds widened by half a relative step and the segment forms of levels 2 / 3)
+    static const void* const kerns[4] = {(const void*)k_screen3<2, false>, (const void*)k_screen3<4, false>,
+                                         (const void*)k_screen3<2, true>, (const void*)k_screen3<4, true>};
+    const int wide = wide0 + (r.substep ? 2 : 0);
+    const void* kern = kerns[wide];
     int vl_pad = (e->sd.n_steps_max + 3) & ~3;
     int tk_pad = (e->sd.t_max + 3) & ~3;
     const size_t smem = s3_warp_smem(vl_pad, tk_pad) * (S3_BLOCK / 32);
@@ -843,9 +851,14 @@ extern "C" int dcrp_run_async(dcrp_engine* e, const dcrp_run* run, void* stream,
 
     // slices keep the item count of one launch below 2^30
     const bool exact = (run->precision == DCRP_PRECISION_FP64);
-    // the slab-first screen serves plain MIXED runs on tracks its per-warp tables hold; everything else
-    // (replay tables, reach culling, sub-step mode, fp32 decisions, long tracks) goes through k_screen2
-    const bool use3 = run->precision == DCRP_PRECISION_MIXED && !r.replay && !r.cull && !r.substep &&
+    // the slab-first screen serves MIXED runs (sample and sub-step mode) on tracks its per-warp tables hold; everything
+    // else (replay tables, reach culling, fp32 decisions, long tracks) goes through k_screen2
+    // Sub-step mode widens the slab by half a relative step (tens of metres): around a 5 km ring it still clears 90 % of
+    // the trials (0.32 against 0.42 ms per 1.0e7 trials), around a 1 km ring 60 % -- there the 2-D screen alone is the
+    // faster one (0.74 against 0.81 ms).  Same answers either way, so the choice follows what the previous sub-step run
+    // on this scenario saw (dcrp_fetch keeps the survivor fraction).
+    const bool sub_prefers_2d = r.substep && e->sub_survivors > 0.25;
+    const bool use3 = run->precision == DCRP_PRECISION_MIXED && !r.replay && !r.cull && !sub_prefers_2d &&
                       !(run->flags & DCRP_FLAG_SCREEN_2D) && s.n_steps_max <= S3_MAX_VL && s.t_max <= S3_MAX_T;
     e->run_screen3 = use3;
     const uint64_t per_item = exact ? (uint64_t)EXB : (use3 ? (uint64_t)S3_CHW : screen_chunk());
@@ -1116,6 +1129,8 @@ extern "C" int dcrp_fetch(dcrp_engine* e, dcrp_result* res)
     o.candidates = stats[ST_CANDIDATES];
     o.level2 = stats[ST_LEVEL2];
     o.slab_survivors = stats[ST_SLAB_SURVIVORS];
+    if (!e->allpairs_run && e->run_screen3 && (e->run.flags & DCRP_FLAG_SUBSTEP) && o.trials >= 100000)
+        e->sub_survivors = (double)o.slab_survivors / (double)o.trials;
     o.hits = stats[ST_HITS];
     o.kernel_launches = e->launches_this_run;
     o.status = e->run_status;

@@ -723,6 +723,33 @@ __device__ __forceinline__ float min3d_seg_fp32(const ScenarioDev& s, const Trac
     return mn;
 }
 
+// The same minimum by a whole warp on ONE trial (u is warp-uniform): lane l takes the segments that END at the indices
+// t1st + l + 32 k.  Both ends of a segment go through the expressions of min3d_seg_fp32 (there the first end is carried
+// over from the previous iteration: the same fused expression at the same index, hence the same bits), and a minimum
+// does not depend on the order.
+__device__ __forceinline__ float min3d_seg_fp32_warp(const ScenarioDev& s, const TrackDev& t, const Setup32& u, int lane)
+{
+    const float4* __restrict__ g = s.trk32 + (size_t)t.off;
+    float mn = 3.0e38f;
+    for (int i = u.t1st + lane; i < t.n_steps; i += 32) {
+        const float4 q = __ldg(&g[i - 1]), p = __ldg(&g[i]);
+        const float x0 = fmaf(q.w, u.ray.sx, u.ray.bx) + q.x, y0 = fmaf(q.w, u.ray.sy, u.ray.by) + q.y,
+                    z0 = fmaf(q.w, u.ray.sz, u.ray.bz) + q.z;
+        const float x1 = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x, y1 = fmaf(p.w, u.ray.sy, u.ray.by) + p.y,
+                    z1 = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
+        const float ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
+        const float a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+        const float b = fmaf(z0, ez, fmaf(y0, ey, x0 * ex));
+        const float c = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
+        const float tt = a > 0.f ? fminf(fmaxf(__fdividef(-b, a), 0.f), 1.f) : 0.f;
+        const float dmin = fmaf(tt, fmaf(tt, a, 2.f * b), c);
+        mn = fminf(mn, fminf(dmin, c));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    return mn;
+}
+
 // =========================================================================
 // k_screen2: the fp32 packed screen, balanced rounds
 // =========================================================================

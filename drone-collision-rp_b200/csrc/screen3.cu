@@ -39,6 +39,7 @@ constexpr int S3_MAX_VL = 512;            // longest track the per-warp projecte
 constexpr int S3_MAX_T = 128;             // largest takeoff_t the per-warp kink tables hold
 constexpr int S3_REBASE = 128;            // exact re-base of the running position every so many indices
 constexpr int S3_DIRS = 16;               // candidate slab directions k*pi/16
+constexpr int S3_L2_SERIAL = 6;           // sub-step mode: up to this many flagged trials of a re-scan round are taken one at a time by the warp
 
 static_assert(S3_CHW <= 4096, "local trial index is packed in 12 bits");
 
@@ -128,13 +129,26 @@ __global__ void __launch_bounds__(S3_AXIS_BLOCK) k_slab_axis(const ScenarioDev s
     }
 }
 
+// First stage-1 conflict of a pair as "every trial whose kink index is >= this must be confirmed": a sample index in
+// sample mode, (segment index + 1) in sub-step mode (as in k_screen2).
+template <bool SUB>
+__device__ __forceinline__ int s3_s1_first(const ScenarioDev& s, int pair)
+{
+    if (!SUB) return __ldg(&s.s1_first_hit[pair]);
+    const int sg = __ldg(&s.s1sub_first_seg[pair]);
+    return sg == INT_MAX ? INT_MAX : sg + 1;
+}
+
 // 2-D level-1 re-scan of n <= S3_RESCAN queued survivors of track a (4 per lane as two packed pairs);
 // the draws are regenerated from the trial id (nothing but (item, local) was kept), the track is the warp's
 // own shared-memory tile (the queue is drained before the tile is reloaded for another track).
 // NP packed pairs per lane: 2 for a full round of S3_RESCAN survivors, 1 for the up to 64 left over when a warp
 // changes track or ends (on the 5 km ring a warp queues a dozen survivors per launch: that one call is its whole
 // re-scan work, and it stands at the very end of the launch).
-template <int NP>
+// SUB (DCRP_FLAG_SUBSTEP, the interpolated-separation extension): the scan also takes the kink sample (the first end
+// of the first stage-2 segment), level 1b and level 2 use the per-track thresholds widened by half a relative step
+// (engine.cu), level 2 is the fp32 closest approach per segment, level 3 (exact_any_warp) follows r.substep.
+template <int NP, bool SUB>
 __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
                                           uint32_t chunks_per_pair, const float2* __restrict__ tile)
 {
@@ -165,7 +179,7 @@ __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r,
             const int t1st = draw_t1st(w.x, takeoff_t);
             const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
             const Fast32 u = setup_fast32(s, ts, s.kink + (size_t)pair * s.t_max, s.p1f + (size_t)j * s.t_max,
-                                          __ldg(&s.s1_first_hit[pair]), q);
+                                          s3_s1_first<SUB>(s, pair), q);
             bx = u.bx; by = u.by; sx = u.sx; sy = u.sy;
             fmask |= u.force ? (1u << m) : 0u;
             tmin = min(tmin, t1st);
@@ -178,7 +192,7 @@ __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r,
         BX[p] = pk2(bxs[2 * p], bxs[2 * p + 1]); BY[p] = pk2(bys[2 * p], bys[2 * p + 1]);
         SX[p] = pk2(sxs[2 * p], sxs[2 * p + 1]); SY[p] = pk2(sys[2 * p], sys[2 * p + 1]);
     }
-    const int imin = __reduce_min_sync(0xffffffffu, tmin);
+    const int imin = __reduce_min_sync(0xffffffffu, tmin) - (SUB ? 1 : 0);
     if (imin < VL) acc_is += (uint32_t)(VL - imin) * (uint32_t)TR;
     float mn[TR];
 #pragma unroll
@@ -194,8 +208,9 @@ __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r,
             scan_tile_xy<NP>(tile + t0, t0, lo, hi, PX, PY, SX, SY, mn);
         }
     }
+    const float thr1 = SUB ? __ldg(&tk->thr2_l1_sub) : s.thr2_screen;
 #pragma unroll
-    for (int m = 0; m < TR; ++m) if (mn[m] < s.thr2_screen) fmask |= 1u << m;
+    for (int m = 0; m < TR; ++m) if (mn[m] < thr1) fmask |= 1u << m;
     // ---- rare: LEVEL 2 (3-D fp32, fused form) of the flagged trials, then LEVEL 3 (fp64) of what survives -- one
     // trial at a time by the WHOLE warp (every lane re-derives the trial from its queue entry, the indices are dealt
     // out over the lanes: min3d_fp32_warp, exact_any_warp).  Same decisions and bits as one lane per trial; what
@@ -206,6 +221,38 @@ __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r,
     uint32_t hits = 0;
     if (__any_sync(0xffffffffu, fmask != 0u)) {
         const TrackDev t = *tk;
+        // Sub-step mode: the level-1 radius is wider by half a relative step (tens of metres), so next to the flight
+        // path a round of survivors can hold dozens of flagged trials, and taking those one at a time -- ~1500 cycles of
+        // latency each -- made single 256-trial items last tens of microseconds (the tail of the launch).  A round with
+        // more than S3_L2_SERIAL flagged trials therefore runs level 2 with one LANE per trial (min3d_seg_fp32, as
+        // k_screen2 does), and only what level 2 passes goes through the warp-wide level 3 below.
+        bool l2_done = false;
+        if (SUB) {
+            int nflag = 0;
+#pragma unroll
+            for (int m = 0; m < TR; ++m) nflag += __popc(__ballot_sync(0xffffffffu, ((fmask >> m) & 1u) && m * 32 + lane < n));
+            if (nflag > S3_L2_SERIAL) {
+#pragma unroll 1
+                for (int m = 0; m < TR; ++m) {
+                    if (!((fmask >> m) & 1u) || m * 32 + lane >= n) continue;
+                    const uint2 e = list[m * 32 + lane];
+                    const int pair = (int)r.div_chunks.div(e.x);
+                    const uint32_t c = e.x - (uint32_t)pair * chunks_per_pair;
+                    const int j = pair - a * s.n_drones;
+                    const uint64_t trial = r.trial_begin + r.slice_first + (uint64_t)c * S3_CHW + e.y;
+                    const U4 w = philox4x32_10_rk((uint32_t)trial, (uint32_t)(trial >> 32), r.drone_base + (uint32_t)j,
+                                                  r.track_base + (uint32_t)a, r.rk);
+                    const int t1st = draw_t1st(w.x, takeoff_t);
+                    const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
+                    const Setup32 u = setup_trial32(s, r, t, pair, j, s3_s1_first<SUB>(s, pair), 0, q);
+                    const bool cand = u.force || min3d_seg_fp32(s, t, u) < t.thr2_l2_sub;
+                    ++npass;
+                    if (cand) ++ncand; else fmask &= ~(1u << m);
+                }
+                __syncwarp();
+                l2_done = true;
+            }
+        }
 #pragma unroll 1
         for (int m = 0; m < TR; ++m) {
             uint32_t todo = __ballot_sync(0xffffffffu, ((fmask >> m) & 1u) && m * 32 + lane < n);
@@ -221,9 +268,13 @@ __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r,
                                               r.track_base + (uint32_t)a, r.rk);
                 const int t1st = draw_t1st(w.x, takeoff_t);
                 const uint4 q = make_uint4(w.y, w.z, w.w, e.y | ((uint32_t)t1st << 12));
-                const Setup32 u = setup_trial32(s, r, t, pair, j, __ldg(&s.s1_first_hit[pair]), 0, q);
-                const bool cand = u.force || min3d_fp32_warp(s, t, u, lane) < s.thr2_screen;
-                if (lane == 0) { ++npass; ncand += cand ? 1u : 0u; }
+                bool cand = true;                                         // (level 2 already done lane by lane)
+                if (!(SUB && l2_done)) {
+                    const Setup32 u = setup_trial32(s, r, t, pair, j, s3_s1_first<SUB>(s, pair), 0, q);
+                    cand = u.force || (SUB ? min3d_seg_fp32_warp(s, t, u, lane) < t.thr2_l2_sub
+                                           : min3d_fp32_warp(s, t, u, lane) < s.thr2_screen);
+                    if (lane == 0) { ++npass; ncand += cand ? 1u : 0u; }
+                }
                 if (cand) {
                     const Draw d = make_draw(r.seed, trial, r.drone_base + (uint32_t)j, r.track_base + (uint32_t)a,
                                              t.takeoff_t, t.box);
@@ -247,11 +298,12 @@ __device__ __noinline__ void s3_rescan_np(const ScenarioDev& s, const RunDev& r,
     }
 }
 
+template <bool SUB>
 __device__ __forceinline__ void s3_rescan(const ScenarioDev& s, const RunDev& r, const uint2* list, int n, int a,
                                           uint32_t chunks_per_pair, const float2* __restrict__ tile)
 {
-    if (n <= 64) s3_rescan_np<1>(s, r, list, n, a, chunks_per_pair, tile);
-    else         s3_rescan_np<2>(s, r, list, n, a, chunks_per_pair, tile);
+    if (n <= 64) s3_rescan_np<1, SUB>(s, r, list, n, a, chunks_per_pair, tile);
+    else         s3_rescan_np<2, SUB>(s, r, list, n, a, chunks_per_pair, tile);
 }
 
 // griddepcontrol.wait: returns once the grid this one was programmatically launched behind has completed and its
@@ -285,7 +337,7 @@ __device__ __forceinline__ unsigned long long tl_now()
 #define TL_COUNT(n) do {} while (0)
 #endif
 
-template <int MINB>
+template <int MINB, bool SUB>
 __global__ void __launch_bounds__(S3_BLOCK, MINB)
 k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev r, uint32_t chunks_per_pair, uint32_t n_items, int vl_pad, int tk_pad,
           uint32_t first_block, const __grid_constant__ S3Sched sch)
@@ -353,7 +405,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         uint32_t phase = 0;
         if (a != list_track) {                    // (once per run for a one-track scenario)
             // queued survivors share one track: drain them before it changes
-            if (list_n) { griddep_wait(); s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile); list_n = 0; }
+            if (list_n) { griddep_wait(); s3_rescan<SUB>(s, r, list, list_n, list_track, chunks_per_pair, tile); list_n = 0; }
             list_track = a;
             // the track's samples come in by ONE 1-D TMA bulk copy (waited for below, behind the loads that do not
             // need them); the per-pair projection on the pair's direction then reads shared memory, not L2
@@ -369,7 +421,8 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             tile_wait = true;
         }
         const uint32_t n_valid = (uint32_t)min((uint64_t)S3_CHW, r.slice_count - (uint64_t)c * S3_CHW);
-        const int s1_first = __ldg(&s.s1_first_hit[pair]);
+        const int s1_first = s3_s1_first<SUB>(s, pair);
+        const float thr_slab = SUB ? __ldg(&tk->thr_slab_sub) : s.thr_slab;
         const float2 nd = __ldg(&s.slab_dir[pair]);
         TrackScale ts;
         ts.wx32 = __ldg(&tk->wx32); ts.wy32 = __ldg(&tk->wy32); ts.wz32 = __ldg(&tk->wz32); ts.z0rel = __ldg(&tk->z0rel);
@@ -397,7 +450,8 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             const int vlr = (VL + 3) & ~3;
             for (int i = lane; i < vlr; i += 32) {
                 float v = 1e15f;
-                if (i >= 1 && i < VL) { const float2 p = tile[i]; v = fmaf(nd.x, p.x, nd.y * p.y); }
+                // (index 0 is never a stage-2 sample; in sub-step mode it can be the first end of the first segment)
+                if (i >= (SUB ? 0 : 1) && i < VL) { const float2 p = tile[i]; v = fmaf(nd.x, p.x, nd.y * p.y); }
                 DCRP_ASSERT(i < vl_pad);
                 tabT[i] = v;
             }
@@ -483,9 +537,9 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
         for (int m = 1; m + 1 < S3_TL; m += 2) mall = fminf(fminf(mall, mn[m]), mn[m + 1]);
         mall = fminf(mall, mn[S3_TL - 1]);
         uint32_t pass = fmask;
-        if (mall < s.thr_slab) {
+        if (mall < thr_slab) {
 #pragma unroll
-            for (int m = 0; m < S3_TL; ++m) if (mn[m] < s.thr_slab) pass |= 1u << m;
+            for (int m = 0; m < S3_TL; ++m) if (mn[m] < thr_slab) pass |= 1u << m;
         }
         if (__any_sync(0xffffffffu, pass != 0u)) {
 #pragma unroll
@@ -501,7 +555,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
             while (list_n >= S3_RESCAN) {
                 griddep_wait();
                 list_n -= S3_RESCAN;
-                s3_rescan(s, r, list + list_n, S3_RESCAN, list_track, chunks_per_pair, tile);
+                s3_rescan<SUB>(s, r, list + list_n, S3_RESCAN, list_track, chunks_per_pair, tile);
                 __syncwarp();
             }
         }
@@ -523,7 +577,7 @@ k_screen3(const __grid_constant__ ScenarioDev s, const __grid_constant__ RunDev 
     }
     TL_MARK(3);
     griddep_wait();
-    if (list_n) s3_rescan(s, r, list, list_n, list_track, chunks_per_pair, tile);
+    if (list_n) s3_rescan<SUB>(s, r, list, list_n, list_track, chunks_per_pair, tile);
     TL_MARK(4);
     TL_COUNT(tl_items);
 #ifdef DCRP_TIMELINE

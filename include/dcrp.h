@@ -188,7 +188,8 @@ typedef struct dcrp_stats {
                                   trial for the cleared pairs; never part of tests_evaluated             */
     uint64_t slab_survivors;   /* MIXED runs through the slab-first screen: trials the 1-D slab level could not
                                   clear and queued for the 2-D level-1 re-scan (0 when every trial goes through
-                                  the 2-D scan: DCRP_FLAG_SCREEN_2D, replay, culling, sub-step, long tracks)  */
+                                  the 2-D scan: DCRP_FLAG_SCREEN_2D, replay, culling, long tracks, and sub-step
+                                  runs on a scenario whose previous sub-step run kept > 25 % survivors)      */
 } dcrp_stats;
 
 /* Result buffers (host, caller-owned).  counts is required; the rest optional. */

@@ -94,10 +94,15 @@ def test_random_shapes_mixed_and_cull_equal_fp64(engine, tracks, ring1, ring5, c
             engine.simulate(trks, drones, precision=capi.FP64, flags=capi.FLAG_SUBSTEP, **kw)
         return
     sref = engine.simulate(trks, drones, precision=capi.FP64, flags=capi.FLAG_SUBSTEP, **kw)
-    smix = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_SUBSTEP, **kw)
+    smix = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_SUBSTEP, **kw)       # slab-first (k_screen3)
+    smix2d = engine.simulate(trks, drones, precision=capi.MIXED, flags=capi.FLAG_SUBSTEP | capi.FLAG_SCREEN_2D, **kw)
+    assert smix2d.stats["slab_survivors"] == 0
     if not sref.overflow:
-        _same(sref, smix, "substep")
-        assert np.array_equal(sref.records["first_time"], smix.records["first_time"])
+        for name, got in (("substep", smix), ("substep, 2-D screen", smix2d)):
+            _same(sref, got, name)
+            assert np.array_equal(sref.records["first_time"], got.records["first_time"]), name
+        if eligible:
+            assert smix.stats["slab_survivors"] >= smix.stats["level2"] >= smix.stats["candidates"] >= sref.hits
     if min(t["n_steps"] for t in trks) >= 2:         # a 1-sample track has no segment to interpolate on
         assert sref.hits >= ref.hits
 

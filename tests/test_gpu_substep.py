@@ -46,6 +46,14 @@ def test_substep_mixed_equals_fp64(engine, tracks, ring1, ring5):
                               b.records[["track", "drone", "trial", "first_hit"]])
         assert np.array_equal(a.records["first_time"], b.records["first_time"])
         assert np.array_equal(a.records["min_dist"], b.records["min_dist"])
+        # the same through the 2-D screen (k_screen2): both screens serve the sub-step mode
+        b2 = engine.simulate(trks, ring, seed=9, trial_count=n, precision=capi.MIXED,
+                             flags=capi.FLAG_SUBSTEP | capi.FLAG_SCREEN_2D)
+        assert np.array_equal(a.counts, b2.counts) and np.array_equal(a.records["first_time"], b2.records["first_time"])
+        assert np.array_equal(a.records[["track", "drone", "trial", "first_hit"]],
+                              b2.records[["track", "drone", "trial", "first_hit"]])
+        assert b.stats["slab_survivors"] > 0 and b2.stats["slab_survivors"] == 0
+        assert b.stats["slab_survivors"] >= b.stats["level2"] >= b.stats["candidates"] >= b.hits
         s = engine.simulate(trks, ring, seed=9, trial_count=n, precision=capi.MIXED)
         assert b.hits >= s.hits
         assert b.stats["level2"] > s.stats["level2"]          # the wider level-1 radius passes more trials on
