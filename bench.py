@@ -699,6 +699,9 @@ def engine_arm(args):
         "sustained": {"achieved": sustain["tests_per_s"] * FLOP_PER_TEST * 1e-12,
                       "frac": sustain["tests_per_s"] * FLOP_PER_TEST * 1e-12 / peak, **sustain},
         "hbm": {"note": "track 3.3 KB + ring tables per launch; records 64 B per hit: not HBM-bound",
+                "achieved_gbs": (traffic / (k_ms * 1e-3) * 1e-9) if traffic else None,
+                "achieved_is": "DRAM bytes per launch (ncu, roofline.traffic) / the live kernel time: trajectory tiles, tables "
+                               "and collision records together",
                 "peak_gbs": json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0},
     }
