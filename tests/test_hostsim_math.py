@@ -131,3 +131,42 @@ def test_slab_level_is_conservative_and_within_its_margin(hostsim, golden, track
             assert (got[hit2] < 3.69 + 2e-2).all(), (p, k)             # reference hits are always flagged
     print("worst |fp32 slab - fp64| = %.2e m" % worst)
     assert worst < 0.08
+
+
+def test_substep_slab_threshold_is_conservative(hostsim, oracle, golden, tracks, ring1):
+    """Level 1a of k_screen3<., SUB> (DCRP_FLAG_SUBSTEP): on a segment in conflict |n . D| at ONE of its two ends is
+    below R + half the projected relative step, so the engine compares the slab minimum -- taken over every sample,
+    index 0 included -- against thr_slab_sub = R + slab margin + (max aircraft step + vmax) / 2 (engine.cu).  Checked
+    against the oracle's sub-step decisions (stage-2 conflicts; a stage-1 segment in conflict forces the trial) for
+    the reference's radius and for a 40 m one, on 16 directions: every conflict is flagged."""
+    origin = (np.floor(0.5 * (671819.02 + 678600.0)), np.floor(0.5 * (5704300.0 + 5706300.0)), 250.0)
+    n_conf = 0
+    for p, (a, j) in enumerate(golden["pairs"][:6]):
+        t = tracks[a]
+        draws = golden["pair%d_draws" % p][:3000]
+        amax = np.hypot(np.diff(t["x"]), np.diff(t["y"])).max()
+        x0, y0, h = ring1[j]
+        last = draws["t1st"].astype(np.int64) - 1
+        # the ray at index 0 in fp64 (the fp32 scan of hostsim.slab starts at index 1, the device's sub-step build at 0)
+        kx = x0 + np.cumsum(np.r_[0.0, np.full(t["takeoff_t"] - 1, np.sin(h) * 19.0)])[last]
+        ky = y0 + np.cumsum(np.r_[0.0, np.full(t["takeoff_t"] - 1, np.cos(h) * 19.0)])[last]
+        dl, db = draws["tx"] - kx, draws["ty"] - ky
+        m = np.hypot(dl, db)
+        vf = 19.0 - (2.0 * (19.0 - 8.0) / np.pi) * np.arctan(np.abs(draws["tz"] - 100.0) / m)
+        d0x = kx - last * (dl / m * vf) - t["x"][0]
+        d0y = ky - last * (db / m * vf) - t["y"][0]
+        for r_ac in (3.5, 40.0):
+            om = type(oracle.model)()
+            oracle.L.orc_default_model(om)
+            om.aircraft_radius = r_ac
+            radius = r_ac + 0.19
+            hit, first_seg, _, _ = oracle.run_trials_substep(t, ring1[j], draws, model=om)
+            stage2 = (hit == 1) & (first_seg >= last)
+            thr = radius + 0.10 + 0.5 * (amax + 19.0) * (1 + 1e-6)
+            for k in range(16):
+                n = (np.cos(np.pi * k / 16), np.sin(np.pi * k / 16))
+                got = hostsim.slab(t, ring1[j], draws, origin, n).astype(np.float64)
+                got = np.minimum(got, np.abs(n[0] * d0x + n[1] * d0y))
+                assert (got[stage2] < thr).all(), (p, r_ac, k, got[stage2].max(), thr)
+            n_conf += int(stage2.sum())
+    assert n_conf > 200
