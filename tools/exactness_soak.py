@@ -22,11 +22,17 @@ for name, path in (("1km", pk.RING_1KM), ("5km", pk.RING_5KM)):
     for ti in range(len(tracks)):
         a = eng.simulate(tracks[ti:ti + 1], ring, seed=99, trial_count=n, precision=capi.FP64, record_capacity=1 << 19)
         rows = {}
+        sub_ref = None
         for mode, flags in (("mixed", 0), ("mixed2d", capi.FLAG_SCREEN_2D), ("cull", capi.FLAG_REACH_CULL),
-                            ("substep", capi.FLAG_SUBSTEP)):
-            ref = a if mode != "substep" else eng.simulate(tracks[ti:ti + 1], ring, seed=99, trial_count=n // 8,
-                                                           precision=capi.FP64, flags=flags, record_capacity=1 << 20)
-            cnt = n if mode != "substep" else n // 8
+                            ("substep", capi.FLAG_SUBSTEP), ("substep2d", capi.FLAG_SUBSTEP | capi.FLAG_SCREEN_2D)):
+            if mode == "substep2d":
+                ref = sub_ref
+            else:
+                ref = a if mode != "substep" else eng.simulate(tracks[ti:ti + 1], ring, seed=99, trial_count=n // 8,
+                                                               precision=capi.FP64, flags=flags, record_capacity=1 << 20)
+            if mode == "substep":
+                sub_ref = ref
+            cnt = n if not mode.startswith("substep") else n // 8
             b = eng.simulate(tracks[ti:ti + 1], ring, seed=99, trial_count=cnt, precision=capi.MIXED, flags=flags,
                              record_capacity=1 << 20)
             same = bool(np.array_equal(ref.counts, b.counts) and not ref.overflow and not b.overflow and
