@@ -55,6 +55,8 @@ struct TrackDev {
     float    thr2_l2_sub;// sub-step mode, level-2 threshold: (R + margin)^2 + the fp32 error of the segment closest approach
     float    dir0x, dir0y;// default slab direction of this track's pairs: the aircraft's main direction of travel (unit)
     float    thr_slab_sub;// sub-step mode, slab threshold (NOT squared): R + slab margin + (max |dA_xy| + vmax)/2
+    float    thr2_near_sub;// sub-step mode, level 2: a segment whose two ends are both farther than this (squared) cannot
+                          // come within the level-2 radius (ends closer than sqrt(thr2_l2_sub) + half the longest relative step)
 };
 
 struct ScenarioDev {

@@ -464,6 +464,10 @@ extern "C" int dcrp_scenario_upload(dcrp_engine* e, const dcrp_track* tracks, in
         const double E = amax3 + 1.4143 * vmax;
         d.thr2_l2_sub = std::nextafterf((float)((s.radius + margin) * (s.radius + margin) +
                                                 4e-6 * (s.radius + E) * (s.radius + E)), INFINITY);
+        // |D(t)| >= min(|D_0|, |D_1|) - |E| / 2 on a segment: with both ends beyond this the closest approach is not
+        // evaluated (1e-4 relative and 0.05 m for the fp32 rounding of the two squared end distances)
+        const double near = (std::sqrt((double)d.thr2_l2_sub) + 0.5 * E) * (1.0 + 1e-4) + 0.05;
+        d.thr2_near_sub = std::nextafterf((float)(near * near), INFINITY);
     }
     s.thr2_fp32 = (float)(s.radius * s.radius);
     s.v_straight_f = (float)model->v_straight;

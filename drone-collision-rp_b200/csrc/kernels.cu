@@ -706,19 +706,25 @@ __device__ __forceinline__ float min3d_seg_fp32(const ScenarioDev& s, const Trac
     float4 p = __ldg(&g[last]);
     float x0 = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x, y0 = fmaf(p.w, u.ray.sy, u.ray.by) + p.y,
           z0 = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
+    float c = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
+    const float near = t.thr2_near_sub;
     for (int i = u.t1st; i < t.n_steps; ++i) {
         p = __ldg(&g[i]);
         const float x1 = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x, y1 = fmaf(p.w, u.ray.sy, u.ray.by) + p.y,
                     z1 = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
-        const float ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
-        const float a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-        const float b = fmaf(z0, ez, fmaf(y0, ey, x0 * ex));
-        const float c = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
-        const float tt = a > 0.f ? fminf(fmaxf(__fdividef(-b, a), 0.f), 1.f) : 0.f;
-        // the interior minimum c - b^2/a cancels: bound its fp32 error by comparing against both ends too
-        const float dmin = fmaf(tt, fmaf(tt, a, 2.f * b), c);
-        mn = fminf(mn, fminf(dmin, c));
-        x0 = x1; y0 = y1; z0 = z1;
+        const float c1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+        // most of a trial's ~100 segments are kilometres away: with both ends beyond thr2_near_sub the closest approach
+        // cannot reach the level-2 radius (TrackDev) and the value is only ever compared with that radius
+        if (fminf(c, c1) < near) {
+            const float ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
+            const float a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+            const float b = fmaf(z0, ez, fmaf(y0, ey, x0 * ex));
+            const float tt = a > 0.f ? fminf(fmaxf(__fdividef(-b, a), 0.f), 1.f) : 0.f;
+            // the interior minimum c - b^2/a cancels: bound its fp32 error by comparing against both ends too
+            const float dmin = fmaf(tt, fmaf(tt, a, 2.f * b), c);
+            mn = fminf(mn, fminf(dmin, c));
+        }
+        x0 = x1; y0 = y1; z0 = z1; c = c1;
     }
     return mn;
 }
@@ -737,13 +743,16 @@ __device__ __forceinline__ float min3d_seg_fp32_warp(const ScenarioDev& s, const
                     z0 = fmaf(q.w, u.ray.sz, u.ray.bz) + q.z;
         const float x1 = fmaf(p.w, u.ray.sx, u.ray.bx) + p.x, y1 = fmaf(p.w, u.ray.sy, u.ray.by) + p.y,
                     z1 = fmaf(p.w, u.ray.sz, u.ray.bz) + p.z;
-        const float ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
-        const float a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-        const float b = fmaf(z0, ez, fmaf(y0, ey, x0 * ex));
         const float c = fmaf(z0, z0, fmaf(y0, y0, x0 * x0));
-        const float tt = a > 0.f ? fminf(fmaxf(__fdividef(-b, a), 0.f), 1.f) : 0.f;
-        const float dmin = fmaf(tt, fmaf(tt, a, 2.f * b), c);
-        mn = fminf(mn, fminf(dmin, c));
+        const float c1 = fmaf(z1, z1, fmaf(y1, y1, x1 * x1));
+        if (fminf(c, c1) < t.thr2_near_sub) {            // (as in min3d_seg_fp32)
+            const float ex = x1 - x0, ey = y1 - y0, ez = z1 - z0;
+            const float a = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+            const float b = fmaf(z0, ez, fmaf(y0, ey, x0 * ex));
+            const float tt = a > 0.f ? fminf(fmaxf(__fdividef(-b, a), 0.f), 1.f) : 0.f;
+            const float dmin = fmaf(tt, fmaf(tt, a, 2.f * b), c);
+            mn = fminf(mn, fminf(dmin, c));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
