@@ -170,3 +170,33 @@ def test_substep_slab_threshold_is_conservative(hostsim, oracle, golden, tracks,
                 assert (got[stage2] < thr).all(), (p, r_ac, k, got[stage2].max(), thr)
             n_conf += int(stage2.sum())
     assert n_conf > 200
+
+
+def test_substep_level2_far_segment_skip_is_safe(oracle, golden, tracks, ring1):
+    """Level 2 of the sub-step mode (kernels.cu min3d_seg_fp32) skips a segment whose two ends are both farther than
+    thr2_near_sub = ((R + margin) + E / 2)^2 with E = longest 3-D aircraft step + sqrt(2) vmax (engine.cu): on
+    reference-exact trajectories (oracle.trajectory) the relative step of every stage-2 segment is within E, and no
+    skipped segment's closest approach comes within the level-2 radius."""
+    n_skipped = n_near = 0
+    for p, (a, j) in enumerate(golden["pairs"][:6]):
+        t = tracks[a]
+        amax3 = np.sqrt(np.diff(t["x"]) ** 2 + np.diff(t["y"]) ** 2 + np.diff(t["z"]) ** 2).max()
+        E = amax3 + 1.4143 * 19.0
+        for r_ac in (3.5, 60.0):
+            level2_radius = r_ac + 0.19 + 0.10                       # R + margin (+ the 4e-6 (R + E)^2 fp32 term, negligible)
+            near = (level2_radius + 0.5 * E) * (1 + 1e-4) + 0.05
+            for d in golden["pair%d_draws" % p][:150]:
+                x, y, z = oracle.trajectory(t, ring1[j], d)
+                D = np.stack([x - t["x"], y - t["y"], z - t["z"]], axis=1)
+                last = int(d["t1st"]) - 1
+                D0, D1 = D[last:-1], D[last + 1:]
+                Ev = D1 - D0
+                assert np.sqrt((Ev ** 2).sum(1)).max() <= E + 1e-9
+                aa, bb = (Ev ** 2).sum(1), (D0 * Ev).sum(1)
+                tt = np.clip(-bb / np.where(aa > 0, aa, 1.0), 0.0, 1.0)
+                closest = np.sqrt(((D0 + tt[:, None] * Ev) ** 2).sum(1))
+                ends = np.minimum(np.sqrt((D0 ** 2).sum(1)), np.sqrt((D1 ** 2).sum(1)))
+                skipped = ends >= near
+                assert (closest[skipped] >= level2_radius).all()
+                n_skipped += int(skipped.sum()); n_near += int((~skipped).sum())
+    assert n_skipped > 10 * n_near > 0          # even on these near-miss-enriched trials all but a few segments per trial are far
